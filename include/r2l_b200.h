@@ -1,0 +1,54 @@
+/* r2l_b200 — C ABI of the B200-native R2L hot path.
+ *
+ * The reference (snap-research/R2L) has no FFI: its hot path is the Python module
+ * model/nerf_raybased.py executed by stock PyTorch.  Each entry point below replaces the chain of
+ * ATen/cuBLAS launches the cited reference lines produce; the Python shim in r2l_b200/ binds them with
+ * ctypes.  All pointers are DEVICE pointers unless marked "host"; the library never
+ * allocates, never synchronises, and enqueues on the CUDA stream passed as `stream` (a cudaStream_t).
+ * Return value: 0 on success, negative on error; r2l_last_error() gives the message for the calling thread.
+ */
+#ifndef R2L_B200_H_
+#define R2L_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define R2L_NUM_PARAMS 5917187 /* floats in the flat state_dict-ordered parameter buffer */
+
+/* input kinds of r2l_forward */
+#define R2L_INPUT_RAYS 0 /* in0 = rays_o[N,3], in1 = rays_d[N,3]  (PointSampler.sample_train, nerf_raybased.py:114-126) */
+#define R2L_INPUT_PTS 1  /* in0 = pts[N,48]   (output of PointSampler.sample_*, :94-126)                       */
+#define R2L_INPUT_X 2    /* in0 = x[N,1008]   (output of PositionalEmbedder.__call__, :198-208)                 */
+
+const char* r2l_last_error(void);
+int r2l_abi_version(void);
+
+/* Bytes of the packed-weight buffer / of the forward workspace for n_rays. */
+size_t r2l_packed_bytes(void);
+size_t r2l_fwd_workspace_bytes(int64_t n_rays);
+
+/* params[R2L_NUM_PARAMS] fp32 in state_dict order (head.0.weight, head.0.bias, body.k.body.{0,2}.{weight,bias},
+ * tail.0.weight, tail.0.bias; NeRF_v3_2.__init__, nerf_raybased.py:483-537)  ->  bf16 hi/lo tensor-core operand
+ * images + fp32 bias tables in `packed`.  Call again after every parameter update. */
+int r2l_pack_weights(const float* params, void* packed, void* stream);
+
+/* rgb[N,3] = NeRF_v3_2.forward(PositionalEmbedder(PointSampler.sample(...)))   (nerf_raybased.py:539-544)
+ *   z_lo, z_diff : HOST pointers to 16 floats each (only for R2L_INPUT_RAYS): z_vals (t_rand == NULL) or
+ *                  `lower` and `upper - lower` of sample_train's stratified jitter (:118-123)
+ *   t_rand       : device [N,16] uniform numbers or NULL
+ *   workspace    : device scratch of r2l_fwd_workspace_bytes(n_rays) bytes */
+int r2l_forward(int input_kind, const float* in0, const float* in1, const float* t_rand, const float* z_lo,
+                const float* z_diff, const void* packed, float* rgb, void* workspace, size_t workspace_bytes,
+                int64_t n_rays, void* stream);
+
+/* Debug / test hook: C[128,256] = A[128,256] * W_l^T through one tcgen05 layer step, l = body layer 0..85. */
+int r2l_selftest_layer(const float* A, const void* packed, int layer, float* C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* R2L_B200_H_ */

@@ -1,0 +1,65 @@
+"""ctypes binding of libr2l_b200.so (the C ABI declared in include/r2l_b200.h).
+
+The library is built in-tree by `make -C r2l_b200/csrc` (see __graft_entry__.build()).  There is no
+fallback: if the shared object is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import c_char_p, c_int, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libr2l_b200.so")
+
+_lib = None
+
+# name -> (restype, argtypes); mirrors include/r2l_b200.h one to one
+_PROTOTYPES = {
+    "r2l_last_error": (c_char_p, []),
+    "r2l_abi_version": (c_int, []),
+    "r2l_packed_bytes": (c_size_t, []),
+    "r2l_fwd_workspace_bytes": (c_size_t, [c_int64]),
+    "r2l_pack_weights": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "r2l_forward": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                            c_void_p, c_size_t, c_int64, c_void_p]),
+    "r2l_selftest_layer": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+}
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the CUDA sources for sm_100a (nvcc cross-compiles without a GPU)."""
+    res = subprocess.run(["make", "-C", CSRC, "-j4"], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("building libr2l_b200.so failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stdout)
+    return LIB_PATH
+
+
+def exported_symbols():
+    return list(_PROTOTYPES)
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(r2l_b200 has no CPU or PyTorch fallback for the hot path)")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in _PROTOTYPES.items():
+            fn = getattr(handle, name)  # AttributeError if the ABI and the header drift apart
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = lib().r2l_last_error()
+        raise RuntimeError(f"{what} failed ({status}): {msg.decode() if msg else '?'}")

@@ -1,0 +1,112 @@
+"""Tensor-level wrappers over the C ABI: torch owns memory and streams, the library does the arithmetic.
+
+Shape / dtype / device / contiguity checks live here (SURVEY.md section 8b "error convention"); the C
+side only sees raw device pointers.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+INPUT_RAYS, INPUT_PTS, INPUT_X = 0, 1, 2
+NUM_PARAMS = 5917187
+N_SAMPLES = 16
+IN_DIM = 1008
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda_f32(t: torch.Tensor, name: str, shape_tail=None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: r2l_b200 runs on CUDA tensors only (no CPU fallback); got {t.device}")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name}: expected float32, got {t.dtype}")
+    if shape_tail is not None and tuple(t.shape[1:]) != tuple(shape_tail):
+        raise ValueError(f"{name}: expected shape [N,{','.join(map(str, shape_tail))}], got {tuple(t.shape)}")
+    return t.contiguous()
+
+
+def packed_bytes() -> int:
+    return int(_lib.lib().r2l_packed_bytes())
+
+
+def pack_weights(flat_params: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """flat fp32 parameters (state_dict order) -> tensor-core operand images (uint8 device buffer)."""
+    flat_params = _require_cuda_f32(flat_params, "flat_params")
+    if flat_params.numel() != NUM_PARAMS:
+        raise ValueError(f"flat_params: expected {NUM_PARAMS} floats, got {flat_params.numel()}")
+    if out is None:
+        out = torch.empty(packed_bytes(), dtype=torch.uint8, device=flat_params.device)
+    with torch.cuda.device(flat_params.device):
+        _lib.check(_lib.lib().r2l_pack_weights(_ptr(flat_params), _ptr(out), _stream()), "r2l_pack_weights")
+    return out
+
+
+_workspaces: dict = {}
+
+
+def _workspace(device, nbytes: int) -> torch.Tensor:
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def forward(packed: torch.Tensor, *, rays_o=None, rays_d=None, z_vals=None, t_rand=None, z_lower=None,
+            z_diff=None, pts=None, x=None, out=None) -> torch.Tensor:
+    """rgb[N,3] for one of three input forms:
+       rays_o,rays_d (+ z_vals host 16-vector; or z_lower,z_diff,t_rand for the stratified jitter),
+       pts[N,48], or x[N,1008]."""
+    L = _lib.lib()
+    zl = zd = None
+    if x is not None:
+        kind, in0, in1 = INPUT_X, _require_cuda_f32(x, "x", (IN_DIM,)), None
+    elif pts is not None:
+        kind, in0, in1 = INPUT_PTS, _require_cuda_f32(pts, "pts", (3 * N_SAMPLES,)), None
+    else:
+        kind = INPUT_RAYS
+        in0 = _require_cuda_f32(rays_o, "rays_o", (3,))
+        in1 = _require_cuda_f32(rays_d, "rays_d", (3,))
+        if in0.shape != in1.shape:
+            raise ValueError("rays_o / rays_d shape mismatch")
+        if t_rand is not None:
+            t_rand = _require_cuda_f32(t_rand, "t_rand", (N_SAMPLES,))
+            if t_rand.shape[0] != in0.shape[0]:
+                raise ValueError("t_rand: wrong number of rays")
+            zl = (ctypes.c_float * N_SAMPLES)(*[float(v) for v in z_lower])
+            zd = (ctypes.c_float * N_SAMPLES)(*[float(v) for v in z_diff])
+        else:
+            zl = (ctypes.c_float * N_SAMPLES)(*[float(v) for v in z_vals])
+    n = in0.shape[0]
+    dev = in0.device
+    if packed.device != dev:
+        raise RuntimeError("packed weights live on a different device")
+    if out is None:
+        out = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        wbytes = int(L.r2l_fwd_workspace_bytes(n))
+        ws = _workspace(dev, wbytes)
+        _lib.check(L.r2l_forward(kind, _ptr(in0), _ptr(in1), _ptr(t_rand), zl, zd, _ptr(packed), _ptr(out),
+                                 _ptr(ws), wbytes, n, _stream()), "r2l_forward")
+    return out
+
+
+def selftest_layer(a: torch.Tensor, packed: torch.Tensor, layer: int) -> torch.Tensor:
+    a = _require_cuda_f32(a, "a", (256,))
+    c = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.lib().r2l_selftest_layer(_ptr(a), _ptr(packed), layer, _ptr(c), _stream()), "r2l_selftest_layer")
+    return c

@@ -1,0 +1,116 @@
+"""CPU tests: the numpy oracle (oracle/r2l_oracle.py) against fixtures produced by the reference itself."""
+import numpy as np
+
+from oracle import r2l_oracle as orc
+from r2l_b200.nerf_raybased import state_dict_layout
+
+
+def rel(a, b):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-30))
+
+
+def test_seeded_weights_match_reference_checksums(golden_r2l, flat_seed0):
+    layout = state_dict_layout()
+    assert [n for n, _, _ in layout] == list(golden_r2l["param_names"])
+    for (name, shape, off), s, ss in zip(layout, golden_r2l["param_sum"], golden_r2l["param_sumsq"]):
+        v = flat_seed0[off:off + int(np.prod(shape))].astype(np.float64)
+        # fp64 checksums; torch and numpy sum in different orders, hence 1e-13 instead of ==
+        assert abs(v.sum() - s) <= 1e-13 * max(1.0, abs(s)) and abs((v ** 2).sum() - ss) <= 1e-13 * ss, name
+
+
+def test_point_sampler(golden_r2l):
+    g = golden_r2l
+    z = orc.sampler_z_vals(2.0, 6.0)
+    assert np.array_equal(z, g["z_vals"])
+    dirs = orc.sampler_dirs(400, 400, float(g["focal"]))
+    assert np.array_equal(dirs[:3, :5], g["dirs_corner"])
+    assert np.array_equal(orc.sample_train(g["rays_o"], g["rays_d"], z, None), g["pts"])
+    assert np.array_equal(orc.sample_train(g["rays_o"], g["rays_d"], z, g["t_rand"]), g["pts_jit"])
+    pts_test = orc.sample_test(dirs, g["c2w"][:3, :4], z)
+    np.testing.assert_allclose(pts_test[:64], g["pts_test_first64"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(pts_test[g["pix"]], g["pts_test_pix"], rtol=0, atol=2e-6)
+
+
+def test_positional_embed(golden_r2l):
+    x = orc.positional_embed(golden_r2l["pts"])
+    assert x.shape == (200, 1008)
+    np.testing.assert_allclose(x, golden_r2l["x_embed"], rtol=0, atol=5e-7)
+
+
+def test_forward_fp32(golden_r2l, flat_seed0):
+    g = golden_r2l
+    rgb, s = orc.r2l_forward(flat_seed0, g["x_embed"], keep=True)
+    assert rel(rgb, g["rgb"]) < 2e-5
+    assert rel(rgb, g["rgb_f64"]) < 2e-5
+    np.testing.assert_allclose(s["h"], g["h_head"], rtol=1e-4, atol=1e-5)
+    for k in (0, 9, 19, 29):
+        np.testing.assert_allclose(s["z"][k + 1], g[f"z_after_block{k}"], rtol=1e-3, atol=1e-4)
+    rgb_jit = orc.r2l_forward(flat_seed0, orc.positional_embed(g["pts_jit"]))
+    assert rel(rgb_jit, g["rgb_jit"]) < 2e-5
+
+
+def test_forward_fp64_truth(golden_r2l, flat_seed0):
+    g = golden_r2l
+    # the reference's fp64 run consumed the fp32 embedding cast to double (make_golden.py)
+    rgb = orc.r2l_forward(flat_seed0.astype(np.float64), g["x_embed"].astype(np.float64))
+    assert rel(rgb, g["rgb_f64"]) < 1e-9
+
+
+def test_loss_and_grads_fp64(golden_r2l, flat_seed0):
+    g = golden_r2l
+    f64 = flat_seed0.astype(np.float64)
+    # the reference's fp64 run used the fp32 embedding cast to double: do the same for exactness
+    x64 = g["x_embed"].astype(np.float64)
+    loss, grads, rgb, sq = orc.r2l_loss_and_grads(f64, x64, g["target"].astype(np.float64))
+    assert abs(loss - g["loss_f64"]) < 1e-12
+    sub = grads[g["grad_idx"]]
+    assert np.linalg.norm(sub - g["grad_f64_sub"]) / np.linalg.norm(g["grad_f64_sub"]) < 1e-9
+    assert abs(np.linalg.norm(grads) - g["grad_f64_norm"]) / g["grad_f64_norm"] < 1e-9
+    layout = {n: (o, int(np.prod(s))) for n, s, o in state_dict_layout()}
+    for name in ("tail.0.weight", "tail.0.bias", "head.0.bias", "body.0.body.0.bias", "body.42.body.2.bias"):
+        o, n = layout[name]
+        np.testing.assert_allclose(grads[o:o + n], g["g64_" + name], rtol=1e-8, atol=1e-14)
+
+
+def test_loss_and_grads_fp32_within_reference_noise(golden_r2l, flat_seed0):
+    g = golden_r2l
+    loss, grads, rgb, sq = orc.r2l_loss_and_grads(flat_seed0, g["x_embed"], g["target"])
+    assert abs(loss - g["loss"]) < 1e-6
+    sub = grads[g["grad_idx"]].astype(np.float64)
+    # the oracle in fp32 is as far from fp64 truth as the reference's own fp32 autograd is
+    err = np.linalg.norm(sub - g["grad_f64_sub"]) / np.linalg.norm(g["grad_f64_sub"])
+    assert err < 3 * float(g["grad_f32_vs_f64_rel"])
+
+
+def test_teacher_embed_and_mlp(golden_teacher):
+    t = golden_teacher
+    np.testing.assert_allclose(orc.teacher_embed(t["pts"].reshape(-1, 3)[:8], 10), t["embed_pts_first8"], rtol=0, atol=5e-7)
+    import torch
+    from r2l_b200.teacher import init_teacher_params
+    params = [p.numpy() for p in init_teacher_params(0)]
+    sums = [float(p.astype(np.float64).sum()) for p in params]
+    # state_dict order of the reference: pts_linears, views_linears, feature, alpha, rgb
+    assert np.allclose(sums, t["param_sum"], rtol=1e-13, atol=1e-13)
+    raw = orc.run_network(t["pts"], t["viewdirs"], params)
+    np.testing.assert_allclose(raw, t["raw"], rtol=1e-4, atol=2e-6)
+
+
+def test_raw2outputs(golden_teacher):
+    t = golden_teacher
+    for tag, wb in (("net", True), ("synth", False)):
+        rgb, disp, acc, w, depth = orc.raw2outputs(t[f"r2o_{tag}_raw"], t["z_vals"], t["rays_d"], wb)
+        np.testing.assert_allclose(w, t[f"r2o_{tag}_weights"], rtol=2e-5, atol=3e-7)  # 1-exp(-x) cancellation: 1 ulp of exp
+        np.testing.assert_allclose(rgb, t[f"r2o_{tag}_rgb"], rtol=2e-5, atol=3e-6)
+        np.testing.assert_allclose(acc, t[f"r2o_{tag}_acc"], rtol=2e-5, atol=3e-6)
+        np.testing.assert_allclose(depth, t[f"r2o_{tag}_depth"], rtol=2e-5, atol=3e-6)
+        np.testing.assert_allclose(disp, t[f"r2o_{tag}_disp"], rtol=3e-4, atol=1e-6, equal_nan=True)
+    assert np.isnan(t["r2o_synth_disp"][0])  # the transparent ray: 0/0 propagates through torch.max (Appendix A)
+
+
+def test_sample_pdf(golden_teacher):
+    t = golden_teacher
+    zs = orc.sample_pdf(t["pdf_bins"], t["pdf_weights"], 32)
+    # u = 1.0 lands on cdf[-1] == 1 +- 1 ulp, whose rounding depends on the cumsum order (torch vs numpy):
+    # near-flat cdf segments divide that ulp by a ~1e-3 denominator, hence the absolute tolerance
+    np.testing.assert_allclose(zs, t["pdf_samples"], rtol=1e-5, atol=1.5e-4)
+    assert np.mean(np.abs(zs - t["pdf_samples"]) > 1e-5) < 0.03  # and only a few samples are affected at all
