@@ -45,6 +45,11 @@ int r2l_forward(int input_kind, const float* in0, const float* in1, const float*
                 const float* z_diff, const void* packed, float* rgb, void* workspace, size_t workspace_bytes,
                 int64_t n_rays, void* stream);
 
+/* Debug: device buffer [grid][8] of int64 cycle counters filled by the next r2l_forward calls (NULL = off):
+ * [0] MMA wait on head A chunks, [1] on body A chunks, [2] on weight stages, [3] producer wait on free stages,
+ * [4] MMA-thread total. */
+int r2l_debug_set_stats(long long* stats);
+
 /* Debug / test hook: C[128,256] = A[128,256] * W_l^T through one tcgen05 layer step, l = body layer 0..85. */
 int r2l_selftest_layer(const float* A, const void* packed, int layer, float* C, void* stream);
 

@@ -7,6 +7,7 @@
 
 namespace {
 thread_local char g_err[512] = "";
+long long* g_stats = nullptr;  // debug cycle counters, see r2l_debug_set_stats
 
 int fail(const char* fmt, const char* detail) {
   snprintf(g_err, sizeof(g_err), fmt, detail);
@@ -80,7 +81,13 @@ int r2l_forward(int input_kind, const float* in0, const float* in1, const float*
   p.n_rays = n_rays;
   p.num_tiles = num_tiles(n_rays);
   p.input_kind = input_kind;
+  p.stats = g_stats;
   return check(r2l::launch_fwd(p, fwd_grid(n_rays), (cudaStream_t)stream), "r2l_forward");
+}
+
+int r2l_debug_set_stats(long long* stats) {
+  g_stats = stats;
+  return 0;
 }
 
 int r2l_selftest_layer(const float* A, const void* packed, int layer, float* C, void* stream) {

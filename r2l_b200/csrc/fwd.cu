@@ -9,7 +9,9 @@
 // Per CTA (384 threads):
 //   warp 0      weight producer: streams 32 KiB bf16 operand images (TMA bulk copy) into a 3-slot ring
 //   warp 1      MMA issuer: tcgen05.mma M=128,N=256,K=16, bf16x3 split (hi*hi + lo*hi + hi*lo), fp32 in TMEM
-//   warp 2      TMEM allocator (512 columns: Z = residual stream [0,256), H = block hidden [256,512))
+//   warp 2      TMEM allocator (512 columns: Z = residual stream [0,256), H = block hidden [256,512));
+//               the head accumulates into Z (its epilogue rewrites Z in place with relu(h)), because H is
+//               overwritten by block 0's first Linear while the head epilogue is still draining
 //   warp 3      spare
 //   warps 4-11  epilogue / encoder: two threads per ray (column halves). They build the head's A operand
 //               (positional encoding) and, after every layer, turn the fp32 accumulator into the next
@@ -122,42 +124,57 @@ __global__ void __launch_bounds__(kFwdThreads, 1) r2l_fwd_kernel(const __grid_co
     // ======================= weight producer =======================
     if (lane == 0) {
       uint32_t it = 0;
+      long long t_wait = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         for (int i = 0; i < 32 + 8 * kBodyLayers; ++i, ++it) {
           const uint32_t ws = it % kNumWStages, ph = (it / kNumWStages) & 1u;
+          const long long t0 = p.stats ? clock64() : 0;
           mbar_wait(bar(kBarWEmpty + ws), ph ^ 1u);
+          if (p.stats) t_wait += clock64() - t0;
           mbar_arrive_expect_tx(bar(kBarWFull + ws), kWImageBytes);
           const uint8_t* src = i < 32 ? head_images + (int64_t)i * kWImageBytes
                                       : body_images + (int64_t)(i - 32) * kWImageBytes;
           bulk_g2s(smem_base + kSmemW + ws * kWImageBytes, src, kWImageBytes, bar(kBarWFull + ws));
         }
       }
+      if (p.stats) p.stats[blockIdx.x * 8 + 3] = t_wait;
     }
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 256, 0, 0);
       uint32_t it = 0, a_phase = 0;
+      long long t_a_head = 0, t_a_body = 0, t_w = 0;
+      const long long t_begin = p.stats ? clock64() : 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         for (int l = 0; l <= kBodyLayers; ++l) {
           const int nkc = l == 0 ? 16 : 4;
-          const bool to_h = (l == 0) || (l & 1);
+          const bool to_h = (l & 1) != 0;            // head (l=0) and every block's 2nd Linear -> Z
+          const bool fresh = (l == 0) || to_h;      // first MMA overwrites the accumulator
           const uint32_t d = tmem_base + (to_h ? kTmemH : kTmemZ);
           for (int kc = 0; kc < nkc; ++kc) {
             const uint32_t slot = kc & 3;
-            mbar_wait(bar(kBarAFull + slot), (a_phase >> slot) & 1u);
+            {
+              const long long t0 = p.stats ? clock64() : 0;
+              mbar_wait(bar(kBarAFull + slot), (a_phase >> slot) & 1u);
+              if (p.stats) { if (l == 0) t_a_head += clock64() - t0; else t_a_body += clock64() - t0; }
+            }
             a_phase ^= 1u << slot;
             const uint32_t a_hi = smem_base + kSmemA + slot * kAChunkBytes;
             const uint32_t a_lo = a_hi + kPlaneBytes;
             {  // W_hi image: A_hi*W_hi + A_lo*W_hi
               const uint32_t ws = it % kNumWStages;
-              mbar_wait(bar(kBarWFull + ws), (it / kNumWStages) & 1u);
+              {
+                const long long t0 = p.stats ? clock64() : 0;
+                mbar_wait(bar(kBarWFull + ws), (it / kNumWStages) & 1u);
+                if (p.stats) t_w += clock64() - t0;
+              }
               tc_fence_after_sync();
               const uint32_t b = smem_base + kSmemW + ws * kWImageBytes;
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
                 umma_bf16(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b + 32 * ks, 16, 1024),
-                          idesc, (to_h && kc == 0 && ks == 0) ? 0u : 1u);
+                          idesc, (fresh && kc == 0 && ks == 0) ? 0u : 1u);
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
                 umma_bf16(d, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw128(b + 32 * ks, 16, 1024),
@@ -167,7 +184,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) r2l_fwd_kernel(const __grid_co
             }
             {  // W_lo image: A_hi*W_lo
               const uint32_t ws = it % kNumWStages;
-              mbar_wait(bar(kBarWFull + ws), (it / kNumWStages) & 1u);
+              {
+                const long long t0 = p.stats ? clock64() : 0;
+                mbar_wait(bar(kBarWFull + ws), (it / kNumWStages) & 1u);
+                if (p.stats) t_w += clock64() - t0;
+              }
               tc_fence_after_sync();
               const uint32_t b = smem_base + kSmemW + ws * kWImageBytes;
 #pragma unroll
@@ -181,6 +202,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) r2l_fwd_kernel(const __grid_co
           }
           umma_commit(bar(kBarAccFull));
         }
+      }
+      if (p.stats) {
+        p.stats[blockIdx.x * 8 + 0] = t_a_head;
+        p.stats[blockIdx.x * 8 + 1] = t_a_body;
+        p.stats[blockIdx.x * 8 + 2] = t_w;
+        p.stats[blockIdx.x * 8 + 4] = clock64() - t_begin;
       }
     }
   } else if (warp >= 4) {
@@ -249,7 +276,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) r2l_fwd_kernel(const __grid_co
         mbar_wait(bar(kBarAccFull), acc_phase);
         acc_phase ^= 1u;
         tc_fence_after_sync();
-        const bool from_h = (l == 0) || (l & 1);
+        const bool from_h = (l & 1) != 0;
+        const bool relu = (l == 0) || from_h;
         const float* bias = l == 0 ? headb : ((l & 1) ? b1 + (l >> 1) * kWidth : cumbias + (l >> 1) * kWidth);
         for (int c = 0; c < kAChunks; ++c) {
           const uint32_t col = 64u * c + 32u * hf;
@@ -265,7 +293,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) r2l_fwd_kernel(const __grid_co
             v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b4.z;
             v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b4.w;
           }
-          if (from_h) {
+          if (relu) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
           }

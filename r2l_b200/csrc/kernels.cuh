@@ -16,6 +16,7 @@ struct FwdParams {
   const uint8_t* packed;
   float* rgb;             // [N,3]
   float* h_scratch;       // [gridDim.x][128][256] fp32: head output kept for the outer residual
+  long long* stats;       // optional [gridDim.x][8] cycle counters (debug), nullptr in production
   int64_t n_rays;
   int num_tiles;
   int input_kind;
