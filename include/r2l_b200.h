@@ -45,6 +45,22 @@ int r2l_forward(int input_kind, const float* in0, const float* in1, const float*
                 const float* z_diff, const void* packed, float* rgb, void* workspace, size_t workspace_bytes,
                 int64_t n_rays, void* stream);
 
+/* ---- training: fused forward that keeps what the backward needs, and the fused backward ----
+ * Replaces loss.backward() through NeRF_v3_2 (main.py:1404; autograd of nerf_raybased.py:539-544).
+ *   zf        : [N,256] fp32 out, z_43 + h (input of the tail Linear)
+ *   fwd_saved : r2l_train_fwd_saved_bytes(n) bytes; the bf16 hi/lo input operand of every Linear
+ *   bwd_saved : r2l_train_bwd_saved_bytes(n) bytes; the bf16 hi/lo output-gradient operand of every Linear
+ *   grads     : [R2L_NUM_PARAMS] fp32 in state_dict order, OVERWRITTEN with dL/dparams given grad_rgb = dL/drgb
+ * `workspace` as in r2l_forward.  The three kernels of r2l_backward are enqueued back to back on `stream`. */
+size_t r2l_train_fwd_saved_bytes(int64_t n_rays);
+size_t r2l_train_bwd_saved_bytes(int64_t n_rays);
+int r2l_forward_train(int input_kind, const float* in0, const float* in1, const float* t_rand, const float* z_lo,
+                      const float* z_diff, const void* packed, float* rgb, float* zf, void* fwd_saved,
+                      void* workspace, size_t workspace_bytes, int64_t n_rays, void* stream);
+int r2l_backward(int input_kind, const void* packed, const float* rgb, const float* grad_rgb, const float* zf,
+                 const void* fwd_saved, void* bwd_saved, float* grads, void* workspace, size_t workspace_bytes,
+                 int64_t n_rays, void* stream);
+
 /* Debug: device buffer [grid][8] of int64 cycle counters filled by the next r2l_forward calls (NULL = off):
  * [0] MMA wait on head A chunks, [1] on body A chunks, [2] on weight stages, [3] producer wait on free stages,
  * [4] MMA-thread total. */

@@ -25,6 +25,12 @@ _PROTOTYPES = {
     "r2l_pack_weights": (c_int, [c_void_p, c_void_p, c_void_p]),
     "r2l_forward": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                             c_void_p, c_size_t, c_int64, c_void_p]),
+    "r2l_train_fwd_saved_bytes": (c_size_t, [c_int64]),
+    "r2l_train_bwd_saved_bytes": (c_size_t, [c_int64]),
+    "r2l_forward_train": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_size_t, c_int64, c_void_p]),
+    "r2l_backward": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                             c_void_p, c_size_t, c_int64, c_void_p]),
     "r2l_debug_set_stats": (c_int, [c_void_p]),
     "r2l_selftest_layer": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
 }

@@ -53,21 +53,13 @@ int r2l_pack_weights(const float* params, void* packed, void* stream) {
   return check(r2l::launch_pack(params, packed, (cudaStream_t)stream), "r2l_pack_weights");
 }
 
-int r2l_forward(int input_kind, const float* in0, const float* in1, const float* t_rand, const float* z_lo,
-                const float* z_diff, const void* packed, float* rgb, void* workspace, size_t workspace_bytes,
-                int64_t n_rays, void* stream) {
-  if (n_rays == 0) return 0;
-  if (n_rays < 0) return fail("r2l_forward: %s", "negative n_rays");
-  if (!in0 || !packed || !rgb || !workspace) return fail("r2l_forward: %s", "null pointer");
-  if (input_kind < 0 || input_kind > 2) return fail("r2l_forward: %s", "unknown input_kind");
-  if (input_kind == R2L_INPUT_RAYS && (!in1 || !z_lo)) return fail("r2l_forward: %s", "rays input needs in1 and z_lo");
-  if (t_rand && (input_kind != R2L_INPUT_RAYS || !z_diff))
-    return fail("r2l_forward: %s", "t_rand needs R2L_INPUT_RAYS and z_diff");
-  if (workspace_bytes < r2l_fwd_workspace_bytes(n_rays)) return fail("r2l_forward: %s", "workspace too small");
-  if (((uintptr_t)packed & 15) || ((uintptr_t)workspace & 15)) return fail("r2l_forward: %s", "packed/workspace must be 16-byte aligned");
-
-  r2l::FwdParams p;
-  memset(&p, 0, sizeof(p));
+namespace {
+int fill_inputs(r2l::ChainParams& p, const char* who, int input_kind, const float* in0, const float* in1,
+                const float* t_rand, const float* z_lo, const float* z_diff) {
+  if (!in0) return fail("%s: null input pointer", who);
+  if (input_kind < 0 || input_kind > 2) return fail("%s: unknown input_kind", who);
+  if (input_kind == R2L_INPUT_RAYS && (!in1 || !z_lo)) return fail("%s: rays input needs in1 and z_lo", who);
+  if (t_rand && (input_kind != R2L_INPUT_RAYS || !z_diff)) return fail("%s: t_rand needs R2L_INPUT_RAYS and z_diff", who);
   p.in0 = in0;
   p.in1 = in1;
   p.t_rand = t_rand;
@@ -75,14 +67,102 @@ int r2l_forward(int input_kind, const float* in0, const float* in1, const float*
     p.z_lo[i] = z_lo ? z_lo[i] : 0.f;
     p.z_diff[i] = z_diff ? z_diff[i] : 0.f;
   }
+  p.input_kind = input_kind;
+  return 0;
+}
+bool misaligned(const void* q) { return ((uintptr_t)q & 15) != 0; }
+}  // namespace
+
+int r2l_forward(int input_kind, const float* in0, const float* in1, const float* t_rand, const float* z_lo,
+                const float* z_diff, const void* packed, float* rgb, void* workspace, size_t workspace_bytes,
+                int64_t n_rays, void* stream) {
+  if (n_rays == 0) return 0;
+  if (n_rays < 0) return fail("r2l_forward: %s", "negative n_rays");
+  if (!packed || !rgb || !workspace) return fail("r2l_forward: %s", "null pointer");
+  if (workspace_bytes < r2l_fwd_workspace_bytes(n_rays)) return fail("r2l_forward: %s", "workspace too small");
+  if (misaligned(packed) || misaligned(workspace)) return fail("r2l_forward: %s", "packed/workspace must be 16-byte aligned");
+  r2l::ChainParams p;
+  memset(&p, 0, sizeof(p));
+  if (int rc = fill_inputs(p, "r2l_forward", input_kind, in0, in1, t_rand, z_lo, z_diff)) return rc;
   p.packed = static_cast<const uint8_t*>(packed);
   p.rgb = rgb;
-  p.h_scratch = static_cast<float*>(workspace);
+  p.scratch = static_cast<float*>(workspace);
+  p.n_rays = n_rays;
+  p.num_tiles = num_tiles(n_rays);
+  p.stats = g_stats;
+  return check(r2l::launch_chain(r2l::kFwdInfer, p, fwd_grid(n_rays), (cudaStream_t)stream), "r2l_forward");
+}
+
+size_t r2l_train_fwd_saved_bytes(int64_t n_rays) {
+  return (size_t)num_tiles(n_rays) * r2l::kFwdSavedChunks * r2l::kAChunkBytes;
+}
+size_t r2l_train_bwd_saved_bytes(int64_t n_rays) {
+  return (size_t)num_tiles(n_rays) * r2l::kBwdSavedChunks * r2l::kAChunkBytes;
+}
+
+int r2l_forward_train(int input_kind, const float* in0, const float* in1, const float* t_rand, const float* z_lo,
+                      const float* z_diff, const void* packed, float* rgb, float* zf, void* fwd_saved,
+                      void* workspace, size_t workspace_bytes, int64_t n_rays, void* stream) {
+  if (n_rays == 0) return 0;
+  if (n_rays < 0) return fail("r2l_forward_train: %s", "negative n_rays");
+  if (!packed || !rgb || !zf || !fwd_saved || !workspace) return fail("r2l_forward_train: %s", "null pointer");
+  if (workspace_bytes < r2l_fwd_workspace_bytes(n_rays)) return fail("r2l_forward_train: %s", "workspace too small");
+  if (misaligned(packed) || misaligned(workspace) || misaligned(fwd_saved) || misaligned(zf))
+    return fail("r2l_forward_train: %s", "buffers must be 16-byte aligned");
+  r2l::ChainParams p;
+  memset(&p, 0, sizeof(p));
+  if (int rc = fill_inputs(p, "r2l_forward_train", input_kind, in0, in1, t_rand, z_lo, z_diff)) return rc;
+  p.packed = static_cast<const uint8_t*>(packed);
+  p.rgb = rgb;
+  p.zf_out = zf;
+  p.saved = static_cast<uint8_t*>(fwd_saved);
+  p.scratch = static_cast<float*>(workspace);
+  p.n_rays = n_rays;
+  p.num_tiles = num_tiles(n_rays);
+  p.stats = g_stats;
+  return check(r2l::launch_chain(r2l::kFwdTrain, p, fwd_grid(n_rays), (cudaStream_t)stream), "r2l_forward_train");
+}
+
+int r2l_backward(int input_kind, const void* packed, const float* rgb, const float* grad_rgb, const float* zf,
+                 const void* fwd_saved, void* bwd_saved, float* grads, void* workspace, size_t workspace_bytes,
+                 int64_t n_rays, void* stream) {
+  if (n_rays == 0) return 0;
+  if (n_rays < 0) return fail("r2l_backward: %s", "negative n_rays");
+  if (!packed || !rgb || !grad_rgb || !zf || !fwd_saved || !bwd_saved || !grads || !workspace)
+    return fail("r2l_backward: %s", "null pointer");
+  if (input_kind < 0 || input_kind > 2) return fail("r2l_backward: %s", "unknown input_kind");
+  if (workspace_bytes < r2l_fwd_workspace_bytes(n_rays)) return fail("r2l_backward: %s", "workspace too small");
+  if (misaligned(packed) || misaligned(workspace) || misaligned(fwd_saved) || misaligned(bwd_saved) || misaligned(zf) || misaligned(grads))
+    return fail("r2l_backward: %s", "buffers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  r2l::ChainParams p;
+  memset(&p, 0, sizeof(p));
+  p.packed = static_cast<const uint8_t*>(packed);
+  p.scratch = static_cast<float*>(workspace);
+  p.saved = static_cast<uint8_t*>(bwd_saved);
+  p.fwd_saved = static_cast<const uint8_t*>(fwd_saved);
+  p.rgb_in = rgb;
+  p.grad_rgb = grad_rgb;
   p.n_rays = n_rays;
   p.num_tiles = num_tiles(n_rays);
   p.input_kind = input_kind;
   p.stats = g_stats;
-  return check(r2l::launch_fwd(p, fwd_grid(n_rays), (cudaStream_t)stream), "r2l_forward");
+  if (int rc = check(r2l::launch_chain(r2l::kBwd, p, fwd_grid(n_rays), st), "r2l_backward(chain)")) return rc;
+  r2l::DwParams d;
+  d.fwd_saved = p.fwd_saved;
+  d.bwd_saved = p.saved;
+  d.grads = grads;
+  d.num_tiles = p.num_tiles;
+  d.input_kind = input_kind;
+  d.accumulate = 0;
+  if (int rc = check(r2l::launch_dw(d, st), "r2l_backward(dw)")) return rc;
+  r2l::TailGradParams t;
+  t.zf = zf;
+  t.rgb = rgb;
+  t.grad_rgb = grad_rgb;
+  t.grads = grads;
+  t.n_rays = n_rays;
+  return check(r2l::launch_tail_grads(t, true, st), "r2l_backward(tail)");
 }
 
 int r2l_debug_set_stats(long long* stats) {

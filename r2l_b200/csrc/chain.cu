@@ -1,0 +1,616 @@
+// The "chain" kernel: one persistent CTA per SM walks a 128-ray tile through the whole 88-layer network
+// without the activations ever leaving the SM.  Three instantiations share the machinery:
+//
+//   kFwdInfer  rays -> 16 points -> sin/cos encoding -> head -> 43 ResMLP blocks -> +h -> tail -> sigmoid
+//   kFwdTrain  same, and every A operand it builds (the input of every Linear) is bulk-stored to HBM as a
+//              ready-made tensor-core operand image for the weight-gradient kernel (dw.cu)
+//   kBwd       d rgb -> d logit -> g = dL/dz_43 -> for k = 42..0 : da = g W2_k ; dh = da * (a_k > 0) ;
+//              g += dh W1_k  -> (g + dL/dz_43) * (h > 0); every dY operand is stored for dw.cu
+//
+// Reference semantics: /root/reference/model/nerf_raybased.py — PointSampler.sample_train :114-126,
+// PositionalEmbedder.__call__ :198-208, NeRF_v3_2.forward :539-544, ResMLP.forward :461-465; the backward
+// is what torch.autograd derives for that graph (loss.backward(), main.py:1404).
+//
+// Per CTA (384 threads):
+//   warp 0      weight producer: streams 32 KiB bf16 operand images (TMA bulk copy) into a 3-slot ring
+//   warp 1      MMA issuer: tcgen05.mma M=128,N=256,K=16, bf16x3 split (hi*hi + lo*hi + hi*lo), fp32 in TMEM
+//   warp 2      TMEM allocator (512 columns: Z [0,256) = residual stream / running gradient,
+//               H [256,512) = block hidden / its gradient)
+//   warp 3      (train / bwd) operand-image store warp: smem A chunk -> HBM via bulk async stores
+//   warps 4-11  epilogue / encoder: two threads per ray (column halves). They build the first A operand
+//               (positional encoding, or dL/dz_43) and after every layer turn the fp32 accumulator into the
+//               next layer's bf16 hi/lo A operand in shared memory (bias/ReLU or mask, split, 128B swizzle).
+//
+// TMEM residency of the residual stream: Z holds z_k - sum_{j<k} b2_j (forward) or g_k (backward) in fp32;
+// the second GEMM of each block accumulates straight onto it, so the skip connection costs nothing.
+// The head accumulates into Z as well (its epilogue rewrites Z in place with relu(h)): H is overwritten by
+// block 0's first Linear while the head epilogue is still draining.
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace r2l {
+
+constexpr int kNumWStages = 3;
+constexpr int kChainThreads = 384;
+constexpr int kEpiWarps = 8;
+constexpr uint32_t kSmemA = 0;
+constexpr uint32_t kSmemW = kABytes;                                  // 131072
+constexpr uint32_t kSmemBar = kSmemW + kNumWStages * kWImageBytes;    // 229376
+constexpr uint32_t kSmemTail = kSmemBar + 256;                        // 128 x 3 floats
+constexpr uint32_t kSmemUsed = kSmemTail + kTileM * 3 * 4;            // 231168
+constexpr uint32_t kChainSmemBytes = kSmemUsed + 1024;                // + alignment slack
+
+constexpr uint32_t kTmemZ = 0;
+constexpr uint32_t kTmemH = 256;
+
+// barrier slots (8 bytes each) inside kSmemBar
+enum : uint32_t {
+  kBarWFull = 0,                          // [3] weight image landed            (TMA tx -> MMA)
+  kBarWEmpty = kBarWFull + kNumWStages,   // [3] weight slot consumed           (MMA commit -> producer)
+  kBarAFull = kBarWEmpty + kNumWStages,   // [4] A chunk written                (8 epilogue warps -> MMA, store warp)
+  kBarAEmpty = kBarAFull + kAChunks,      // [4] A chunk consumed (head ring)    (MMA commit -> encoder)
+  kBarASaved = kBarAEmpty + kAChunks,     // [4] A chunk copied out to HBM       (store warp -> epilogue)
+  kBarAccFull = kBarASaved + kAChunks,    //     accumulator of a layer complete (MMA commit -> epilogue)
+  kBarCount
+};
+
+template <int HF>
+__device__ __forceinline__ void encode_half(const float (&x)[3], float (&out)[32]) {
+  // fused feature order of layout.cuh: slot 2p = sin, 2p+1 = cos, pair p = coordinate*10 + frequency
+#pragma unroll
+  for (int i = 0; i < (HF == 0 ? 16 : 14); ++i) {
+    const int p = HF * 16 + i;
+    const int c = p / kFreqs, f = p % kFreqs;
+    const float arg = __fmul_rn(x[c], static_cast<float>(1 << f));  // exact: power-of-two scale
+    float s, co;
+    sincosf(arg, &s, &co);
+    out[2 * i] = s;
+    out[2 * i + 1] = co;
+  }
+  if (HF == 1) {
+    out[28] = x[0];
+    out[29] = x[1];
+    out[30] = x[2];
+    out[31] = 0.f;
+  }
+}
+
+// Write 32 consecutive K-values of one row into an A chunk (both planes).
+__device__ __forceinline__ void store_a_half(uint32_t a_chunk_addr, uint32_t row, uint32_t hf,
+                                             const float (&v)[32]) {
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split2(v[8 * jj + 2 * e], v[8 * jj + 2 * e + 1], hi[e], lo[e]);
+    const uint32_t off = row * 128u + (((4u * hf + jj) ^ (row & 7u)) << 4);
+    st_shared_v4(a_chunk_addr + off, hi[0], hi[1], hi[2], hi[3]);
+    st_shared_v4(a_chunk_addr + kPlaneBytes + off, lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __grid_constant__ ChainParams p) {
+  constexpr bool kIsBwd = MODE == kBwd;
+  constexpr bool kSave = MODE != kFwdInfer;
+  constexpr int kFirstChunks = kIsBwd ? kAChunks : kSamples;   // A chunks built before the first GEMM
+  constexpr int kLayers = kIsBwd ? kBodyLayers : kBodyLayers + 1;  // GEMMs per tile
+  constexpr int kImagesPerTile = kIsBwd ? 8 * kBodyLayers : 32 + 8 * kBodyLayers;
+  // chunks saved per tile: forward 16 (PE) + 86*4 ; backward 4 (g_43) + 86*4
+  constexpr int kSavedChunksPerTile = kFirstChunks + 4 * kBodyLayers;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar0 = smem_base + kSmemBar;
+  auto bar = [&](uint32_t i) { return bar0 + 8u * i; };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + kSmemBar + 8 * kBarCount);
+  float* tail_smem = reinterpret_cast<float*>(smem_gen + kSmemTail);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kNumWStages; ++i) {
+      mbar_init(bar(kBarWFull + i), 1);
+      mbar_init(bar(kBarWEmpty + i), 1);
+    }
+    for (int i = 0; i < kAChunks; ++i) {
+      mbar_init(bar(kBarAFull + i), kEpiWarps);
+      mbar_init(bar(kBarAEmpty + i), 1);
+      mbar_init(bar(kBarASaved + i), 1);
+    }
+    mbar_init(bar(kBarAccFull), 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ======================= weight producer =======================
+    if (lane == 0) {
+      const uint8_t* head_images =
+          p.packed + (int64_t)(p.input_kind == kInputX ? kImgHeadNatural : kImgHeadFused) * kWImageBytes;
+      const uint8_t* body_images = p.packed + (int64_t)(kIsBwd ? kImgBodyT : kImgBody) * kWImageBytes;
+      uint32_t it = 0;
+      long long t_wait = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int i = 0; i < kImagesPerTile; ++i, ++it) {
+          const uint32_t ws = it % kNumWStages, ph = (it / kNumWStages) & 1u;
+          const long long t0 = p.stats ? clock64() : 0;
+          mbar_wait(bar(kBarWEmpty + ws), ph ^ 1u);
+          if (p.stats) t_wait += clock64() - t0;
+          mbar_arrive_expect_tx(bar(kBarWFull + ws), kWImageBytes);
+          const uint8_t* src;
+          if (kIsBwd) src = body_images + (int64_t)i * kWImageBytes;
+          else src = i < 32 ? head_images + (int64_t)i * kWImageBytes : body_images + (int64_t)(i - 32) * kWImageBytes;
+          bulk_g2s(smem_base + kSmemW + ws * kWImageBytes, src, kWImageBytes, bar(kBarWFull + ws));
+        }
+      }
+      if (p.stats) p.stats[blockIdx.x * 8 + 3] = t_wait;
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 256, 0, 0);
+      uint32_t it = 0, a_phase = 0;
+      long long t_a_head = 0, t_a_body = 0, t_w = 0;
+      const long long t_begin = p.stats ? clock64() : 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int l = 0; l < kLayers; ++l) {
+          // forward: l = 0 head (16 chunks, -> Z fresh), odd l -> H fresh, even l -> Z accumulate
+          // backward: j = l: even j (da = g W2) -> H fresh, odd j (g += dh W1) -> Z accumulate
+          const int nkc = (!kIsBwd && l == 0) ? kSamples : kAChunks;
+          const bool to_h = kIsBwd ? ((l & 1) == 0) : ((l & 1) != 0);
+          const bool fresh = to_h || (!kIsBwd && l == 0);
+          const bool ring = !kIsBwd && l == 0;   // head: A chunks recycle through the 4 slots
+          const uint32_t d = tmem_base + (to_h ? kTmemH : kTmemZ);
+          for (int kc = 0; kc < nkc; ++kc) {
+            const uint32_t slot = kc & 3;
+            {
+              const long long t0 = p.stats ? clock64() : 0;
+              mbar_wait(bar(kBarAFull + slot), (a_phase >> slot) & 1u);
+              if (p.stats) { if (l == 0) t_a_head += clock64() - t0; else t_a_body += clock64() - t0; }
+            }
+            a_phase ^= 1u << slot;
+            const uint32_t a_hi = smem_base + kSmemA + slot * kAChunkBytes;
+            const uint32_t a_lo = a_hi + kPlaneBytes;
+            {  // W_hi image: A_hi*W_hi + A_lo*W_hi
+              const uint32_t ws = it % kNumWStages;
+              {
+                const long long t0 = p.stats ? clock64() : 0;
+                mbar_wait(bar(kBarWFull + ws), (it / kNumWStages) & 1u);
+                if (p.stats) t_w += clock64() - t0;
+              }
+              tc_fence_after_sync();
+              const uint32_t b = smem_base + kSmemW + ws * kWImageBytes;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma_bf16(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b + 32 * ks, 16, 1024),
+                          idesc, (fresh && kc == 0 && ks == 0) ? 0u : 1u);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma_bf16(d, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw128(b + 32 * ks, 16, 1024),
+                          idesc, 1u);
+              umma_commit(bar(kBarWEmpty + ws));
+              ++it;
+            }
+            {  // W_lo image: A_hi*W_lo
+              const uint32_t ws = it % kNumWStages;
+              {
+                const long long t0 = p.stats ? clock64() : 0;
+                mbar_wait(bar(kBarWFull + ws), (it / kNumWStages) & 1u);
+                if (p.stats) t_w += clock64() - t0;
+              }
+              tc_fence_after_sync();
+              const uint32_t b = smem_base + kSmemW + ws * kWImageBytes;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma_bf16(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b + 32 * ks, 16, 1024),
+                          idesc, 1u);
+              umma_commit(bar(kBarWEmpty + ws));
+              ++it;
+            }
+            if (ring) umma_commit(bar(kBarAEmpty + slot));
+          }
+          umma_commit(bar(kBarAccFull));
+        }
+        if constexpr (kIsBwd) {
+          // the last backward epilogue publishes 4 more chunks (d head pre-activation, consumed only by the
+          // store warp): step over those phases so the parity bookkeeping stays aligned for the next tile
+          for (uint32_t slot = 0; slot < kAChunks; ++slot) {
+            mbar_wait(bar(kBarAFull + slot), (a_phase >> slot) & 1u);
+            a_phase ^= 1u << slot;
+          }
+        }
+      }
+      if (p.stats) {
+        p.stats[blockIdx.x * 8 + 0] = t_a_head;
+        p.stats[blockIdx.x * 8 + 1] = t_a_body;
+        p.stats[blockIdx.x * 8 + 2] = t_w;
+        p.stats[blockIdx.x * 8 + 4] = clock64() - t_begin;
+      }
+    }
+  } else if (warp == 3) {
+    // ======================= operand-image store warp (train / bwd) =======================
+    if (kSave && lane == 0) {
+      uint32_t a_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        uint8_t* dst = p.saved + (int64_t)tile * kSavedChunksPerTile * kAChunkBytes;
+        for (int i = 0; i < kSavedChunksPerTile; ++i) {
+          const uint32_t slot = i & 3;   // first chunks cycle the ring; body chunk c lives in slot c
+          mbar_wait(bar(kBarAFull + slot), (a_phase >> slot) & 1u);
+          a_phase ^= 1u << slot;
+          bulk_s2g(dst + (int64_t)i * kAChunkBytes, smem_base + kSmemA + slot * kAChunkBytes, kAChunkBytes);
+          bulk_commit();
+          bulk_wait_read<0>();           // smem has been read: the slot may be rewritten
+          mbar_arrive(bar(kBarASaved + slot));
+        }
+      }
+      bulk_wait_all<0>();
+    }
+  } else if (warp >= 4) {
+    // ======================= encoder / epilogue =======================
+    const uint32_t ew = warp - 4;
+    const uint32_t q = ew & 3u;       // TMEM lane quarter (== warp % 4)
+    const uint32_t hf = ew >> 2;      // column half inside each 64-wide chunk
+    const uint32_t row = q * 32u + lane;
+    const uint32_t tmem_row = tmem_base + ((q * 32u) << 16);
+    const float* cumbias = reinterpret_cast<const float*>(p.packed + kPackOffCumBias);
+    const float* headb = reinterpret_cast<const float*>(p.packed + kPackOffHeadB);
+    const float* b1 = reinterpret_cast<const float*>(p.packed + kPackOffB1);
+    const float* tailw = reinterpret_cast<const float*>(p.packed + kPackOffTailW);
+    const float* tailb = reinterpret_cast<const float*>(p.packed + kPackOffTailB);
+    float* hrow = p.scratch + ((int64_t)blockIdx.x * kTileM + row) * kWidth;
+    uint32_t acc_phase = 0;
+    uint32_t saved_phase = 0;   // per-slot parity of kBarASaved
+    (void)cumbias; (void)headb; (void)b1; (void)tailb; (void)tail_smem;
+
+    // publish one A chunk: make the generic-proxy writes visible to the tensor core, then signal
+    auto publish = [&](uint32_t slot) {
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(kBarAFull + slot));
+    };
+    // before rewriting a slot in save modes: the store warp must have copied the previous content out
+    auto wait_saved = [&](uint32_t slot, bool first_use) {
+      if (kSave) {
+        if (!first_use) mbar_wait(bar(kBarASaved + slot), (saved_phase >> slot) & 1u);
+        if (!first_use) saved_phase ^= 1u << slot;
+      }
+    };
+
+    bool first_tile = true;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, first_tile = false) {
+      const int64_t grow = (int64_t)tile * kTileM + row;
+      const bool valid = grow < p.n_rays;
+
+      if constexpr (!kIsBwd) {
+        // ---- head A operand: 16 chunks through the 4-slot A ring ----
+        float o[3] = {0.f, 0.f, 0.f}, dd[3] = {0.f, 0.f, 0.f};
+        if (p.input_kind == kInputRays && valid) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            o[c] = __ldg(p.in0 + grow * 3 + c);
+            dd[c] = __ldg(p.in1 + grow * 3 + c);
+          }
+        }
+        for (int c = 0; c < kSamples; ++c) {
+          const uint32_t slot = c & 3;
+          float f[32];
+          if (p.input_kind == kInputX) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int feat = 64 * c + 32 * (int)hf + i;
+              f[i] = (valid && feat < kInDim) ? __ldg(p.in0 + grow * kInDim + feat) : 0.f;
+            }
+          } else {
+            float x[3] = {0.f, 0.f, 0.f};
+            if (valid) {
+              if (p.input_kind == kInputPts) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) x[k] = __ldg(p.in0 + grow * (3 * kSamples) + 3 * c + k);
+              } else {
+                float z = p.z_lo[c];
+                if (p.t_rand != nullptr)  // lower + (upper - lower) * t_rand, nerf_raybased.py:123
+                  z = __fadd_rn(z, __fmul_rn(p.z_diff[c], __ldg(p.t_rand + grow * kSamples + c)));
+#pragma unroll
+                for (int k = 0; k < 3; ++k) x[k] = __fadd_rn(o[k], __fmul_rn(dd[k], z));  // :124
+              }
+            }
+            if (hf == 0) encode_half<0>(x, f); else encode_half<1>(x, f);
+          }
+          if (c >= 4) mbar_wait(bar(kBarAEmpty + slot), ((c >> 2) - 1) & 1u);
+          wait_saved(slot, first_tile && c < 4);
+          store_a_half(smem_base + kSmemA + slot * kAChunkBytes, row, hf, f);
+          publish(slot);
+        }
+      } else {
+        // ---- backward prologue: d logit = d rgb * rgb (1 - rgb);  g = d logit . W_tail  (dL/dz_43 = dL/dh_skip) ----
+        float dl[3] = {0.f, 0.f, 0.f};
+        if (valid) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float y = __ldg(p.rgb_in + grow * 3 + c);
+            dl[c] = __ldg(p.grad_rgb + grow * 3 + c) * y * (1.f - y);
+          }
+        }
+        for (int c = 0; c < kAChunks; ++c) {
+          const uint32_t col = 64u * c + 32u * hf;
+          float v[32];
+          uint32_t r[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(tailw + col) + i);
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(tailw + kWidth + col) + i);
+            const float4 w2 = __ldg(reinterpret_cast<const float4*>(tailw + 2 * kWidth + col) + i);
+            v[4 * i + 0] = fmaf(dl[2], w2.x, fmaf(dl[1], w1.x, dl[0] * w0.x));
+            v[4 * i + 1] = fmaf(dl[2], w2.y, fmaf(dl[1], w1.y, dl[0] * w0.y));
+            v[4 * i + 2] = fmaf(dl[2], w2.z, fmaf(dl[1], w1.z, dl[0] * w0.z));
+            v[4 * i + 3] = fmaf(dl[2], w2.w, fmaf(dl[1], w1.w, dl[0] * w0.w));
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(v[i]);
+          tmem_st32(tmem_row + kTmemZ + col, r);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            reinterpret_cast<float4*>(hrow + col)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          tmem_st_wait();
+          wait_saved(c, first_tile);
+          store_a_half(smem_base + kSmemA + c * kAChunkBytes, row, hf, v);
+          publish(c);
+        }
+      }
+
+      // ---- layer epilogues ----
+      float dot0 = 0.f, dot1 = 0.f, dot2 = 0.f;
+      for (int l = 0; l < kLayers; ++l) {
+        mbar_wait(bar(kBarAccFull), acc_phase);
+        acc_phase ^= 1u;
+        tc_fence_after_sync();
+        const bool from_h = kIsBwd ? ((l & 1) == 0) : ((l & 1) != 0);
+        const bool last = l == kLayers - 1;
+        // forward tables
+        const bool relu = !kIsBwd && ((l == 0) || from_h);
+        const float* bias = nullptr;
+        if constexpr (!kIsBwd)
+          bias = l == 0 ? headb : ((l & 1) ? b1 + (l >> 1) * kWidth : cumbias + (l >> 1) * kWidth);
+        // backward: mask source = hi plane of a saved forward operand image.
+        //   even j (da -> dh): a_k with k = 42 - j/2, forward saved chunk index 16 + 4*(2k+1) + c
+        //   last (j = 85):     h (= A_z(0), forward saved chunks 16 + c), applied to g_0 + dL/dz_43
+        const uint8_t* mask_img = nullptr;
+        if constexpr (kIsBwd) {
+          const int k = (kBlocks - 1) - (l >> 1);
+          const int64_t fwd_chunks_per_tile = kSamples + 4 * kBodyLayers;
+          const int64_t chunk0 = from_h ? (kSamples + 4 * (2 * k + 1)) : kSamples;
+          mask_img = p.fwd_saved + ((int64_t)tile * fwd_chunks_per_tile + chunk0) * kAChunkBytes;
+        }
+        for (int c = 0; c < kAChunks; ++c) {
+          const uint32_t col = 64u * c + 32u * hf;
+          uint32_t r[32];
+          tmem_ld32(tmem_row + (from_h ? kTmemH : kTmemZ) + col, r);
+          tmem_ld_wait();
+          float v[32];
+          if constexpr (!kIsBwd) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col) + i);
+              v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + b4.x;
+              v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b4.y;
+              v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b4.z;
+              v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b4.w;
+            }
+            if (relu) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            if (l == 0) {
+              // z_0 = h: seed the TMEM residual stream and keep h for the outer skip (:543)
+#pragma unroll
+              for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(v[i]);
+              tmem_st32(tmem_row + kTmemZ + col, r);
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                reinterpret_cast<float4*>(hrow + col)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              tmem_st_wait();
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+            if (last) {  // + dL/dz_43 through the outer skip
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 g4 = reinterpret_cast<const float4*>(hrow + col)[i];
+                v[4 * i] += g4.x; v[4 * i + 1] += g4.y; v[4 * i + 2] += g4.z; v[4 * i + 3] += g4.w;
+              }
+            }
+            if (from_h || last) {
+              // ReLU mask from the hi plane of the saved forward operand (a > 0  <=>  bf16 hi > 0)
+              const uint8_t* plane = mask_img + (int64_t)c * kAChunkBytes;
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const uint4 m = __ldg(reinterpret_cast<const uint4*>(plane + row * 128u + (((4u * hf + jj) ^ (row & 7u)) << 4)));
+                const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  // a >= 0 always, so "positive" == non-zero bf16 bits (ignoring the sign bit of -0)
+                  if ((w[e] & 0x00007FFFu) == 0u) v[8 * jj + 2 * e] = 0.f;
+                  if ((w[e] & 0x7FFF0000u) == 0u) v[8 * jj + 2 * e + 1] = 0.f;
+                }
+              }
+            }
+          }
+          const bool feeds_mma = !last;          // the last epilogue of a tile produces no further GEMM input
+          const bool produces_chunk = feeds_mma || kIsBwd;  // backward's last output (d head pre-activation) is saved for dw
+          if (produces_chunk) {
+            wait_saved(c, false);
+            store_a_half(smem_base + kSmemA + c * kAChunkBytes, row, hf, v);
+            publish(c);
+          }
+          if constexpr (!kIsBwd) {
+            if (last) {
+              // tail: rgb = sigmoid(W_t (z_43 + h) + b_t), partial dot over my 32 columns
+              float zf[32];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 h4 = reinterpret_cast<const float4*>(hrow + col)[i];
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(tailw + col) + i);
+                const float4 w1 = __ldg(reinterpret_cast<const float4*>(tailw + kWidth + col) + i);
+                const float4 w2 = __ldg(reinterpret_cast<const float4*>(tailw + 2 * kWidth + col) + i);
+                const float z0 = v[4 * i] + h4.x, z1 = v[4 * i + 1] + h4.y, z2 = v[4 * i + 2] + h4.z,
+                            z3 = v[4 * i + 3] + h4.w;
+                zf[4 * i] = z0; zf[4 * i + 1] = z1; zf[4 * i + 2] = z2; zf[4 * i + 3] = z3;
+                dot0 = fmaf(z0, w0.x, dot0); dot0 = fmaf(z1, w0.y, dot0); dot0 = fmaf(z2, w0.z, dot0); dot0 = fmaf(z3, w0.w, dot0);
+                dot1 = fmaf(z0, w1.x, dot1); dot1 = fmaf(z1, w1.y, dot1); dot1 = fmaf(z2, w1.z, dot1); dot1 = fmaf(z3, w1.w, dot1);
+                dot2 = fmaf(z0, w2.x, dot2); dot2 = fmaf(z1, w2.y, dot2); dot2 = fmaf(z2, w2.z, dot2); dot2 = fmaf(z3, w2.w, dot2);
+              }
+              if (MODE == kFwdTrain && valid) {  // z_43 + h for the tail weight gradient
+                float* zrow = p.zf_out + grow * kWidth + col;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  reinterpret_cast<float4*>(zrow)[i] = make_float4(zf[4 * i], zf[4 * i + 1], zf[4 * i + 2], zf[4 * i + 3]);
+              }
+            }
+          }
+        }
+      }
+      if constexpr (!kIsBwd) {
+        // combine the two column halves of each ray, sigmoid, store
+        tc_fence_before_sync();
+        if (hf == 1) {
+          tail_smem[row * 3 + 0] = dot0;
+          tail_smem[row * 3 + 1] = dot1;
+          tail_smem[row * 3 + 2] = dot2;
+        }
+        named_bar_sync(1, kEpiWarps * 32);
+        if (hf == 0 && valid) {
+          const float s0 = dot0 + tail_smem[row * 3 + 0] + __ldg(tailb + 0);
+          const float s1 = dot1 + tail_smem[row * 3 + 1] + __ldg(tailb + 1);
+          const float s2 = dot2 + tail_smem[row * 3 + 2] + __ldg(tailb + 2);
+          p.rgb[grow * 3 + 0] = 1.f / (1.f + expf(-s0));
+          p.rgb[grow * 3 + 1] = 1.f / (1.f + expf(-s1));
+          p.rgb[grow * 3 + 2] = 1.f / (1.f + expf(-s2));
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Single-layer self test: C[128,256] = A[128,256] * W^T using exactly the operand images, descriptors
+// and TMEM read-back the chain kernel uses. `images` = 8 consecutive 32 KiB images (4 chunks x {hi,lo}).
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) r2l_umma_selftest_kernel(const float* __restrict__ A,
+                                                                  const uint8_t* __restrict__ images,
+                                                                  float* __restrict__ C) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t wbase = smem_base + kABytes;
+  const uint32_t bar_w = smem_base + kABytes + 2 * kWImageBytes;
+  const uint32_t bar_m = bar_w + 8;
+  volatile uint32_t* tmem_ptr_smem =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + kABytes + 2 * kWImageBytes + 16);
+  const int warp = threadIdx.x >> 5;
+  const uint32_t row = threadIdx.x;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_m, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), 256);
+    tmem_relinquish();
+  }
+  // A operand: every thread splits its own row
+  for (int c = 0; c < kAChunks; ++c) {
+    for (uint32_t hf = 0; hf < 2; ++hf) {
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = A[row * kWidth + 64 * c + 32 * hf + i];
+      store_a_half(smem_base + c * kAChunkBytes, row, hf, v);
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (threadIdx.x == 0) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 256, 0, 0);
+    for (int kc = 0; kc < kAChunks; ++kc) {
+      mbar_arrive_expect_tx(bar_w, 2 * kWImageBytes);
+      bulk_g2s(wbase, images + (int64_t)(2 * kc) * kWImageBytes, kWImageBytes, bar_w);
+      bulk_g2s(wbase + kWImageBytes, images + (int64_t)(2 * kc + 1) * kWImageBytes, kWImageBytes, bar_w);
+      mbar_wait(bar_w, kc & 1);
+      tc_fence_after_sync();
+      const uint32_t a_hi = smem_base + kc * kAChunkBytes, a_lo = a_hi + kPlaneBytes;
+      for (int ks = 0; ks < 4; ++ks)
+        umma_bf16(tmem_base, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(wbase + 32 * ks, 16, 1024),
+                  idesc, (kc == 0 && ks == 0) ? 0u : 1u);
+      for (int ks = 0; ks < 4; ++ks)
+        umma_bf16(tmem_base, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw128(wbase + 32 * ks, 16, 1024),
+                  idesc, 1u);
+      for (int ks = 0; ks < 4; ++ks)
+        umma_bf16(tmem_base, umma_desc_sw128(a_hi + 32 * ks, 16, 1024),
+                  umma_desc_sw128(wbase + kWImageBytes + 32 * ks, 16, 1024), idesc, 1u);
+      umma_commit(bar_m);
+      mbar_wait(bar_m, kc & 1);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  for (int c8 = 0; c8 < 8; ++c8) {
+    uint32_t r[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + 32 * c8, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) C[row * kWidth + 32 * c8 + i] = __uint_as_float(r[i]);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+template <int MODE>
+static cudaError_t launch_chain_mode(const ChainParams& p, int grid, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(r2l_chain_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kChainSmemBytes);
+  if (e != cudaSuccess) return e;
+  r2l_chain_kernel<MODE><<<grid, kChainThreads, kChainSmemBytes, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_chain(int mode, const ChainParams& p, int grid, cudaStream_t stream) {
+  switch (mode) {
+    case kFwdInfer: return launch_chain_mode<kFwdInfer>(p, grid, stream);
+    case kFwdTrain: return launch_chain_mode<kFwdTrain>(p, grid, stream);
+    case kBwd: return launch_chain_mode<kBwd>(p, grid, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_umma_selftest(const float* A, const void* images, float* C, cudaStream_t stream) {
+  const int smem = kABytes + 2 * kWImageBytes + 64 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(r2l_umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  r2l_umma_selftest_kernel<<<1, 128, smem, stream>>>(A, static_cast<const uint8_t*>(images), C);
+  return cudaGetLastError();
+}
+
+}  // namespace r2l

@@ -1,0 +1,236 @@
+// Weight-gradient kernel: dW_l[o,i] = sum_rays dY_l[ray,o] * X_l[ray,i] and db_l[o] = sum_rays dY_l[ray,o]
+// for the head and the 86 body Linears, as tcgen05 GEMMs whose K dimension is the ray axis.
+//
+// Both operands are the bf16 hi/lo operand images the chain kernels stored (chain.cu): X_l = the A operand
+// the forward pass fed to Linear l, dY_l = the A operand the backward pass built from dL/d(output of Linear l).
+// An image chunk is [128 rays][64 features] with 128-byte swizzled rows, i.e. exactly a UMMA *MN-major*
+// SWIZZLE_128B tile when the ray axis plays K — so the same bytes serve as K-major A operand in the chain
+// kernels and as MN-major A/B operands here, with no transposition anywhere.
+//
+// One CTA per unit (86 body layers + 4 head column groups of 256 features); it loops over all ray tiles:
+//   warp 0     producer: per 32-ray stage, 16 bulk copies of 4 KiB (dY: 4 chunks x {hi,lo}, X: same) -> 64 KiB stage
+//   warp 1     MMA issuer: per stage 2 k-steps x 2 output halves x 3 split terms, M=128 N=256 K=16
+//   warp 2     TMEM allocator: two fp32 accumulators [128 x 256] (output rows 0-127 and 128-255) = 512 columns
+//   warps 4-7  bias gradient: column sums of dY straight from the staged smem tiles; then the epilogue
+//              (TMEM -> registers -> global)
+// Autograd equivalent in the reference: the weight/bias gradients torch.autograd produces for every
+// nn.Linear of NeRF_v3_2 (model/nerf_raybased.py:500,:453-456) under loss.backward() (main.py:1404).
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace r2l {
+
+constexpr int kDwThreads = 256;
+constexpr int kDwStages = 3;
+constexpr int kDwRowsPerStage = 32;
+constexpr uint32_t kDwPiece = kDwRowsPerStage * 128;   // 4096: 32 rays of one plane of one chunk
+constexpr uint32_t kDwOperand = 8 * kDwPiece;          // 32768: 4 chunks x 2 planes
+constexpr uint32_t kDwStageBytes = 2 * kDwOperand;     // dY + X
+constexpr uint32_t kDwSmemBar = kDwStages * kDwStageBytes;  // 196608
+constexpr uint32_t kDwSmemBytes = kDwSmemBar + 128 + 1024;
+constexpr int kDwUnits = kBodyLayers + 4;
+
+__global__ void __launch_bounds__(kDwThreads, 1) r2l_dw_kernel(const __grid_constant__ DwParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar0 = smem_base + kDwSmemBar;
+  auto bar_full = [&](uint32_t s) { return bar0 + 8u * s; };
+  auto bar_empty = [&](uint32_t s) { return bar0 + 8u * (kDwStages + s); };
+  const uint32_t bar_done = bar0 + 8u * (2 * kDwStages);
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + kDwSmemBar + 8 * (2 * kDwStages + 1));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int unit = blockIdx.x;
+  const bool is_head = unit >= kBodyLayers;
+  const int layer = unit;                 // body layer 0..85 when !is_head
+  const int hg = unit - kBodyLayers;      // head feature group 0..3 (256 encoded features each)
+  // chunk offsets inside a tile's saved images (see chain.cu for the order they are written in)
+  const int x_chunk0 = is_head ? 4 * hg : kSamples + 4 * layer;
+  const int dy_chunk0 = is_head ? kAChunks + 4 * (kBodyLayers - 1) : kAChunks + 4 * (kBodyLayers - 2 - layer);
+  const int num_stages_total = p.num_tiles * (kTileM / kDwRowsPerStage);
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kDwStages; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1 + 4);   // MMA commit + the four bias warps
+    }
+    mbar_init(bar_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < num_stages_total; ++it) {
+        const uint32_t s = it % kDwStages, ph = (it / kDwStages) & 1u;
+        const int tile = it >> 2, qr = it & 3;
+        mbar_wait(bar_empty(s), ph ^ 1u);
+        mbar_arrive_expect_tx(bar_full(s), kDwStageBytes);
+        const uint8_t* dy = p.bwd_saved + ((int64_t)tile * kBwdSavedChunks + dy_chunk0) * kAChunkBytes + qr * kDwPiece;
+        const uint8_t* x = p.fwd_saved + ((int64_t)tile * kFwdSavedChunks + x_chunk0) * kAChunkBytes + qr * kDwPiece;
+        const uint32_t dst = smem_base + s * kDwStageBytes;
+#pragma unroll
+        for (int cp = 0; cp < 8; ++cp) {   // cp = chunk*2 + plane; planes are 16 KiB apart inside a 32 KiB chunk
+          bulk_g2s(dst + cp * kDwPiece, dy + (int64_t)cp * kPlaneBytes, kDwPiece, bar_full(s));
+          bulk_g2s(dst + kDwOperand + cp * kDwPiece, x + (int64_t)cp * kPlaneBytes, kDwPiece, bar_full(s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 256, 1, 1);   // both operands MN-major
+      constexpr uint32_t kLbo = 2 * kDwPiece;   // next 64-feature group of the same plane
+      constexpr uint32_t kSbo = 1024;           // next 8 rays
+      for (int it = 0; it < num_stages_total; ++it) {
+        const uint32_t s = it % kDwStages, ph = (it / kDwStages) & 1u;
+        mbar_wait(bar_full(s), ph);
+        tc_fence_after_sync();
+        const uint32_t dy = smem_base + s * kDwStageBytes, x = dy + kDwOperand;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const uint32_t d = tmem_base + 256u * half;
+            const uint32_t a_hi = dy + (4 * half) * kDwPiece + ks * 2048, a_lo = a_hi + kDwPiece;
+            const uint32_t b_hi = x + ks * 2048, b_lo = b_hi + kDwPiece;
+            const uint32_t first = (it == 0 && ks == 0) ? 0u : 1u;
+            umma_bf16(d, umma_desc_sw128(a_hi, kLbo, kSbo), umma_desc_sw128(b_hi, kLbo, kSbo), idesc, first);
+            umma_bf16(d, umma_desc_sw128(a_lo, kLbo, kSbo), umma_desc_sw128(b_hi, kLbo, kSbo), idesc, 1u);
+            umma_bf16(d, umma_desc_sw128(a_hi, kLbo, kSbo), umma_desc_sw128(b_lo, kLbo, kSbo), idesc, 1u);
+          }
+        }
+        umma_commit(bar_empty(s));
+      }
+      umma_commit(bar_done);
+    }
+  } else if (warp >= 4) {
+    const uint32_t t = (warp - 4) * 32 + lane;   // 0..127: owns output columns 2t, 2t+1 of dY for the bias sum
+    const uint32_t c = t >> 5;                   // chunk of those columns
+    const uint32_t k = (2 * t) & 63;             // position inside the chunk
+    float s0 = 0.f, s1 = 0.f;
+    for (int it = 0; it < num_stages_total; ++it) {
+      const uint32_t s = it % kDwStages, ph = (it / kDwStages) & 1u;
+      mbar_wait(bar_full(s), ph);
+      const uint8_t* dy = smem_gen + s * kDwStageBytes;
+#pragma unroll 8
+      for (uint32_t r = 0; r < kDwRowsPerStage; ++r) {
+        const uint32_t off = r * 128u + ((((k >> 3) ^ (r & 7u)) << 4) | ((k & 7u) << 1));
+        const uint32_t hi = *reinterpret_cast<const uint32_t*>(dy + (2 * c) * kDwPiece + off);
+        const uint32_t lo = *reinterpret_cast<const uint32_t*>(dy + (2 * c + 1) * kDwPiece + off);
+        s0 += __uint_as_float(hi << 16) + __uint_as_float(lo << 16);
+        s1 += __uint_as_float(hi & 0xFFFF0000u) + __uint_as_float(lo & 0xFFFF0000u);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_empty(s));
+    }
+    // bias gradient (head groups all compute the same sum; group 0 writes it)
+    if (!is_head || hg == 0) {
+      float* db = p.grads + (is_head ? kOffHeadB : off_body_b(layer)) + 2 * t;
+      if (p.accumulate) { db[0] += s0; db[1] += s1; } else { db[0] = s0; db[1] = s1; }
+    }
+    // epilogue: both accumulators -> global
+    mbar_wait(bar_done, 0);
+    tc_fence_after_sync();
+    const uint32_t q = warp & 3;
+    const uint32_t tmem_row = tmem_base + ((q * 32u) << 16);
+    for (int half = 0; half < 2; ++half) {
+      const int o = half * 128 + q * 32 + lane;   // output feature (row of dW)
+      for (int c8 = 0; c8 < 8; ++c8) {
+        uint32_t r[32];
+        tmem_ld32(tmem_row + 256u * half + 32u * c8, r);
+        tmem_ld_wait();
+        if (!is_head) {
+          float4* dst = reinterpret_cast<float4*>(p.grads + off_body_w(layer) + (int64_t)o * kWidth + 32 * c8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 v = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                   __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+            if (p.accumulate) { const float4 a = dst[i]; v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
+            dst[i] = v;
+          }
+        } else {
+          float* dst = p.grads + kOffHeadW + (int64_t)o * kInDim;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int col = 32 * c8 + i;            // column inside this 256-feature group
+            const int chunk = 4 * hg + (col >> 6);  // K-chunk of the head GEMM
+            const int slot = col & 63;
+            const int feat = p.input_kind == kInputX ? (64 * chunk + slot < kInDim ? 64 * chunk + slot : -1)
+                                                      : fused_slot_to_feature(chunk, slot);
+            if (feat >= 0) {
+              const float v = __uint_as_float(r[i]);
+              if (p.accumulate) dst[feat] += v; else dst[feat] = v;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// tail.0.weight / tail.0.bias gradients: dW_t[c,j] = sum_n dlogit[n,c] (z_43 + h)[n,j]; 768+3 outputs, CUDA cores.
+__global__ void __launch_bounds__(256) r2l_tail_grad_kernel(const __grid_constant__ TailGradParams p) {
+  __shared__ float dl[128][3];
+  const int64_t n0 = (int64_t)blockIdx.x * 128;
+  if (threadIdx.x < 128) {
+    const int64_t n = n0 + threadIdx.x;
+    float v[3] = {0.f, 0.f, 0.f};
+    if (n < p.n_rays) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float y = p.rgb[n * 3 + c];
+        v[c] = p.grad_rgb[n * 3 + c] * y * (1.f - y);
+      }
+    }
+    dl[threadIdx.x][0] = v[0]; dl[threadIdx.x][1] = v[1]; dl[threadIdx.x][2] = v[2];
+  }
+  __syncthreads();
+  const int j = threadIdx.x;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  const int rows = (int)((p.n_rays - n0) < 128 ? (p.n_rays - n0) : 128);
+  for (int r = 0; r < rows; ++r) {
+    const float z = p.zf[(n0 + r) * kWidth + j];
+    a0 = fmaf(dl[r][0], z, a0); a1 = fmaf(dl[r][1], z, a1); a2 = fmaf(dl[r][2], z, a2);
+  }
+  atomicAdd(p.grads + kOffTailW + j, a0);
+  atomicAdd(p.grads + kOffTailW + kWidth + j, a1);
+  atomicAdd(p.grads + kOffTailW + 2 * kWidth + j, a2);
+  if (j < 3) {
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += dl[r][j];
+    atomicAdd(p.grads + kOffTailB + j, s);
+  }
+}
+
+cudaError_t launch_dw(const DwParams& p, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(r2l_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDwSmemBytes);
+  if (e != cudaSuccess) return e;
+  r2l_dw_kernel<<<kDwUnits, kDwThreads, kDwSmemBytes, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tail_grads(const TailGradParams& p, bool zero_first, cudaStream_t stream) {
+  if (zero_first) {
+    cudaError_t e = cudaMemsetAsync(p.grads + kOffTailW, 0, (kOutDim * kWidth + kOutDim) * sizeof(float), stream);
+    if (e != cudaSuccess) return e;
+  }
+  const int blocks = (int)((p.n_rays + 127) / 128);
+  r2l_tail_grad_kernel<<<blocks, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace r2l

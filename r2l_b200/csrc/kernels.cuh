@@ -7,23 +7,55 @@
 
 namespace r2l {
 
-struct FwdParams {
+enum ChainMode : int { kFwdInfer = 0, kFwdTrain = 1, kBwd = 2 };
+
+struct ChainParams {
+  // forward inputs
   const float* in0;       // rays_o[N,3] | pts[N,48] | x[N,1008]
   const float* in1;       // rays_d[N,3] | unused
   const float* t_rand;    // [N,16] or nullptr (kInputRays only)
   float z_lo[kSamples];   // z_vals (no jitter) or `lower` (jitter)
   float z_diff[kSamples]; // `upper - lower` (jitter)
   const uint8_t* packed;
-  float* rgb;             // [N,3]
-  float* h_scratch;       // [gridDim.x][128][256] fp32: head output kept for the outer residual
+  float* rgb;             // forward out [N,3]
+  float* scratch;         // [gridDim.x][128][256] fp32: head output (fwd) / dL/dz_43 (bwd) for the outer skip
   long long* stats;       // optional [gridDim.x][8] cycle counters (debug), nullptr in production
+  // training
+  uint8_t* saved;         // out: operand images this pass stores, [tile][chunk][32 KiB]
+  float* zf_out;          // kFwdTrain out: z_43 + h, [N,256] fp32
+  const uint8_t* fwd_saved;  // kBwd in: the forward pass's `saved`
+  const float* rgb_in;    // kBwd in: forward rgb [N,3]
+  const float* grad_rgb;  // kBwd in: dL/d rgb [N,3]
   int64_t n_rays;
   int num_tiles;
   int input_kind;
 };
 
+// saved operand images per 128-ray tile (32 KiB chunks)
+constexpr int kFwdSavedChunks = kSamples + 4 * kBodyLayers;   // 16 PE chunks + input of each body Linear
+constexpr int kBwdSavedChunks = kAChunks + 4 * kBodyLayers;   // dL/dz_43 + output gradient of each body Linear (+ head)
+
+struct DwParams {
+  const uint8_t* fwd_saved;
+  const uint8_t* bwd_saved;
+  float* grads;           // flat [kNumParams]; weight blocks are overwritten, (or accumulated when `accumulate`)
+  int num_tiles;
+  int input_kind;         // kInputX: head features in natural order, else fused-PE order
+  int accumulate;
+};
+
+struct TailGradParams {
+  const float* zf;        // [N,256]
+  const float* rgb;       // [N,3]
+  const float* grad_rgb;  // [N,3]
+  float* grads;           // flat; tail.0.weight / tail.0.bias accumulated atomically
+  int64_t n_rays;
+};
+
 cudaError_t launch_pack(const float* params, void* packed, cudaStream_t stream);
-cudaError_t launch_fwd(const FwdParams& p, int grid, cudaStream_t stream);
+cudaError_t launch_chain(int mode, const ChainParams& p, int grid, cudaStream_t stream);
+cudaError_t launch_dw(const DwParams& p, cudaStream_t stream);
+cudaError_t launch_tail_grads(const TailGradParams& p, bool zero_first, cudaStream_t stream);
 cudaError_t launch_umma_selftest(const float* A, const void* images, float* C, cudaStream_t stream);
 
 }  // namespace r2l

@@ -110,3 +110,75 @@ def selftest_layer(a: torch.Tensor, packed: torch.Tensor, layer: int) -> torch.T
     with torch.cuda.device(a.device):
         _lib.check(_lib.lib().r2l_selftest_layer(_ptr(a), _ptr(packed), layer, _ptr(c), _stream()), "r2l_selftest_layer")
     return c
+
+
+# ------------------------------------------------------------------------------------------------
+# training: fused forward that keeps the tensor-core operand images, fused backward
+# ------------------------------------------------------------------------------------------------
+class TrainContext:
+    """Everything r2l_backward needs from the forward pass (device buffers owned by torch)."""
+    __slots__ = ("kind", "n", "rgb", "zf", "fwd_saved")
+
+
+def _resolve_inputs(rays_o, rays_d, z_vals, t_rand, z_lower, z_diff, pts, x):
+    zl = zd = None
+    if x is not None:
+        kind, in0, in1 = INPUT_X, _require_cuda_f32(x, "x", (IN_DIM,)), None
+    elif pts is not None:
+        kind, in0, in1 = INPUT_PTS, _require_cuda_f32(pts, "pts", (3 * N_SAMPLES,)), None
+    else:
+        kind = INPUT_RAYS
+        in0 = _require_cuda_f32(rays_o, "rays_o", (3,))
+        in1 = _require_cuda_f32(rays_d, "rays_d", (3,))
+        if in0.shape != in1.shape:
+            raise ValueError("rays_o / rays_d shape mismatch")
+        if t_rand is not None:
+            t_rand = _require_cuda_f32(t_rand, "t_rand", (N_SAMPLES,))
+            if t_rand.shape[0] != in0.shape[0]:
+                raise ValueError("t_rand: wrong number of rays")
+            zl = (ctypes.c_float * N_SAMPLES)(*[float(v) for v in z_lower])
+            zd = (ctypes.c_float * N_SAMPLES)(*[float(v) for v in z_diff])
+        else:
+            zl = (ctypes.c_float * N_SAMPLES)(*[float(v) for v in z_vals])
+    return kind, in0, in1, t_rand, zl, zd
+
+
+def forward_train(packed: torch.Tensor, *, rays_o=None, rays_d=None, z_vals=None, t_rand=None, z_lower=None,
+                  z_diff=None, pts=None, x=None):
+    """Like forward(), but also returns the TrainContext for backward()."""
+    L = _lib.lib()
+    kind, in0, in1, t_rand, zl, zd = _resolve_inputs(rays_o, rays_d, z_vals, t_rand, z_lower, z_diff, pts, x)
+    n, dev = in0.shape[0], in0.device
+    ctx = TrainContext()
+    ctx.kind, ctx.n = kind, n
+    ctx.rgb = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    ctx.zf = torch.empty((n, 256), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ctx.fwd_saved = torch.empty(int(L.r2l_train_fwd_saved_bytes(n)), dtype=torch.uint8, device=dev)
+        wbytes = int(L.r2l_fwd_workspace_bytes(n))
+        ws = _workspace(dev, wbytes)
+        _lib.check(L.r2l_forward_train(kind, _ptr(in0), _ptr(in1), _ptr(t_rand), zl, zd, _ptr(packed), _ptr(ctx.rgb),
+                                       _ptr(ctx.zf), _ptr(ctx.fwd_saved), _ptr(ws), wbytes, n, _stream()),
+                   "r2l_forward_train")
+    return ctx.rgb, ctx
+
+
+def backward(packed: torch.Tensor, ctx: TrainContext, grad_rgb: torch.Tensor, grads: torch.Tensor | None = None) -> torch.Tensor:
+    """dL/dparams (flat, state_dict order) for dL/drgb = grad_rgb.  `grads` is overwritten if given."""
+    L = _lib.lib()
+    grad_rgb = _require_cuda_f32(grad_rgb, "grad_rgb", (3,))
+    if grad_rgb.shape[0] != ctx.n:
+        raise ValueError("grad_rgb: wrong number of rays")
+    dev = grad_rgb.device
+    if grads is None:
+        grads = torch.empty(NUM_PARAMS, dtype=torch.float32, device=dev)
+    elif grads.numel() != NUM_PARAMS or grads.dtype != torch.float32 or not grads.is_contiguous() or grads.device != dev:
+        raise ValueError("grads: expected a contiguous float32 CUDA tensor of NUM_PARAMS elements")
+    with torch.cuda.device(dev):
+        bwd_saved = torch.empty(int(L.r2l_train_bwd_saved_bytes(ctx.n)), dtype=torch.uint8, device=dev)
+        wbytes = int(L.r2l_fwd_workspace_bytes(ctx.n))
+        ws = _workspace(dev, wbytes)
+        _lib.check(L.r2l_backward(ctx.kind, _ptr(packed), _ptr(ctx.rgb), _ptr(grad_rgb), _ptr(ctx.zf),
+                                  _ptr(ctx.fwd_saved), _ptr(bwd_saved), _ptr(grads), _ptr(ws), wbytes, ctx.n,
+                                  _stream()), "r2l_backward")
+    return grads
