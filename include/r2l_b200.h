@@ -61,6 +61,16 @@ int r2l_backward(int input_kind, const void* packed, const float* rgb, const flo
                  const void* fwd_saved, void* bwd_saved, float* grads, void* workspace, size_t workspace_bytes,
                  int64_t n_rays, void* stream);
 
+/* raw2outputs (nerf_raybased.py:226-295, raw_noise_std = 0): raw[N,S,4], z_vals[N,S], rays_d[N,3] ->
+ * rgb_map[N,3], disp_map[N], acc_map[N], weights[N,S], depth_map[N].  One warp per ray, one pass over HBM. */
+int r2l_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, int64_t n_rays, int n_samples,
+                    int white_bkgd, float* rgb_map, float* disp_map, float* acc_map, float* weights, float* depth_map,
+                    void* stream);
+
+/* Dense positional encoding x[N,dim] -> out[N, dim*(2*n_freqs+1)].
+ * style 0: PositionalEmbedder.__call__ (:198-208) layout; style 1: Embedder.embed (:54-55, get_embedder :58-73) layout. */
+int r2l_positional_embed(const float* x, float* out, int64_t n, int dim, int n_freqs, int style, void* stream);
+
 /* Debug: device buffer [grid][8] of int64 cycle counters filled by the next r2l_forward calls (NULL = off):
  * [0] MMA wait on head A chunks, [1] on body A chunks, [2] on weight stages, [3] producer wait on free stages,
  * [4] MMA-thread total. */

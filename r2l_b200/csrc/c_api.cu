@@ -165,6 +165,26 @@ int r2l_backward(int input_kind, const void* packed, const float* rgb, const flo
   return check(r2l::launch_tail_grads(t, true, st), "r2l_backward(tail)");
 }
 
+int r2l_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, int64_t n_rays, int n_samples,
+                    int white_bkgd, float* rgb_map, float* disp_map, float* acc_map, float* weights, float* depth_map,
+                    void* stream) {
+  if (n_rays == 0) return 0;
+  if (n_rays < 0 || n_samples <= 0) return fail("r2l_raw2outputs: %s", "bad sizes");
+  if (!raw || !z_vals || !rays_d || !rgb_map || !disp_map || !acc_map || !weights || !depth_map)
+    return fail("r2l_raw2outputs: %s", "null pointer");
+  if (misaligned(raw)) return fail("r2l_raw2outputs: %s", "raw must be 16-byte aligned");
+  return check(r2l::launch_raw2outputs(raw, z_vals, rays_d, n_rays, n_samples, white_bkgd, rgb_map, disp_map, acc_map,
+                                       weights, depth_map, (cudaStream_t)stream), "r2l_raw2outputs");
+}
+
+int r2l_positional_embed(const float* x, float* out, int64_t n, int dim, int n_freqs, int style, void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || dim <= 0 || n_freqs <= 0 || n_freqs > 24 || (style != 0 && style != 1))
+    return fail("r2l_positional_embed: %s", "bad arguments");
+  if (!x || !out) return fail("r2l_positional_embed: %s", "null pointer");
+  return check(r2l::launch_embed(x, out, n, dim, n_freqs, style, (cudaStream_t)stream), "r2l_positional_embed");
+}
+
 int r2l_debug_set_stats(long long* stats) {
   g_stats = stats;
   return 0;

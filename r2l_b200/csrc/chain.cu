@@ -240,19 +240,29 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
   } else if (warp == 3) {
     // ======================= operand-image store warp (train / bwd) =======================
     if (kSave && lane == 0) {
+      // Up to four 32 KiB stores in flight: chunk i's slot is released (kBarASaved) once store i has finished
+      // READING shared memory, which we learn when at most 3 younger bulk groups are still pending.  The
+      // epilogue rewrites a slot exactly 4 chunks after it published it, so this lag can never deadlock.
       uint32_t a_phase = 0;
+      int64_t issued = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         uint8_t* dst = p.saved + (int64_t)tile * kSavedChunksPerTile * kAChunkBytes;
-        for (int i = 0; i < kSavedChunksPerTile; ++i) {
+        for (int i = 0; i < kSavedChunksPerTile; ++i, ++issued) {
           const uint32_t slot = i & 3;   // first chunks cycle the ring; body chunk c lives in slot c
           mbar_wait(bar(kBarAFull + slot), (a_phase >> slot) & 1u);
           a_phase ^= 1u << slot;
           bulk_s2g(dst + (int64_t)i * kAChunkBytes, smem_base + kSmemA + slot * kAChunkBytes, kAChunkBytes);
           bulk_commit();
-          bulk_wait_read<0>();           // smem has been read: the slot may be rewritten
-          mbar_arrive(bar(kBarASaved + slot));
+          if (issued >= 3) {
+            bulk_wait_read<3>();         // store (issued - 3) has read its slot
+            mbar_arrive(bar(kBarASaved + ((slot + 1) & 3)));
+          }
         }
       }
+      // drain: release the last three slots in issue order, then wait for the writes to land
+      const int64_t tail = issued < 3 ? issued : 3;
+      bulk_wait_read<0>();
+      for (int64_t k = 0; k < tail; ++k) mbar_arrive(bar(kBarASaved + (uint32_t)((issued - tail + k) & 3)));
       bulk_wait_all<0>();
     }
   } else if (warp >= 4) {
@@ -372,9 +382,6 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
       // ---- layer epilogues ----
       float dot0 = 0.f, dot1 = 0.f, dot2 = 0.f;
       for (int l = 0; l < kLayers; ++l) {
-        mbar_wait(bar(kBarAccFull), acc_phase);
-        acc_phase ^= 1u;
-        tc_fence_after_sync();
         const bool from_h = kIsBwd ? ((l & 1) == 0) : ((l & 1) != 0);
         const bool last = l == kLayers - 1;
         // forward tables
@@ -386,26 +393,46 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
         //   even j (da -> dh): a_k with k = 42 - j/2, forward saved chunk index 16 + 4*(2k+1) + c
         //   last (j = 85):     h (= A_z(0), forward saved chunks 16 + c), applied to g_0 + dL/dz_43
         const uint8_t* mask_img = nullptr;
+        const bool masked = kIsBwd && (from_h || last);
         if constexpr (kIsBwd) {
           const int k = (kBlocks - 1) - (l >> 1);
-          const int64_t fwd_chunks_per_tile = kSamples + 4 * kBodyLayers;
           const int64_t chunk0 = from_h ? (kSamples + 4 * (2 * k + 1)) : kSamples;
-          mask_img = p.fwd_saved + ((int64_t)tile * fwd_chunks_per_tile + chunk0) * kAChunkBytes;
+          mask_img = p.fwd_saved + ((int64_t)tile * kFwdSavedChunks + chunk0) * kAChunkBytes;
         }
+        // Chunk 0 sits on the critical path between two GEMMs: fetch its bias / mask while the MMAs still run.
+        float4 bq[8];
+        uint4 mq[4];
+        auto load_side = [&](int c) {
+          if constexpr (!kIsBwd) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) bq[i] = __ldg(reinterpret_cast<const float4*>(bias + 64 * c + 32 * hf) + i);
+          } else {
+            if (masked) {
+              const uint8_t* plane = mask_img + (int64_t)c * kAChunkBytes;
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj)
+                mq[jj] = __ldg(reinterpret_cast<const uint4*>(plane + row * 128u + (((4u * hf + jj) ^ (row & 7u)) << 4)));
+            }
+          }
+        };
+        load_side(0);
+        mbar_wait(bar(kBarAccFull), acc_phase);
+        acc_phase ^= 1u;
+        tc_fence_after_sync();
         for (int c = 0; c < kAChunks; ++c) {
           const uint32_t col = 64u * c + 32u * hf;
           uint32_t r[32];
           tmem_ld32(tmem_row + (from_h ? kTmemH : kTmemZ) + col, r);
+          if (c > 0) load_side(c);
           tmem_ld_wait();
           float v[32];
           if constexpr (!kIsBwd) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col) + i);
-              v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + b4.x;
-              v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b4.y;
-              v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b4.z;
-              v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b4.w;
+              v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + bq[i].x;
+              v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bq[i].y;
+              v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bq[i].z;
+              v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bq[i].w;
             }
             if (relu) {
 #pragma unroll
@@ -431,16 +458,13 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
                 v[4 * i] += g4.x; v[4 * i + 1] += g4.y; v[4 * i + 2] += g4.z; v[4 * i + 3] += g4.w;
               }
             }
-            if (from_h || last) {
-              // ReLU mask from the hi plane of the saved forward operand (a > 0  <=>  bf16 hi > 0)
-              const uint8_t* plane = mask_img + (int64_t)c * kAChunkBytes;
+            if (masked) {
+              // ReLU mask from the hi plane of the saved forward operand (a > 0  <=>  bf16 hi != 0; a >= 0 always)
 #pragma unroll
               for (int jj = 0; jj < 4; ++jj) {
-                const uint4 m = __ldg(reinterpret_cast<const uint4*>(plane + row * 128u + (((4u * hf + jj) ^ (row & 7u)) << 4)));
-                const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+                const uint32_t w[4] = {mq[jj].x, mq[jj].y, mq[jj].z, mq[jj].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  // a >= 0 always, so "positive" == non-zero bf16 bits (ignoring the sign bit of -0)
                   if ((w[e] & 0x00007FFFu) == 0u) v[8 * jj + 2 * e] = 0.f;
                   if ((w[e] & 0x7FFF0000u) == 0u) v[8 * jj + 2 * e + 1] = 0.f;
                 }

@@ -56,6 +56,10 @@ cudaError_t launch_pack(const float* params, void* packed, cudaStream_t stream);
 cudaError_t launch_chain(int mode, const ChainParams& p, int grid, cudaStream_t stream);
 cudaError_t launch_dw(const DwParams& p, cudaStream_t stream);
 cudaError_t launch_tail_grads(const TailGradParams& p, bool zero_first, cudaStream_t stream);
+cudaError_t launch_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, int64_t n_rays, int n_samples,
+                               int white_bkgd, float* rgb_map, float* disp_map, float* acc_map, float* weights,
+                               float* depth_map, cudaStream_t stream);
+cudaError_t launch_embed(const float* x, float* out, int64_t n, int dim, int L, int style, cudaStream_t stream);
 cudaError_t launch_umma_selftest(const float* A, const void* images, float* C, cudaStream_t stream);
 
 }  // namespace r2l

@@ -337,3 +337,73 @@ class NeRF_v3_2(nn.Module):
             from .autograd import r2l_apply  # training path (fused backward)
             return r2l_apply(self, inputs)
         return ops.forward(self.packed_weights(), **inputs)
+
+
+# ------------------------------------------------------------------------------------------------
+# teacher-side surface: Embedder / get_embedder / batchify / run_network / raw2outputs (reference :23-73, :226-334)
+# ------------------------------------------------------------------------------------------------
+class Embedder:
+    """NeRF positional encoding [x, sin(2^0 x), cos(2^0 x), ..., cos(2^(L-1) x)] (reference :23-55).
+    CUDA float32 inputs run the one-pass encoding kernel; anything else uses the same torch ops as the reference."""
+
+    def __init__(self, **kwargs):
+        self.kwargs = kwargs
+        d = kwargs["input_dims"]
+        self.n_freqs = kwargs["num_freqs"]
+        max_freq = kwargs["max_freq_log2"]
+        if kwargs["log_sampling"]:
+            self.freq_bands = 2. ** torch.linspace(0., max_freq, steps=self.n_freqs)
+        else:
+            self.freq_bands = torch.linspace(2. ** 0., 2. ** max_freq, steps=self.n_freqs)
+        self.out_dim = d * (int(kwargs["include_input"]) + 2 * self.n_freqs)
+        self._kernel_ok = (kwargs["include_input"] and kwargs["log_sampling"] and max_freq == self.n_freqs - 1
+                           and list(kwargs["periodic_fns"]) == [torch.sin, torch.cos])
+
+    def embed(self, inputs):
+        if self._kernel_ok and inputs.is_cuda and inputs.dtype == torch.float32:
+            return ops.positional_embed(inputs, self.n_freqs, style=1)
+        parts = [inputs] if self.kwargs["include_input"] else []
+        for freq in self.freq_bands:
+            for fn in self.kwargs["periodic_fns"]:
+                parts.append(fn(inputs * freq))
+        return torch.cat(parts, -1)
+
+
+def get_embedder(multires, i=0):
+    if i == -1:
+        return nn.Identity(), 3
+    eo = Embedder(include_input=True, input_dims=3, max_freq_log2=multires - 1, num_freqs=multires,
+                  log_sampling=True, periodic_fns=[torch.sin, torch.cos])
+    return (lambda x, eo=eo: eo.embed(x)), eo.out_dim
+
+
+def batchify(fn, chunk):
+    """Apply `fn` in slices of `chunk` rows (reference :298-309)."""
+    if chunk is None:
+        return fn
+    return lambda inputs: torch.cat([fn(inputs[i:i + chunk]) for i in range(0, inputs.shape[0], chunk)], 0)
+
+
+def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64):
+    """Embed points (and view directions) and apply the network (reference :312-334)."""
+    flat = torch.reshape(inputs, [-1, inputs.shape[-1]])
+    embedded = embed_fn(flat)
+    if viewdirs is not None:
+        dirs = viewdirs[:, None].expand(inputs.shape)
+        embedded = torch.cat([embedded, embeddirs_fn(torch.reshape(dirs, [-1, dirs.shape[-1]]))], -1)
+    out = batchify(fn, netchunk)(embedded)
+    return torch.reshape(out, list(inputs.shape[:-1]) + [out.shape[-1]])
+
+
+def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkgd=False, pytest=False, global_step=-1, print=print):
+    """Alpha compositing of the teacher's raw predictions (reference :226-295) in one warp-per-ray kernel.
+    Returns rgb_map, disp_map, acc_map, weights, depth_map."""
+    if raw_noise_std > 0.:
+        raise NotImplementedError("r2l_b200 raw2outputs: raw_noise_std > 0 is not implemented (the README teacher flow uses 0)")
+    outs = ops.raw2outputs(raw, z_vals.expand(raw.shape[0], raw.shape[1]), rays_d, white_bkgd)
+    if global_step % 100 == 0:  # the reference's periodic alpha dump (:275-279)
+        dists = torch.cat([z_vals[..., 1:] - z_vals[..., :-1], torch.full_like(z_vals[..., :1], 1e10)], -1)
+        alpha = 1. - torch.exp(-torch.relu(raw[..., 3]) * dists * torch.norm(rays_d[..., None, :], dim=-1))
+        for i_ray in range(0, alpha.shape[0], 100):
+            print('%4d: ' % i_ray + ' '.join('%.4f' % v for v in alpha[i_ray]))
+    return outs

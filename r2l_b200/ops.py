@@ -117,7 +117,24 @@ def selftest_layer(a: torch.Tensor, packed: torch.Tensor, layer: int) -> torch.T
 # ------------------------------------------------------------------------------------------------
 class TrainContext:
     """Everything r2l_backward needs from the forward pass (device buffers owned by torch)."""
-    __slots__ = ("kind", "n", "rgb", "zf", "fwd_saved")
+    __slots__ = ("kind", "n", "rgb", "zf", "fwd_saved", "generation", "device_index")
+
+
+# The saved operand images are large (86 KiB per ray and pass).  By default they live in one grow-only buffer
+# per device that the next forward_train() reuses, so a training loop does no cudaMalloc; a context whose
+# buffer has been reused refuses to run backward.  forward_train(..., keep=True) gives a private buffer.
+_saved_pool: dict = {}
+_generation: dict = {}
+
+
+def _pooled(device, tag: str, nbytes: int) -> torch.Tensor:
+    key = (device.index, tag)
+    buf = _saved_pool.get(key)
+    if buf is None or buf.numel() < nbytes:
+        _saved_pool[key] = None
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _saved_pool[key] = buf
+    return buf
 
 
 def _resolve_inputs(rays_o, rays_d, z_vals, t_rand, z_lower, z_diff, pts, x):
@@ -144,7 +161,7 @@ def _resolve_inputs(rays_o, rays_d, z_vals, t_rand, z_lower, z_diff, pts, x):
 
 
 def forward_train(packed: torch.Tensor, *, rays_o=None, rays_d=None, z_vals=None, t_rand=None, z_lower=None,
-                  z_diff=None, pts=None, x=None):
+                  z_diff=None, pts=None, x=None, keep: bool = False):
     """Like forward(), but also returns the TrainContext for backward()."""
     L = _lib.lib()
     kind, in0, in1, t_rand, zl, zd = _resolve_inputs(rays_o, rays_d, z_vals, t_rand, z_lower, z_diff, pts, x)
@@ -154,7 +171,13 @@ def forward_train(packed: torch.Tensor, *, rays_o=None, rays_d=None, z_vals=None
     ctx.rgb = torch.empty((n, 3), dtype=torch.float32, device=dev)
     ctx.zf = torch.empty((n, 256), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        ctx.fwd_saved = torch.empty(int(L.r2l_train_fwd_saved_bytes(n)), dtype=torch.uint8, device=dev)
+        nsaved = int(L.r2l_train_fwd_saved_bytes(n))
+        if keep:
+            ctx.fwd_saved, ctx.generation = torch.empty(nsaved, dtype=torch.uint8, device=dev), None
+        else:
+            ctx.fwd_saved = _pooled(dev, "fwd", nsaved)
+            ctx.generation = _generation[dev.index] = _generation.get(dev.index, 0) + 1
+        ctx.device_index = dev.index
         wbytes = int(L.r2l_fwd_workspace_bytes(n))
         ws = _workspace(dev, wbytes)
         _lib.check(L.r2l_forward_train(kind, _ptr(in0), _ptr(in1), _ptr(t_rand), zl, zd, _ptr(packed), _ptr(ctx.rgb),
@@ -170,15 +193,53 @@ def backward(packed: torch.Tensor, ctx: TrainContext, grad_rgb: torch.Tensor, gr
     if grad_rgb.shape[0] != ctx.n:
         raise ValueError("grad_rgb: wrong number of rays")
     dev = grad_rgb.device
+    if ctx.generation is not None and _generation.get(ctx.device_index) != ctx.generation:
+        raise RuntimeError("this TrainContext's saved activations were overwritten by a later forward_train(); "
+                           "run backward first or use forward_train(..., keep=True)")
     if grads is None:
         grads = torch.empty(NUM_PARAMS, dtype=torch.float32, device=dev)
     elif grads.numel() != NUM_PARAMS or grads.dtype != torch.float32 or not grads.is_contiguous() or grads.device != dev:
         raise ValueError("grads: expected a contiguous float32 CUDA tensor of NUM_PARAMS elements")
     with torch.cuda.device(dev):
-        bwd_saved = torch.empty(int(L.r2l_train_bwd_saved_bytes(ctx.n)), dtype=torch.uint8, device=dev)
+        bwd_saved = _pooled(dev, "bwd", int(L.r2l_train_bwd_saved_bytes(ctx.n)))
         wbytes = int(L.r2l_fwd_workspace_bytes(ctx.n))
         ws = _workspace(dev, wbytes)
         _lib.check(L.r2l_backward(ctx.kind, _ptr(packed), _ptr(ctx.rgb), _ptr(grad_rgb), _ptr(ctx.zf),
                                   _ptr(ctx.fwd_saved), _ptr(bwd_saved), _ptr(grads), _ptr(ws), wbytes, ctx.n,
                                   _stream()), "r2l_backward")
     return grads
+
+
+# ------------------------------------------------------------------------------------------------
+# compositing and dense encodings
+# ------------------------------------------------------------------------------------------------
+def raw2outputs(raw: torch.Tensor, z_vals: torch.Tensor, rays_d: torch.Tensor, white_bkgd: bool = False):
+    """(rgb_map, disp_map, acc_map, weights, depth_map) of reference raw2outputs with raw_noise_std = 0."""
+    raw = _require_cuda_f32(raw, "raw")
+    if raw.dim() != 3 or raw.shape[-1] != 4:
+        raise ValueError(f"raw: expected [N,S,4], got {tuple(raw.shape)}")
+    n, s = raw.shape[0], raw.shape[1]
+    z_vals = _require_cuda_f32(z_vals, "z_vals", (s,))
+    rays_d = _require_cuda_f32(rays_d, "rays_d", (3,))
+    if z_vals.shape[0] != n or rays_d.shape[0] != n:
+        raise ValueError("raw / z_vals / rays_d disagree on the number of rays")
+    dev = raw.device
+    rgb = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    disp, acc, depth = (torch.empty((n,), dtype=torch.float32, device=dev) for _ in range(3))
+    weights = torch.empty((n, s), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().r2l_raw2outputs(_ptr(raw), _ptr(z_vals), _ptr(rays_d), n, s, int(bool(white_bkgd)), _ptr(rgb),
+                                              _ptr(disp), _ptr(acc), _ptr(weights), _ptr(depth), _stream()), "r2l_raw2outputs")
+    return rgb, disp, acc, weights, depth
+
+
+def positional_embed(x: torch.Tensor, n_freqs: int, style: int) -> torch.Tensor:
+    """Dense encoding of x[..., dim]: style 0 = PositionalEmbedder layout, 1 = Embedder (teacher) layout."""
+    x = _require_cuda_f32(x, "x")
+    dim = x.shape[-1]
+    flat = x.reshape(-1, dim).contiguous()
+    out = torch.empty((flat.shape[0], dim * (2 * n_freqs + 1)), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().r2l_positional_embed(_ptr(flat), _ptr(out), flat.shape[0], dim, n_freqs, style, _stream()),
+                   "r2l_positional_embed")
+    return out.view(*x.shape[:-1], out.shape[-1])

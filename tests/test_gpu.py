@@ -1,0 +1,227 @@
+"""GPU parity tests (run on the B200 with `-m gpu`): the CUDA path through the C ABI against the numpy oracle and
+the reference-generated golden fixtures.  Tolerances: forward rgb 1e-3 max relative (BASELINE.json north_star);
+gradients are judged against the fp64 evaluation, see each test."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import r2l_oracle as orc  # noqa: E402
+from r2l_b200 import ops  # noqa: E402
+from r2l_b200 import nerf_raybased as nb  # noqa: E402
+
+DEV = "cuda:0"
+FWD_TOL = 1e-3
+
+
+def relerr(a, b):
+    return float(np.max(np.abs(a - b) / np.abs(b)))
+
+
+@pytest.fixture(scope="module")
+def packed(flat_seed0):
+    return ops.pack_weights(torch.from_numpy(flat_seed0).to(DEV))
+
+
+def test_extension_is_the_loaded_native_library():
+    from r2l_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH)
+    assert _lib.lib().r2l_abi_version() == 1
+
+
+def test_single_layer_tcgen05_selftest(flat_seed0, packed):
+    torch.manual_seed(5)
+    a = torch.randn(128, 256)
+    for layer in (0, 41, 85):
+        c = ops.selftest_layer(a.to(DEV), packed, layer).cpu().numpy()
+        w = orc.unflatten_params(flat_seed0)["body"][layer][0].astype(np.float64)
+        ref = a.numpy().astype(np.float64) @ w.T
+        assert np.abs(c - ref).max() / np.abs(ref).max() < 2e-5
+
+
+def test_forward_golden_all_input_forms(golden_r2l, packed):
+    g = golden_r2l
+    ro, rd = torch.from_numpy(g["rays_o"]).to(DEV), torch.from_numpy(g["rays_d"]).to(DEV)
+    assert relerr(ops.forward(packed, rays_o=ro, rays_d=rd, z_vals=g["z_vals"].tolist()).cpu().numpy(), g["rgb"]) < FWD_TOL
+    assert relerr(ops.forward(packed, pts=torch.from_numpy(g["pts"]).to(DEV)).cpu().numpy(), g["rgb"]) < FWD_TOL
+    assert relerr(ops.forward(packed, x=torch.from_numpy(g["x_embed"]).to(DEV)).cpu().numpy(), g["rgb"]) < FWD_TOL
+    lo, df = orc.jitter_bounds(g["z_vals"])
+    out = ops.forward(packed, rays_o=ro, rays_d=rd, t_rand=torch.from_numpy(g["t_rand"]).to(DEV), z_lower=lo.tolist(), z_diff=df.tolist())
+    assert relerr(out.cpu().numpy(), g["rgb_jit"]) < FWD_TOL
+    out = ops.forward(packed, pts=torch.from_numpy(g["pts_test_pix"]).to(DEV))
+    assert relerr(out.cpu().numpy(), g["rgb_test_pix"]) < FWD_TOL
+    # and it is closer to the fp64 truth than the tolerance by a wide margin
+    assert relerr(ops.forward(packed, pts=torch.from_numpy(g["pts"]).to(DEV)).cpu().numpy(), g["rgb_f64"]) < 2e-4
+
+
+@pytest.mark.parametrize("n", [1, 2, 127, 128, 129, 1000, 4096])
+def test_forward_ragged_sizes_vs_oracle(n, flat_seed0, packed):
+    torch.manual_seed(n)
+    o, d = torch.randn(n, 3) * 0.5, torch.randn(n, 3)
+    z = orc.sampler_z_vals(2.0, 6.0)
+    rgb = ops.forward(packed, rays_o=o.to(DEV), rays_d=d.to(DEV), z_vals=z.tolist()).cpu().numpy()
+    m = min(n, 640)
+    ref = orc.r2l_forward(flat_seed0, orc.positional_embed(orc.sample_train(o.numpy()[-m:], d.numpy()[-m:], z, None)))
+    assert np.isfinite(rgb).all() and relerr(rgb[-m:], ref) < FWD_TOL
+
+
+def test_forward_empty_batch(packed):
+    out = ops.forward(packed, rays_o=torch.zeros(0, 3, device=DEV), rays_d=torch.zeros(0, 3, device=DEV), z_vals=[0.] * 16)
+    assert out.shape == (0, 3)
+
+
+def test_forward_full_frame_properties(packed):
+    """BASELINE config 2 size (400x400 frame = 160,000 rays): size-independent properties.
+    Every ray is independent of its position in the batch and of the batch size (tile / CTA assignment)."""
+    nb.device = torch.device(DEV)
+    ps = nb.PointSampler(400, 400, 555.5555155968841, 16, 2.0, 6.0)
+    c2w = torch.tensor([[-0.9, 0.1, -0.4, -1.6], [-0.4, -0.3, 0.85, 3.4], [0.0, 0.95, 0.33, 1.3]], device=DEV)
+    pts = ps.sample_test(c2w)
+    assert pts.shape == (160000, 48)
+    full = ops.forward(packed, pts=pts)
+    assert torch.isfinite(full).all() and float(full.min()) > 0 and float(full.max()) < 1
+    again = ops.forward(packed, pts=pts)
+    assert torch.equal(full, again)                       # deterministic
+    idx = torch.randperm(160000, device=DEV)[:5000]
+    sub = ops.forward(packed, pts=pts[idx].contiguous())
+    assert torch.equal(sub, full[idx])                    # bit-identical regardless of tile position
+    flipped = ops.forward(packed, pts=pts.flip(0).contiguous()).flip(0)
+    assert torch.equal(flipped, full)
+    # the materialised-encoding entry point agrees with the fused encoder
+    x = nb.PositionalEmbedder(10).encode_dense(pts[:4096]).view(4096, -1)
+    assert float(((ops.forward(packed, x=x) - full[:4096]).abs() / full[:4096]).max()) < 2e-4
+
+
+def _grad_report(ours, g64):
+    return float(np.linalg.norm(ours - g64) / np.linalg.norm(g64))
+
+
+def test_backward_golden_vs_fp64(golden_r2l, flat_seed0, packed):
+    """200 golden rays.  The reference's own fp32 autograd is 6.8e-4 (flat Frobenius) from the fp64 truth on this
+    batch; the bf16x3 tensor-core path must stay within 8x of that and below 5e-3 (per-ray rounding noise averages
+    out with batch size, see the 4096-ray test for the tolerance at the BASELINE batch)."""
+    g = golden_r2l
+    ro, rd = torch.from_numpy(g["rays_o"]).to(DEV), torch.from_numpy(g["rays_d"]).to(DEV)
+    tgt = torch.from_numpy(g["target"]).to(DEV)
+    rgb, ctx = ops.forward_train(packed, rays_o=ro, rays_d=rd, z_vals=g["z_vals"].tolist())
+    assert relerr(rgb.cpu().numpy(), g["rgb"]) < FWD_TOL
+    grads = ops.backward(packed, ctx, (2.0 / 600) * (rgb - tgt)).cpu().numpy().astype(np.float64)
+    sub = grads[g["grad_idx"]]
+    err = np.linalg.norm(sub - g["grad_f64_sub"]) / np.linalg.norm(g["grad_f64_sub"])
+    assert err < 8 * float(g["grad_f32_vs_f64_rel"]) and err < 5e-3
+    layout = {n: (o, int(np.prod(s))) for n, s, o in nb.state_dict_layout()}
+    for name in ("tail.0.weight", "tail.0.bias"):
+        o, n = layout[name]
+        assert _grad_report(grads[o:o + n], g["g64_" + name]) < 1e-3
+    for name in ("head.0.bias", "body.0.body.0.bias", "body.42.body.2.bias", "body.20.body.0.bias"):
+        o, n = layout[name]
+        assert _grad_report(grads[o:o + n], g["g64_" + name]) < 2e-2
+
+
+@pytest.mark.parametrize("n", [1000, 4096])
+def test_backward_vs_fp64_autograd(n, flat_seed0, packed):
+    """Gradient parity at the BASELINE batch: flat-buffer Frobenius error vs the fp64 autograd of the same network
+    <= 1e-3 at 4096 rays and every tensor within 4e-3."""
+    from oracle.torch_reference import RefR2L, embed, sample
+    torch.manual_seed(n)
+    o, d, t = (torch.randn(n, 3) * 0.5).to(DEV), torch.randn(n, 3).to(DEV), torch.rand(n, 3).to(DEV)
+    zt = torch.from_numpy(orc.sampler_z_vals(2.0, 6.0)).to(DEV)
+    rgb, ctx = ops.forward_train(packed, rays_o=o, rays_d=d, z_vals=zt.tolist())
+    grads = ops.backward(packed, ctx, (2.0 / (3 * n)) * (rgb - t)).double()
+    ref = RefR2L().load_flat(torch.from_numpy(flat_seed0)).double().to(DEV)
+    ((ref(embed(sample(o, d, zt)).double()) - t.double()) ** 2).mean().backward()
+    g64 = ref.flat_grads()
+    flat_err = float((grads - g64).norm() / g64.norm())
+    assert flat_err < (1e-3 if n >= 4096 else 2e-3), flat_err
+    worst = 0.0
+    for name, shape, off in nb.state_dict_layout():
+        k = int(np.prod(shape))
+        worst = max(worst, float((grads[off:off + k] - g64[off:off + k]).norm() / g64[off:off + k].norm()))
+    assert worst < (4e-3 if n >= 4096 else 8e-3), worst
+
+
+def test_backward_is_linear_in_grad_rgb_and_rows_beyond_n_are_inert(packed):
+    """Size-independent properties at a ragged size: backward is linear in dL/drgb; padded rows contribute nothing."""
+    n = 300
+    torch.manual_seed(0)
+    o, d = (torch.randn(n, 3) * 0.5).to(DEV), torch.randn(n, 3).to(DEV)
+    z = orc.sampler_z_vals(2.0, 6.0).tolist()
+    g1, g2 = torch.randn(n, 3, device=DEV) * 1e-3, torch.randn(n, 3, device=DEV) * 1e-3
+    rgb, ctx = ops.forward_train(packed, rays_o=o, rays_d=d, z_vals=z, keep=True)
+    a = ops.backward(packed, ctx, g1).clone()
+    b = ops.backward(packed, ctx, g2).clone()
+    ab = ops.backward(packed, ctx, g1 + g2).clone()
+    assert float((ab - (a + b)).norm() / ab.norm()) < 2e-3
+    zero = ops.backward(packed, ctx, torch.zeros(n, 3, device=DEV))
+    assert float(zero.abs().max()) == 0.0
+
+
+def test_module_autograd_and_optimizer_step(golden_r2l):
+    """The drop-in module: forward_rays + loss.backward() + Adam on the flat parameter, as main.py:1365-1406 does."""
+    g = golden_r2l
+    nb.device = torch.device(DEV)
+    model = nb.NeRF_v3_2(nb.readme_args(), 1008, 3).to(DEV)
+    with torch.no_grad():
+        model.flat.copy_(nb.init_flat_params(0).to(DEV))
+    ps = nb.PointSampler(400, 400, float(g["focal"]), 16, 2.0, 6.0)
+    emb = nb.PositionalEmbedder(L=10)
+    ro, rd = torch.from_numpy(g["rays_o"]).to(DEV), torch.from_numpy(g["rays_d"]).to(DEV)
+    tgt = torch.from_numpy(g["target"]).to(DEV)
+    with torch.no_grad():
+        rgb_eval = model(emb(ps.sample_train(ro, rd, perturb=0)))     # the reference's three-step idiom
+    assert relerr(rgb_eval.cpu().numpy(), g["rgb"]) < FWD_TOL
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+    losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        rgb = model(emb(ps.sample_train(ro, rd, perturb=0)))
+        loss = nb.img2mse(rgb, tgt)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert abs(losses[0] - float(g["loss"])) < 1e-5
+    assert losses[2] < losses[0]                     # the step goes downhill
+    assert model.flat.grad is not None and torch.isfinite(model.flat.grad).all()
+    sd = model.state_dict()
+    assert sd["head.0.weight"].shape == (256, 1008)
+
+
+def test_raw2outputs_golden(golden_teacher):
+    t = golden_teacher
+    for tag, wb in (("net", True), ("synth", False)):
+        outs = ops.raw2outputs(torch.from_numpy(t[f"r2o_{tag}_raw"]).to(DEV), torch.from_numpy(t["z_vals"]).to(DEV),
+                               torch.from_numpy(t["rays_d"]).to(DEV), wb)
+        rgb, disp, acc, w, depth = (x.cpu().numpy() for x in outs)
+        np.testing.assert_allclose(w, t[f"r2o_{tag}_weights"], rtol=2e-5, atol=3e-7)
+        np.testing.assert_allclose(rgb, t[f"r2o_{tag}_rgb"], rtol=2e-5, atol=3e-6)
+        np.testing.assert_allclose(acc, t[f"r2o_{tag}_acc"], rtol=2e-5, atol=3e-6)
+        np.testing.assert_allclose(depth, t[f"r2o_{tag}_depth"], rtol=2e-5, atol=3e-6)
+        np.testing.assert_allclose(disp, t[f"r2o_{tag}_disp"], rtol=3e-4, atol=1e-6, equal_nan=True)
+    assert np.isnan(disp[0])
+
+
+def test_raw2outputs_teacher_sizes_vs_oracle():
+    """create_data.py sizes: 4096 rays x 192 fine samples; compared with the numpy oracle, plus sum(weights) = acc."""
+    torch.manual_seed(7)
+    n, s = 4096, 192
+    raw = torch.randn(n, s, 4) * 2
+    z = torch.sort(torch.rand(n, s) * 4 + 2, dim=-1).values
+    d = torch.randn(n, 3)
+    outs = ops.raw2outputs(raw.to(DEV), z.to(DEV), d.to(DEV), True)
+    ref = orc.raw2outputs(raw.numpy(), z.numpy(), d.numpy(), True)
+    for got, want, tol in zip(outs, ref, (3e-5, 1e-3, 3e-5, 3e-6, 3e-5)):
+        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-4, atol=tol)
+    assert float((outs[3].sum(-1) - outs[2]).abs().max()) < 1e-5
+
+
+def test_dense_embeddings_match_oracle(golden_r2l, golden_teacher):
+    pts = torch.from_numpy(golden_r2l["pts"]).to(DEV)
+    got = ops.positional_embed(pts, 10, style=0).cpu().numpy()
+    np.testing.assert_allclose(got, golden_r2l["x_embed"], rtol=0, atol=1e-6)
+    p3 = torch.from_numpy(golden_teacher["pts"].reshape(-1, 3)[:8]).to(DEV)
+    np.testing.assert_allclose(ops.positional_embed(p3, 10, style=1).cpu().numpy(), golden_teacher["embed_pts_first8"], rtol=0, atol=1e-6)
+    embed_fn, ch = nb.get_embedder(10, 0)
+    assert ch == 63 and embed_fn(p3).shape == (8, 63)
