@@ -99,12 +99,12 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------
 # the reference's CPU code path (stock PyTorch ops on host cores) — oracle/, checker & baseline only
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step_fn(n_rays):
+def cpu_reference_step_fn(n_rays, threads=None):
     import torch
     from oracle import r2l_oracle as orc
     from oracle.torch_reference import RefR2L, embed, sample
     from r2l_b200.nerf_raybased import init_flat_params
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     torch.autograd.set_detect_anomaly(False)
     model = RefR2L().load_flat(init_flat_params(0))
     ro, rd, tg = synthetic_rays(n_rays, 0)
@@ -117,8 +117,27 @@ def cpu_reference_step_fn(n_rays):
         loss = ((model(embed(sample(ro, rd, z))) - tg) ** 2).mean()
         loss.backward()
         opt.step()
-        return float(loss)
+        return float(loss.detach())
     return step
+
+
+def best_cpu_threads(n_rays):
+    """The stock PyTorch CPU path does not scale to every core of a big host on these small GEMMs; give the
+    reference its best configuration: try a few intra-op thread counts on one step each and keep the fastest."""
+    import torch
+    cores = os.cpu_count() or 1
+    best = (None, float("inf"))
+    for th in sorted({min(cores, c) for c in (8, 16, 32, 64, cores)}):
+        step = cpu_reference_step_fn(n_rays, th)
+        step()
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+        if dt < best[1]:
+            best = (th, dt)
+        elif dt > 1.5 * best[1]:
+            break   # more threads are only getting slower
+    return best[0]
 
 
 def run_reference(args):
@@ -127,7 +146,8 @@ def run_reference(args):
         return
     import torch
     sample_rays = 1024   # bounded sample of the 4096-ray batch per step (same per-ray work)
-    step = cpu_reference_step_fn(sample_rays)
+    threads = best_cpu_threads(sample_rays)
+    step = cpu_reference_step_fn(sample_rays, threads)
     for _ in range(max(args.warmup, 1)):
         step()
     t0 = time.perf_counter()
@@ -135,13 +155,13 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     rays_s = sample_rays * args.steps / dt
-    cores = os.cpu_count() or 1
+    cores = threads
     line = {"impl": "reference", "metric": METRIC, "value": rays_s, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps * (BATCH / sample_rays), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "note": "reference code path = stock PyTorch CPU ops (oracle/torch_reference.py restates model/nerf_raybased.py; /root/reference is absent on the GPU box)"},
             "cpu_baseline": {"value": rays_s, "unit": "rays/s", "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} train steps (fwd+bwd+Adam) on {sample_rays} of the 4096 rays, torch {torch.__version__} CPU, {cores} threads"},
+                             "sample": f"{args.steps} train steps (fwd+bwd+Adam) on {sample_rays} of the 4096 rays, torch {torch.__version__} CPU, {cores} threads (best of 8/16/32/64/all on this {os.cpu_count()}-core host)"},
             "e2e": {"value": rays_s, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -196,11 +216,11 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     for a, b in evs:
@@ -239,6 +259,26 @@ def run_ours(args):
                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved_tflops / peaks["bf16_tflops"],
                 "traffic": None, "peak_source": peaks["source"], "kernel_ms": k_ms,
                 "note": "algorithmic fp32 FLOPs; the kernel issues 3x that as bf16 MMAs (hi*hi+lo*hi+hi*lo) to meet the 1e-3 fp32 parity bar, and a 4096-ray batch fills 32 of 148 SMs"}
+
+    # ---- the same kernel with every SM busy (148 tiles = 18,944 rays), inference form: kernel quality, not the metric ----
+    n_full = 148 * 128
+    fo, fd, _ = synthetic_rays(n_full, seed=7)
+    fo, fd = torch.from_numpy(fo).to(dev), torch.from_numpy(fd).to(dev)
+    fout = torch.empty(n_full, 3, device=dev)
+    for _ in range(3):
+        ops.forward(packed, rays_o=fo, rays_d=fd, z_vals=z_vals, out=fout)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(10):
+        ops.forward(packed, rays_o=fo, rays_d=fd, z_vals=z_vals, out=fout)
+    b.record()
+    torch.cuda.synchronize()
+    full_ms = a.elapsed_time(b) / 10
+    full_tflops = n_full * FWD_FLOP_PER_RAY / (full_ms * 1e-3) / 1e12
+    roofline["full_chip"] = {"kernel": "r2l_chain_kernel<kFwdInfer> (18,944 rays = one tile per SM)", "kernel_ms": full_ms,
+                             "achieved": full_tflops, "frac": full_tflops / peaks["bf16_tflops"],
+                             "issued_frac": 3 * full_tflops / peaks["bf16_tflops"]}
 
     # ---- end to end through the public module API, host buffers ----
     model = NeRF_v3_2(readme_args(), 1008, 3).to(dev)
@@ -281,15 +321,16 @@ def run_ours(args):
         cpu = None
         if world == 1:
             sample_rays, reps_cpu = 1024, 3
-            stepc = cpu_reference_step_fn(sample_rays)
+            cpu_threads = best_cpu_threads(sample_rays)
+            stepc = cpu_reference_step_fn(sample_rays, cpu_threads)
             stepc()
             t0 = time.perf_counter()
             for _ in range(reps_cpu):
                 stepc()
             dt = time.perf_counter() - t0
-            cores = os.cpu_count() or 1
+            cores = cpu_threads
             cpu = {"value": sample_rays * reps_cpu / dt, "unit": "rays/s", "cores": cores, "kind": "port",
-                   "sample": f"{reps_cpu} train steps on {sample_rays} of the 4096 rays; stock PyTorch CPU ops (oracle/torch_reference.py), {cores} threads"}
+                   "sample": f"{reps_cpu} train steps on {sample_rays} of the 4096 rays; stock PyTorch CPU ops (oracle/torch_reference.py), {cores} threads (best of 8/16/32/64/all on this {os.cpu_count()}-core host)"}
         line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 (bf16x3 split operands, fp32 accumulate)", "data": "synthetic",

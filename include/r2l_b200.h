@@ -61,6 +61,17 @@ int r2l_backward(int input_kind, const void* packed, const float* rgb, const flo
                  const void* fwd_saved, void* bwd_saved, float* grads, void* workspace, size_t workspace_bytes,
                  int64_t n_rays, void* stream);
 
+/* Teacher NeRF (NeRF.forward :377-401 behind run_network :312-334; D=8, W=256, skips=[4], use_viewdirs, multires 10/4).
+ *   params : R2L_TEACHER_NUM_PARAMS floats, state_dict order (pts_linears.0-7, views_linears.0, feature_linear,
+ *            alpha_linear, rgb_linear; weight then bias)
+ *   input  : pts[P,3] + viewdirs[P/samples_per_ray,3] (embeddings built in-kernel), or x_embedded[P,90]
+ *   raw    : [P,4] = (rgb, sigma), no output activation */
+#define R2L_TEACHER_NUM_PARAMS 595844
+size_t r2l_teacher_packed_bytes(void);
+int r2l_teacher_pack_weights(const float* params, void* packed, void* stream);
+int r2l_teacher_forward(const float* pts, const float* viewdirs, const float* x_embedded, const void* packed, float* raw,
+                        int64_t n_points, int64_t samples_per_ray, void* stream);
+
 /* raw2outputs (nerf_raybased.py:226-295, raw_noise_std = 0): raw[N,S,4], z_vals[N,S], rays_d[N,3] ->
  * rgb_map[N,3], disp_map[N], acc_map[N], weights[N,S], depth_map[N].  One warp per ray, one pass over HBM. */
 int r2l_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, int64_t n_rays, int n_samples,

@@ -185,6 +185,34 @@ int r2l_positional_embed(const float* x, float* out, int64_t n, int dim, int n_f
   return check(r2l::launch_embed(x, out, n, dim, n_freqs, style, (cudaStream_t)stream), "r2l_positional_embed");
 }
 
+size_t r2l_teacher_packed_bytes(void) { return (size_t)r2l::kTeacherPackedBytes; }
+
+int r2l_teacher_pack_weights(const float* params, void* packed, void* stream) {
+  if (!params || !packed) return fail("r2l_teacher_pack_weights: %s", "null pointer");
+  return check(r2l::launch_teacher_pack(params, packed, (cudaStream_t)stream), "r2l_teacher_pack_weights");
+}
+
+int r2l_teacher_forward(const float* pts, const float* viewdirs, const float* x_embedded, const void* packed, float* raw,
+                        int64_t n_points, int64_t samples_per_ray, void* stream) {
+  if (n_points == 0) return 0;
+  if (n_points < 0) return fail("r2l_teacher_forward: %s", "negative n_points");
+  if (!packed || !raw) return fail("r2l_teacher_forward: %s", "null pointer");
+  if (!x_embedded && (!pts || !viewdirs || samples_per_ray <= 0))
+    return fail("r2l_teacher_forward: %s", "needs pts + viewdirs + samples_per_ray, or x_embedded");
+  if (misaligned(packed) || misaligned(raw)) return fail("r2l_teacher_forward: %s", "packed/raw must be 16-byte aligned");
+  r2l::TeacherParams p;
+  memset(&p, 0, sizeof(p));
+  p.pts = pts;
+  p.viewdirs = viewdirs;
+  p.x_embedded = x_embedded;
+  p.packed = static_cast<const uint8_t*>(packed);
+  p.raw = raw;
+  p.n_points = n_points;
+  p.samples_per_ray = samples_per_ray > 0 ? samples_per_ray : 1;
+  p.num_tiles = num_tiles(n_points);
+  return check(r2l::launch_teacher(p, fwd_grid(n_points), (cudaStream_t)stream), "r2l_teacher_forward");
+}
+
 int r2l_debug_set_stats(long long* stats) {
   g_stats = stats;
   return 0;

@@ -52,6 +52,19 @@ struct TailGradParams {
   int64_t n_rays;
 };
 
+struct TeacherParams {
+  const float* pts;          // [P,3] sample points (ray-major: point p belongs to ray p / samples_per_ray)
+  const float* viewdirs;     // [P / samples_per_ray, 3] normalised view directions
+  const float* x_embedded;   // alternative input: [P,90] already embedded (pts 63 | views 27); pts/viewdirs unused
+  const uint8_t* packed;
+  float* raw;                // [P,4] = (rgb, sigma) before any activation
+  int64_t n_points;
+  int64_t samples_per_ray;
+  int num_tiles;
+};
+
+cudaError_t launch_teacher_pack(const float* params, void* packed, cudaStream_t stream);
+cudaError_t launch_teacher(const TeacherParams& p, int grid, cudaStream_t stream);
 cudaError_t launch_pack(const float* params, void* packed, cudaStream_t stream);
 cudaError_t launch_chain(int mode, const ChainParams& p, int grid, cudaStream_t stream);
 cudaError_t launch_dw(const DwParams& p, cudaStream_t stream);

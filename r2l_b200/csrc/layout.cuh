@@ -83,6 +83,13 @@ __host__ __device__ inline uint32_t sw128_offset(uint32_t row, uint32_t k) {
   return row * 128u + ((((k >> 3) ^ (row & 7u)) << 4) | ((k & 7u) << 1));
 }
 
+// ---- teacher NeRF (D=8, W=256, input_ch=63, input_ch_views=27, skips=[4], use_viewdirs) ----
+constexpr int kTeacherLayers = 10;            // tensor-core layers T0..T9 (see teacher.cu)
+constexpr int kTeacherImagePairs = 39;        // K chunks over all layers: 1+4+4+4+4+5+4+4+4+5
+constexpr int64_t kTeacherNumParams = 595844; // floats in the teacher state_dict
+constexpr int64_t kTeacherPackOffTables = (int64_t)2 * kTeacherImagePairs * kWImageBytes;
+constexpr int64_t kTeacherPackedBytes = kTeacherPackOffTables + (kTeacherLayers * kWidth + kWidth + 3 * 128 + 4) * 4;
+
 enum InputKind : int {
   kInputRays = 0,  // rays_o[N,3], rays_d[N,3] (+ optional t_rand[N,16]); points and PE built in-kernel
   kInputPts = 1,   // pts[N,48] as returned by PointSampler.sample_*; PE built in-kernel

@@ -384,8 +384,19 @@ def batchify(fn, chunk):
     return lambda inputs: torch.cat([fn(inputs[i:i + chunk]) for i in range(0, inputs.shape[0], chunk)], 0)
 
 
+def _default_embedder(fn, n_freqs):
+    eo = (getattr(fn, "__defaults__", None) or (None,))[0]
+    return isinstance(eo, Embedder) and eo._kernel_ok and eo.n_freqs == n_freqs
+
+
 def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64):
-    """Embed points (and view directions) and apply the network (reference :312-334)."""
+    """Embed points (and view directions) and apply the network (reference :312-334).  With the stock teacher
+    (NeRF below, multires 10 / 4) on the GPU the embeddings, the 12 Linears and the concatenations are one kernel
+    and `netchunk` is irrelevant (nothing is materialised)."""
+    net = getattr(fn, "module", fn)
+    if (isinstance(net, NeRF) and net.fused_ok and viewdirs is not None and inputs.is_cuda and inputs.dim() == 3
+            and inputs.dtype == torch.float32 and _default_embedder(embed_fn, 10) and _default_embedder(embeddirs_fn, 4)):
+        return net.query(inputs, viewdirs)
     flat = torch.reshape(inputs, [-1, inputs.shape[-1]])
     embedded = embed_fn(flat)
     if viewdirs is not None:
@@ -407,3 +418,67 @@ def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkgd=False, pytest=F
         for i_ray in range(0, alpha.shape[0], 100):
             print('%4d: ' % i_ray + ' '.join('%.4f' % v for v in alpha[i_ray]))
     return outs
+
+
+class NeRF(nn.Module):
+    """The teacher NeRF (reference :337-440): 8 x 256 MLP, skip at layer 4, view-direction branch.
+
+    The nn.Linear members only hold the parameters under the reference's state_dict names; the arithmetic is the
+    fused tcgen05 kernel (csrc/teacher.cu).  Only the configuration create_nerf builds (utils/create_data.py:251-293:
+    D=8, W=256, input_ch=63, input_ch_views=27, skips=[4], use_viewdirs=True) is implemented; others raise."""
+
+    def __init__(self, D=8, W=256, input_ch=3, input_ch_views=3, output_ch=4, skips=[4], use_viewdirs=False):
+        super().__init__()
+        self.D, self.W = D, W
+        self.input_ch, self.input_ch_views = input_ch, input_ch_views
+        self.skips, self.use_viewdirs = skips, use_viewdirs
+        self.pts_linears = nn.ModuleList([nn.Linear(input_ch, W)] + [
+            nn.Linear(W + input_ch, W) if i in skips else nn.Linear(W, W) for i in range(D - 1)])
+        self.views_linears = nn.ModuleList([nn.Linear(input_ch_views + W, W // 2)])
+        if use_viewdirs:
+            self.feature_linear = nn.Linear(W, W)
+            self.alpha_linear = nn.Linear(W, 1)
+            self.rgb_linear = nn.Linear(W // 2, 3)
+        else:
+            self.output_linear = nn.Linear(W, output_ch)
+        self.fused_ok = (D == 8 and W == 256 and input_ch == 63 and input_ch_views == 27 and list(skips) == [4] and use_viewdirs)
+        self._packed, self._packed_version = None, None
+
+    def _flat(self):
+        return torch.cat([p.detach().reshape(-1) for p in self.parameters()])
+
+    def packed_weights(self):
+        params = list(self.parameters())
+        version = tuple((p.data_ptr(), p._version) for p in params)
+        if self._packed is None or self._packed_version != version:
+            self._packed = ops.teacher_pack_weights(self._flat().contiguous())
+            self._packed_version = version
+        return self._packed
+
+    def _check(self):
+        if not self.fused_ok:
+            raise NotImplementedError("r2l_b200 NeRF: only D=8, W=256, input_ch=63, input_ch_views=27, skips=[4], "
+                                      "use_viewdirs=True is implemented (the teacher of utils/create_data.py)")
+        if not next(self.parameters()).is_cuda:
+            raise RuntimeError("r2l_b200 NeRF runs on CUDA only: move the model with .to('cuda') (no CPU fallback)")
+
+    def forward(self, x):
+        """x: [..., 90] embedded points | view directions, as run_network builds it (reference :377-401)."""
+        self._check()
+        lead = x.shape[:-1]
+        return ops.teacher_forward(self.packed_weights(), x_embedded=x.reshape(-1, x.shape[-1])).view(*lead, 4)
+
+    def query(self, pts, viewdirs):
+        """Fused run_network: pts[N,S,3], viewdirs[N,3] -> raw[N,S,4]."""
+        self._check()
+        return ops.teacher_forward(self.packed_weights(), pts=pts, viewdirs=viewdirs)
+
+    def load_weights_from_keras(self, weights):
+        """TF-NeRF .npy weight list -> parameters (reference :403-440)."""
+        assert self.use_viewdirs, "Not implemented if use_viewdirs=False"
+        pairs = [(lin, 2 * i) for i, lin in enumerate(self.pts_linears)]
+        pairs += [(self.feature_linear, 2 * self.D), (self.views_linears[0], 2 * self.D + 2),
+                  (self.rgb_linear, 2 * self.D + 4), (self.alpha_linear, 2 * self.D + 6)]
+        for lin, idx in pairs:
+            lin.weight.data = torch.from_numpy(np.transpose(weights[idx]))
+            lin.bias.data = torch.from_numpy(np.transpose(weights[idx + 1]))

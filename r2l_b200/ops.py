@@ -243,3 +243,42 @@ def positional_embed(x: torch.Tensor, n_freqs: int, style: int) -> torch.Tensor:
         _lib.check(_lib.lib().r2l_positional_embed(_ptr(flat), _ptr(out), flat.shape[0], dim, n_freqs, style, _stream()),
                    "r2l_positional_embed")
     return out.view(*x.shape[:-1], out.shape[-1])
+
+
+# ------------------------------------------------------------------------------------------------
+# teacher NeRF
+# ------------------------------------------------------------------------------------------------
+TEACHER_NUM_PARAMS = 595844
+
+
+def teacher_pack_weights(flat_params: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    flat_params = _require_cuda_f32(flat_params, "flat_params")
+    if flat_params.numel() != TEACHER_NUM_PARAMS:
+        raise ValueError(f"teacher flat_params: expected {TEACHER_NUM_PARAMS} floats, got {flat_params.numel()}")
+    if out is None:
+        out = torch.empty(int(_lib.lib().r2l_teacher_packed_bytes()), dtype=torch.uint8, device=flat_params.device)
+    with torch.cuda.device(flat_params.device):
+        _lib.check(_lib.lib().r2l_teacher_pack_weights(_ptr(flat_params), _ptr(out), _stream()), "r2l_teacher_pack_weights")
+    return out
+
+
+def teacher_forward(packed: torch.Tensor, *, pts=None, viewdirs=None, x_embedded=None) -> torch.Tensor:
+    """raw[..., 4] of the teacher MLP.  Either pts[N,S,3] + viewdirs[N,3] (embeddings fused) or x_embedded[P,90]."""
+    L = _lib.lib()
+    if x_embedded is not None:
+        x = _require_cuda_f32(x_embedded, "x_embedded", (90,))
+        raw = torch.empty((x.shape[0], 4), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(L.r2l_teacher_forward(None, None, _ptr(x), _ptr(packed), _ptr(raw), x.shape[0], 1, _stream()), "r2l_teacher_forward")
+        return raw
+    pts = _require_cuda_f32(pts, "pts")
+    if pts.dim() != 3 or pts.shape[-1] != 3:
+        raise ValueError(f"pts: expected [N,S,3], got {tuple(pts.shape)}")
+    viewdirs = _require_cuda_f32(viewdirs, "viewdirs", (3,))
+    if viewdirs.shape[0] != pts.shape[0]:
+        raise ValueError("pts / viewdirs disagree on the number of rays")
+    n, s = pts.shape[0], pts.shape[1]
+    raw = torch.empty((n, s, 4), dtype=torch.float32, device=pts.device)
+    with torch.cuda.device(pts.device):
+        _lib.check(L.r2l_teacher_forward(_ptr(pts), _ptr(viewdirs), None, _ptr(packed), _ptr(raw), n * s, s, _stream()), "r2l_teacher_forward")
+    return raw

@@ -173,18 +173,27 @@ def test_module_autograd_and_optimizer_step(golden_r2l):
     with torch.no_grad():
         rgb_eval = model(emb(ps.sample_train(ro, rd, perturb=0)))     # the reference's three-step idiom
     assert relerr(rgb_eval.cpu().numpy(), g["rgb"]) < FWD_TOL
-    opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+    # one plain gradient step sized for a 10 % first-order decrease: loss must follow the prediction
+    gnorm2 = float(g["grad_f64_norm"]) ** 2
+    lr = 0.1 * float(g["loss"]) / gnorm2
+    opt = torch.optim.SGD(model.parameters(), lr=lr)
     losses = []
-    for _ in range(3):
+    for _ in range(2):
         opt.zero_grad()
         rgb = model(emb(ps.sample_train(ro, rd, perturb=0)))
         loss = nb.img2mse(rgb, tgt)
         loss.backward()
-        opt.step()
-        losses.append(float(loss))
+        if not losses:
+            assert abs(float(model.flat.grad.double().norm()) - float(g["grad_f64_norm"])) < 5e-3 * float(g["grad_f64_norm"])
+        opt.step()                                   # updates the flat parameter -> weights are re-packed
+        losses.append(float(loss.detach()))
     assert abs(losses[0] - float(g["loss"])) < 1e-5
-    assert losses[2] < losses[0]                     # the step goes downhill
+    drop = (losses[0] - losses[1]) / losses[0]
+    assert 0.03 < drop < 0.15, (losses, drop)        # predicted 0.10 to first order
     assert model.flat.grad is not None and torch.isfinite(model.flat.grad).all()
+    # Adam on the single flat parameter runs (the reference's optimizer, main.py:465)
+    adam = torch.optim.Adam(model.parameters(), lr=1e-5)
+    adam.zero_grad(); nb.img2mse(model(emb(ps.sample_train(ro, rd, perturb=0))), tgt).backward(); adam.step()
     sd = model.state_dict()
     assert sd["head.0.weight"].shape == (256, 1008)
 
@@ -225,3 +234,57 @@ def test_dense_embeddings_match_oracle(golden_r2l, golden_teacher):
     np.testing.assert_allclose(ops.positional_embed(p3, 10, style=1).cpu().numpy(), golden_teacher["embed_pts_first8"], rtol=0, atol=1e-6)
     embed_fn, ch = nb.get_embedder(10, 0)
     assert ch == 63 and embed_fn(p3).shape == (8, 63)
+
+
+# ------------------------------------------------------------------------------------------------
+# teacher NeRF (fused MLP) + compositing
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def teacher():
+    nb.device = torch.device(DEV)
+    torch.manual_seed(0)
+    return nb.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=4, skips=[4], use_viewdirs=True).to(DEV)
+
+
+def test_teacher_query_golden(golden_teacher, teacher):
+    """run_network(pts, viewdirs, NeRF) on the reference's own inputs: raw within 1e-3 of max|raw| elementwise."""
+    t = golden_teacher
+    sums = [float(p.detach().double().sum()) for p in teacher.parameters()]
+    assert np.allclose(sums, t["param_sum"], rtol=1e-12, atol=1e-12)          # same seed-0 weights as the reference
+    pts, vd = torch.from_numpy(t["pts"]).to(DEV), torch.from_numpy(t["viewdirs"]).to(DEV)
+    raw = teacher.query(pts, vd).cpu().numpy()
+    scale = np.abs(t["raw"]).max()
+    assert np.abs(raw - t["raw"]).max() / scale < 1e-3
+    embed_fn, _ = nb.get_embedder(10, 0)
+    embeddirs_fn, _ = nb.get_embedder(4, 0)
+    raw2 = nb.run_network(pts, vd, teacher, embed_fn, embeddirs_fn, netchunk=1024)   # drop-in call, fused dispatch
+    assert np.array_equal(raw2.cpu().numpy(), raw)
+    # NeRF.forward on the materialised [P,90] embedding (the reference's calling convention) agrees
+    flat = pts.reshape(-1, 3)
+    emb = torch.cat([embed_fn(flat), embeddirs_fn(vd[:, None].expand(pts.shape).reshape(-1, 3))], -1)
+    raw3 = teacher(emb).view(*pts.shape[:-1], 4).cpu().numpy()
+    assert np.abs(raw3 - t["raw"]).max() / scale < 1e-3
+
+
+def test_teacher_ragged_and_large_vs_oracle(teacher):
+    """Sizes of utils/create_data.py (64 coarse / 192 fine samples) on ragged ray counts, against the numpy oracle."""
+    params = [p.detach().cpu().numpy() for p in teacher.parameters()]
+    for n, s in ((3, 64), (130, 192), (1024, 64)):
+        torch.manual_seed(n)
+        pts = (torch.randn(n, s, 3) * 1.5)
+        vd = torch.nn.functional.normalize(torch.randn(n, 3), dim=-1)
+        raw = teacher.query(pts.to(DEV), vd.to(DEV)).cpu().numpy()
+        m = min(n, 40)
+        ref = orc.run_network(pts.numpy()[:m], vd.numpy()[:m], params)
+        assert np.isfinite(raw).all()
+        assert np.abs(raw[:m] - ref).max() / np.abs(ref).max() < 1e-3
+
+
+def test_teacher_render_pipeline_matches_oracle(golden_teacher, teacher):
+    """query -> raw2outputs, the inner path of render_rays (utils/create_data.py:490-492)."""
+    t = golden_teacher
+    pts, vd = torch.from_numpy(t["pts"]).to(DEV), torch.from_numpy(t["viewdirs"]).to(DEV)
+    z, rd = torch.from_numpy(t["z_vals"]).to(DEV), torch.from_numpy(t["rays_d"]).to(DEV)
+    rgb, disp, acc, w, depth = nb.raw2outputs(teacher.query(pts, vd), z, rd, 0, True)
+    np.testing.assert_allclose(rgb.cpu().numpy(), t["r2o_net_rgb"], rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(w.cpu().numpy(), t["r2o_net_weights"], rtol=1e-3, atol=1e-5)
