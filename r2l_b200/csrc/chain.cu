@@ -39,6 +39,7 @@ constexpr uint32_t kSmemBar = kSmemW + kNumWStages * kWImageBytes;    // 229376
 constexpr uint32_t kSmemTail = kSmemBar + 256;                        // 128 x 3 floats
 constexpr uint32_t kSmemUsed = kSmemTail + kTileM * 3 * 4;            // 231168
 constexpr uint32_t kChainSmemBytes = kSmemUsed + 1024;                // + alignment slack
+static_assert(kChainSmemBytes <= 232448, "exceeds the 227 KiB dynamic shared memory limit");
 
 constexpr uint32_t kTmemZ = 0;
 constexpr uint32_t kTmemH = 256;

@@ -28,6 +28,7 @@ constexpr uint32_t kDwOperand = 8 * kDwPiece;          // 32768: 4 chunks x 2 pl
 constexpr uint32_t kDwStageBytes = 2 * kDwOperand;     // dY + X
 constexpr uint32_t kDwSmemBar = kDwStages * kDwStageBytes;  // 196608
 constexpr uint32_t kDwSmemBytes = kDwSmemBar + 128 + 1024;
+static_assert(kDwSmemBytes <= 232448, "exceeds the 227 KiB dynamic shared memory limit");
 constexpr int kDwUnits = kBodyLayers + 4;
 
 __global__ void __launch_bounds__(kDwThreads, 1) r2l_dw_kernel(const __grid_constant__ DwParams p) {

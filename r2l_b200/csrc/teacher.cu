@@ -22,8 +22,11 @@ constexpr int kTEpiWarps = 8;
 constexpr uint32_t kTSmemA = 0;
 constexpr uint32_t kTSmemW = kABytes;
 constexpr uint32_t kTSmemBar = kTSmemW + kTNumWStages * kWImageBytes;
-constexpr uint32_t kTSmemOut = kTSmemBar + 256;                  // 128 x 4 floats (column-half exchange)
-constexpr uint32_t kTSmemBytes = kTSmemOut + kTileM * 4 * 4 + 1024;
+// The 128 x 4 floats the two column halves exchange at the end of a tile live in A slot 1: every GEMM of the tile has
+// completed by then, and slots 1-3 are next written by these same warps after the next tile's first layer.
+constexpr uint32_t kTSmemOut = kTSmemA + kAChunkBytes;
+constexpr uint32_t kTSmemBytes = kTSmemBar + 256 + 1024;
+static_assert(kTSmemBytes <= 232448, "exceeds the 227 KiB dynamic shared memory limit");
 
 enum : uint32_t {
   kTBarWFull = 0,

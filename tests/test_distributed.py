@@ -1,0 +1,61 @@
+"""world_size-2 gloo test (CPU) of the data-parallel host logic: ray sharding + one flat-gradient all-reduce reproduce the
+full-batch gradient.  The per-shard arithmetic is done by the numpy oracle here (the product has no CPU path); on GPUs
+the same plumbing runs over NCCL (bench.py, torchrun)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from r2l_b200 import parallel
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import r2l_oracle as orc
+    from r2l_b200.nerf_raybased import init_flat_params
+    torch.set_num_threads(2)
+    flat = init_flat_params(0).numpy().astype(np.float64)
+    rng = np.random.RandomState(0)
+    x = rng.randn(n, orc.IN_DIM) * 0.5
+    target = rng.rand(n, 3)
+    lo, hi = parallel.shard_range(n, rank, world)
+    # local gradient of the GLOBAL mean: scale the local-mean gradient by n_local / n_global
+    _, g_local, rgb_local, _ = orc.r2l_loss_and_grads(flat, x[lo:hi], target[lo:hi])
+    g = torch.from_numpy(g_local * ((hi - lo) / n))
+    parallel.allreduce_flat_grads(g)
+    rgb = parallel.gather_rgb(torch.from_numpy(rgb_local), n)
+    if rank == 0:
+        _, g_full, rgb_full, _ = orc.r2l_loss_and_grads(flat, x, target)
+        np.save(os.path.join(out_dir, "err.npy"), np.array([
+            np.linalg.norm(g.numpy() - g_full) / np.linalg.norm(g_full), np.abs(rgb.numpy() - rgb_full).max()]))
+        # the scaling helper is the same statement on tensors
+        gr = parallel.mse_grad_rgb(torch.from_numpy(rgb_local), torch.from_numpy(target[lo:hi]), n)
+        assert torch.allclose(gr, torch.from_numpy((rgb_local - target[lo:hi]) * 2.0 / (3 * n)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 4096, 160000):
+        for world in (1, 2, 3, 8):
+            r = [parallel.shard_range(n, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+            assert max(hi - lo for lo, hi in r) - min(hi - lo for lo, hi in r) <= 1
+
+
+def test_two_rank_gradient_allreduce_matches_full_batch(tmp_path):
+    n = 37   # ragged: shards of 19 and 18 rays
+    mp.spawn(_worker, args=(2, _free_port(), n, str(tmp_path)), nprocs=2, join=True)
+    err = np.load(tmp_path / "err.npy")
+    assert err[0] < 1e-12 and err[1] < 1e-12
