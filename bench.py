@@ -197,7 +197,8 @@ def run_ours(args):
     grads = torch.empty_like(flat)
     flat_param = torch.nn.Parameter(flat)
     flat_param.grad = grads
-    opt = torch.optim.Adam([flat_param], lr=5e-4, fused=True)
+    from r2l_b200.optim import FlatAdam
+    opt = FlatAdam([flat_param], lr=5e-4)
     n_global = BATCH * world
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
@@ -209,7 +210,7 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(grads)                            # one NCCL all-reduce of the flat 23.7 MB buffer
         opt.step()
-    LAUNCHES_PER_STEP = 7  # pack x2, chain fwd, chain bwd, dw, tail (+ its memset node counted once)
+    LAUNCHES_PER_STEP = 7  # pack x2, chain fwd, chain bwd, dw, tail, adam
 
     def barrier():
         if world > 1:
@@ -285,7 +286,7 @@ def run_ours(args):
     with torch.no_grad():
         model.flat.copy_(init_flat_params(0).to(dev))
     ps = PointSampler(400, 400, 555.5555155968841, 16, 2.0, 6.0)
-    opt2 = torch.optim.Adam(model.parameters(), lr=5e-4, fused=True)
+    opt2 = FlatAdam(model.parameters(), lr=5e-4)
     h_loss = torch.empty(1).pin_memory()
 
     def step_e2e():
@@ -337,10 +338,10 @@ def run_ours(args):
                 "config": {"workload": WORKLOAD, "rays_per_gpu": BATCH, "global_batch": n_global,
                            "parallelism": f"dp{world}" if world > 1 else "single",
                            "l2": "256 MiB buffer written between timed iterations (L2 flush, untimed)",
-                           "step": "pack_weights + forward_train + backward(chain, dW, tail) + allreduce(N>1) + fused Adam"},
+                           "step": "pack_weights + forward_train + backward(chain, dW, tail) + allreduce(N>1) + Adam (r2l_adam_step)"},
                 "clocks": sampler.summary(), "gpu_launches": LAUNCHES_PER_STEP * args.steps,
                 "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": BATCH * 9 * 4, "d2h_bytes_per_step": 4,
-                        "api": "NeRF_v3_2.forward_rays + autograd + torch.optim.Adam(fused), pinned host rays -> device each step, loss read back"},
+                        "api": "NeRF_v3_2.forward_rays + autograd + r2l_b200.optim.FlatAdam, pinned host rays -> device each step, loss read back"},
                 "roofline": roofline}
         if cpu is not None:
             line["cpu_baseline"] = cpu

@@ -82,6 +82,11 @@ int r2l_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, 
  * style 0: PositionalEmbedder.__call__ (:198-208) layout; style 1: Embedder.embed (:54-55, get_embedder :58-73) layout. */
 int r2l_positional_embed(const float* x, float* out, int64_t n, int dim, int n_freqs, int style, void* stream);
 
+/* One Adam update of a flat fp32 buffer (torch.optim.Adam defaults: no amsgrad / weight decay; main.py:465,:1406).
+ * `step` counts from 1.  28 bytes of HBM traffic per parameter in one pass. */
+int r2l_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, int64_t step, void* stream);
+
 /* Debug: device buffer [grid][8] of int64 cycle counters filled by the next r2l_forward calls (NULL = off):
  * [0] MMA wait on head A chunks, [1] on body A chunks, [2] on weight stages, [3] producer wait on free stages,
  * [4] MMA-thread total. */

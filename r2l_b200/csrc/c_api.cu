@@ -1,5 +1,6 @@
 // extern "C" boundary (include/r2l_b200.h). Argument checking, launch-geometry policy, error strings.
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 
 #include "../../include/r2l_b200.h"
@@ -211,6 +212,19 @@ int r2l_teacher_forward(const float* pts, const float* viewdirs, const float* x_
   p.samples_per_ray = samples_per_ray > 0 ? samples_per_ray : 1;
   p.num_tiles = num_tiles(n_points);
   return check(r2l::launch_teacher(p, fwd_grid(n_points), (cudaStream_t)stream), "r2l_teacher_forward");
+}
+
+int r2l_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, int64_t step, void* stream) {
+  if (n == 0) return 0;
+  if (!params || !grads || !exp_avg || !exp_avg_sq) return fail("r2l_adam_step: %s", "null pointer");
+  if (n < 0 || step < 1) return fail("r2l_adam_step: %s", "bad n or step (steps count from 1)");
+  if (misaligned(params) || misaligned(grads) || misaligned(exp_avg) || misaligned(exp_avg_sq))
+    return fail("r2l_adam_step: %s", "buffers must be 16-byte aligned");
+  const double bc1 = 1.0 - std::pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - std::pow((double)beta2, (double)step);
+  return check(r2l::launch_adam(params, grads, exp_avg, exp_avg_sq, n, beta1, beta2, eps, (float)((double)lr / bc1),
+                                (float)(1.0 / std::sqrt(bc2)), (cudaStream_t)stream), "r2l_adam_step");
 }
 
 int r2l_debug_set_stats(long long* stats) {

@@ -52,7 +52,9 @@ enum : uint32_t {
   kBarAEmpty = kBarAFull + kAChunks,      // [4] A chunk consumed (head ring)    (MMA commit -> encoder)
   kBarASaved = kBarAEmpty + kAChunks,     // [4] A chunk copied out to HBM       (store warp -> epilogue)
   kBarAccFull = kBarASaved + kAChunks,    //     accumulator of a layer complete (MMA commit -> epilogue)
-  kBarCount
+  kBarA0Sub = kBarAccFull + 1,            // [4] slot 0 is published per 16-column k-step (kBarAFull[0] is unused):
+                                          //     the first GEMM instructions of a layer start after 1/16 of the epilogue
+  kBarCount = kBarA0Sub + 4
 };
 
 template <int HF>
@@ -120,6 +122,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
       mbar_init(bar(kBarAFull + i), kEpiWarps);
       mbar_init(bar(kBarAEmpty + i), 1);
       mbar_init(bar(kBarASaved + i), 1);
+      mbar_init(bar(kBarA0Sub + i), kEpiWarps);
     }
     mbar_init(bar(kBarAccFull), 1);
     mbar_fence_init();
@@ -174,49 +177,65 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
           const uint32_t d = tmem_base + (to_h ? kTmemH : kTmemZ);
           for (int kc = 0; kc < nkc; ++kc) {
             const uint32_t slot = kc & 3;
-            {
-              const long long t0 = p.stats ? clock64() : 0;
-              mbar_wait(bar(kBarAFull + slot), (a_phase >> slot) & 1u);
-              if (p.stats) { if (l == 0) t_a_head += clock64() - t0; else t_a_body += clock64() - t0; }
-            }
-            a_phase ^= 1u << slot;
             const uint32_t a_hi = smem_base + kSmemA + slot * kAChunkBytes;
             const uint32_t a_lo = a_hi + kPlaneBytes;
-            {  // W_hi image: A_hi*W_hi + A_lo*W_hi
-              const uint32_t ws = it % kNumWStages;
-              {
-                const long long t0 = p.stats ? clock64() : 0;
-                mbar_wait(bar(kBarWFull + ws), (it / kNumWStages) & 1u);
-                if (p.stats) t_w += clock64() - t0;
-              }
+            auto wait_w = [&](uint32_t i) {
+              const long long t0 = p.stats ? clock64() : 0;
+              mbar_wait(bar(kBarWFull + i % kNumWStages), (i / kNumWStages) & 1u);
+              if (p.stats) t_w += clock64() - t0;
               tc_fence_after_sync();
-              const uint32_t b = smem_base + kSmemW + ws * kWImageBytes;
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                umma_bf16(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b + 32 * ks, 16, 1024),
-                          idesc, (fresh && kc == 0 && ks == 0) ? 0u : 1u);
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                umma_bf16(d, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw128(b + 32 * ks, 16, 1024),
-                          idesc, 1u);
-              umma_commit(bar(kBarWEmpty + ws));
-              ++it;
-            }
-            {  // W_lo image: A_hi*W_lo
-              const uint32_t ws = it % kNumWStages;
-              {
-                const long long t0 = p.stats ? clock64() : 0;
-                mbar_wait(bar(kBarWFull + ws), (it / kNumWStages) & 1u);
-                if (p.stats) t_w += clock64() - t0;
-              }
+            };
+            auto wait_a = [&](uint32_t barrier, uint32_t bit) {
+              const long long t0 = p.stats ? clock64() : 0;
+              mbar_wait(bar(barrier), (a_phase >> bit) & 1u);
+              if (p.stats) { if (l == 0) t_a_head += clock64() - t0; else t_a_body += clock64() - t0; }
+              a_phase ^= 1u << bit;
               tc_fence_after_sync();
-              const uint32_t b = smem_base + kSmemW + ws * kWImageBytes;
+            };
+            if (slot == 0) {
+              // k-step granular: the hi-image MMAs of a k-step are issued as soon as its 16 columns are published;
+              // the W_hi slot is released after them, the lo-image MMAs follow (same issue order as the other chunks)
+              wait_w(it);
+              const uint32_t b_hi = smem_base + kSmemW + (it % kNumWStages) * kWImageBytes;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                wait_a(kBarA0Sub + ks, 4 + ks);
+                umma_bf16(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b_hi + 32 * ks, 16, 1024), idesc,
+                          (fresh && kc == 0 && ks == 0) ? 0u : 1u);
+                umma_bf16(d, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw128(b_hi + 32 * ks, 16, 1024), idesc, 1u);
+              }
+              umma_commit(bar(kBarWEmpty + it % kNumWStages));
+              ++it;
+              wait_w(it);
+              const uint32_t b_lo = smem_base + kSmemW + (it % kNumWStages) * kWImageBytes;
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                umma_bf16(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b + 32 * ks, 16, 1024),
-                          idesc, 1u);
-              umma_commit(bar(kBarWEmpty + ws));
+                umma_bf16(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b_lo + 32 * ks, 16, 1024), idesc, 1u);
+              umma_commit(bar(kBarWEmpty + it % kNumWStages));
               ++it;
+            } else {
+              wait_a(kBarAFull + slot, slot);
+              {  // W_hi image: A_hi*W_hi + A_lo*W_hi
+                wait_w(it);
+                const uint32_t b = smem_base + kSmemW + (it % kNumWStages) * kWImageBytes;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_bf16(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b + 32 * ks, 16, 1024), idesc, 1u);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_bf16(d, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw128(b + 32 * ks, 16, 1024), idesc, 1u);
+                umma_commit(bar(kBarWEmpty + it % kNumWStages));
+                ++it;
+              }
+              {  // W_lo image: A_hi*W_lo
+                wait_w(it);
+                const uint32_t b = smem_base + kSmemW + (it % kNumWStages) * kWImageBytes;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_bf16(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b + 32 * ks, 16, 1024), idesc, 1u);
+                umma_commit(bar(kBarWEmpty + it % kNumWStages));
+                ++it;
+              }
             }
             if (ring) umma_commit(bar(kBarAEmpty + slot));
           }
@@ -225,7 +244,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
         if constexpr (kIsBwd) {
           // the last backward epilogue publishes 4 more chunks (d head pre-activation, consumed only by the
           // store warp): step over those phases so the parity bookkeeping stays aligned for the next tile
-          for (uint32_t slot = 0; slot < kAChunks; ++slot) {
+          for (uint32_t ks = 0; ks < 4; ++ks) {
+            mbar_wait(bar(kBarA0Sub + ks), (a_phase >> (4 + ks)) & 1u);
+            a_phase ^= 1u << (4 + ks);
+          }
+          for (uint32_t slot = 1; slot < kAChunks; ++slot) {
             mbar_wait(bar(kBarAFull + slot), (a_phase >> slot) & 1u);
             a_phase ^= 1u << slot;
           }
@@ -250,7 +273,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
         uint8_t* dst = p.saved + (int64_t)tile * kSavedChunksPerTile * kAChunkBytes;
         for (int i = 0; i < kSavedChunksPerTile; ++i, ++issued) {
           const uint32_t slot = i & 3;   // first chunks cycle the ring; body chunk c lives in slot c
-          mbar_wait(bar(kBarAFull + slot), (a_phase >> slot) & 1u);
+          mbar_wait(bar(slot == 0 ? kBarA0Sub + 3 : kBarAFull + slot), (a_phase >> slot) & 1u);
           a_phase ^= 1u << slot;
           bulk_s2g(dst + (int64_t)i * kAChunkBytes, smem_base + kSmemA + slot * kAChunkBytes, kAChunkBytes);
           bulk_commit();
@@ -284,11 +307,24 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
     (void)cumbias; (void)headb; (void)b1; (void)tailb; (void)tail_smem;
 
     // publish one A chunk: make the generic-proxy writes visible to the tensor core, then signal
-    auto publish = [&](uint32_t slot) {
+    auto publish = [&](uint32_t slot) {          // a whole 64-column chunk
       fence_proxy_async_smem();
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(kBarAFull + slot));
+      if (lane == 0) {
+        if (slot == 0) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) mbar_arrive(bar(kBarA0Sub + ks));
+        } else {
+          mbar_arrive(bar(kBarAFull + slot));
+        }
+      }
+    };
+    auto publish_kstep = [&](uint32_t ks) {      // 16 columns of slot 0
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(kBarA0Sub + ks));
     };
     // before rewriting a slot in save modes: the store warp must have copied the previous content out
     auto wait_saved = [&](uint32_t slot, bool first_use) {
@@ -400,19 +436,26 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
           const int64_t chunk0 = from_h ? (kSamples + 4 * (2 * k + 1)) : kSamples;
           mask_img = p.fwd_saved + ((int64_t)tile * kFwdSavedChunks + chunk0) * kAChunkBytes;
         }
-        // Chunk 0 sits on the critical path between two GEMMs: fetch its bias / mask while the MMAs still run.
+        // Column ownership inside a 64-column chunk is interleaved per k-step: thread (row, hf) owns the 8 columns
+        // 16 g + 8 hf .. +8 of every k-step g = 0..3, i.e. exactly one 16-byte unit (2 g + hf) of the swizzled
+        // operand row.  Chunk 0 is published k-step by k-step so that the next GEMM starts after 16 columns.
+        // Its bias / mask sit on the critical path between two GEMMs: fetch them while the MMAs still run.
         float4 bq[8];
         uint4 mq[4];
         auto load_side = [&](int c) {
           if constexpr (!kIsBwd) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) bq[i] = __ldg(reinterpret_cast<const float4*>(bias + 64 * c + 32 * hf) + i);
+            for (int g = 0; g < 4; ++g) {
+              const float4* b4 = reinterpret_cast<const float4*>(bias + 64 * c + 16 * g + 8 * hf);
+              bq[2 * g] = __ldg(b4);
+              bq[2 * g + 1] = __ldg(b4 + 1);
+            }
           } else {
             if (masked) {
               const uint8_t* plane = mask_img + (int64_t)c * kAChunkBytes;
 #pragma unroll
-              for (int jj = 0; jj < 4; ++jj)
-                mq[jj] = __ldg(reinterpret_cast<const uint4*>(plane + row * 128u + (((4u * hf + jj) ^ (row & 7u)) << 4)));
+              for (int g = 0; g < 4; ++g)
+                mq[g] = __ldg(reinterpret_cast<const uint4*>(plane + row * 128u + (((2u * g + hf) ^ (row & 7u)) << 4)));
             }
           }
         };
@@ -420,90 +463,99 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
         mbar_wait(bar(kBarAccFull), acc_phase);
         acc_phase ^= 1u;
         tc_fence_after_sync();
+        const bool feeds_mma = !last;                     // the last epilogue of a tile produces no further GEMM input
+        const bool produces_chunk = feeds_mma || kIsBwd;  // backward's last output (d head pre-activation) is saved for dw
         for (int c = 0; c < kAChunks; ++c) {
-          const uint32_t col = 64u * c + 32u * hf;
+          // TMEM reads are issued one k-step ahead: tcgen05.wait::ld waits for everything outstanding, so group g is
+          // consumed while only group g+1 is in flight (the first 16 columns never wait for the whole 64-column read)
           uint32_t r[32];
-          tmem_ld32(tmem_row + (from_h ? kTmemH : kTmemZ) + col, r);
+          const uint32_t tacc = tmem_row + (from_h ? kTmemH : kTmemZ) + 64u * c + 8u * hf;
+          tmem_ld8(tacc, &r[0]);
           if (c > 0) load_side(c);
-          tmem_ld_wait();
-          float v[32];
-          if constexpr (!kIsBwd) {
+          if (produces_chunk) wait_saved(c, false);
+          const uint32_t chunk_addr = smem_base + kSmemA + c * kAChunkBytes;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + bq[i].x;
-              v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bq[i].y;
-              v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bq[i].z;
-              v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bq[i].w;
-            }
-            if (relu) {
+          for (int g = 0; g < 4; ++g) {
+            tmem_ld_wait();
+            if (g < 3) tmem_ld8(tacc + 16u * (g + 1), &r[8 * (g + 1)]);
+            const uint32_t col = 64u * c + 16u * g + 8u * hf;
+            float v[8];
+            if constexpr (!kIsBwd) {
+              v[0] = __uint_as_float(r[8 * g + 0]) + bq[2 * g].x;
+              v[1] = __uint_as_float(r[8 * g + 1]) + bq[2 * g].y;
+              v[2] = __uint_as_float(r[8 * g + 2]) + bq[2 * g].z;
+              v[3] = __uint_as_float(r[8 * g + 3]) + bq[2 * g].w;
+              v[4] = __uint_as_float(r[8 * g + 4]) + bq[2 * g + 1].x;
+              v[5] = __uint_as_float(r[8 * g + 5]) + bq[2 * g + 1].y;
+              v[6] = __uint_as_float(r[8 * g + 6]) + bq[2 * g + 1].z;
+              v[7] = __uint_as_float(r[8 * g + 7]) + bq[2 * g + 1].w;
+              if (relu) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-            }
-            if (l == 0) {
-              // z_0 = h: seed the TMEM residual stream and keep h for the outer skip (:543)
-#pragma unroll
-              for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(v[i]);
-              tmem_st32(tmem_row + kTmemZ + col, r);
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                reinterpret_cast<float4*>(hrow + col)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-              tmem_st_wait();
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-            if (last) {  // + dL/dz_43 through the outer skip
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 g4 = reinterpret_cast<const float4*>(hrow + col)[i];
-                v[4 * i] += g4.x; v[4 * i + 1] += g4.y; v[4 * i + 2] += g4.z; v[4 * i + 3] += g4.w;
+                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
               }
-            }
-            if (masked) {
-              // ReLU mask from the hi plane of the saved forward operand (a > 0  <=>  bf16 hi != 0; a >= 0 always)
+              if (l == 0) {
+                // z_0 = h: seed the TMEM residual stream and keep h for the outer skip (:543)
+                uint32_t w[8];
 #pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                const uint32_t w[4] = {mq[jj].x, mq[jj].y, mq[jj].z, mq[jj].w};
+                for (int i = 0; i < 8; ++i) w[i] = __float_as_uint(v[i]);
+                tmem_st8(tmem_row + kTmemZ + col, w);
+                reinterpret_cast<float4*>(hrow + col)[0] = make_float4(v[0], v[1], v[2], v[3]);
+                reinterpret_cast<float4*>(hrow + col)[1] = make_float4(v[4], v[5], v[6], v[7]);
+                tmem_st_wait();
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * g + i]);
+              if (last) {  // + dL/dz_43 through the outer skip
+                const float4 g0 = reinterpret_cast<const float4*>(hrow + col)[0];
+                const float4 g1 = reinterpret_cast<const float4*>(hrow + col)[1];
+                v[0] += g0.x; v[1] += g0.y; v[2] += g0.z; v[3] += g0.w;
+                v[4] += g1.x; v[5] += g1.y; v[6] += g1.z; v[7] += g1.w;
+              }
+              if (masked) {
+                // ReLU mask from the hi plane of the saved forward operand (a > 0  <=>  bf16 hi != 0; a >= 0 always)
+                const uint32_t w[4] = {mq[g].x, mq[g].y, mq[g].z, mq[g].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  if ((w[e] & 0x00007FFFu) == 0u) v[8 * jj + 2 * e] = 0.f;
-                  if ((w[e] & 0x7FFF0000u) == 0u) v[8 * jj + 2 * e + 1] = 0.f;
+                  if ((w[e] & 0x00007FFFu) == 0u) v[2 * e] = 0.f;
+                  if ((w[e] & 0x7FFF0000u) == 0u) v[2 * e + 1] = 0.f;
+                }
+              }
+            }
+            if (produces_chunk) {
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) split2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+              const uint32_t off = row * 128u + (((2u * g + hf) ^ (row & 7u)) << 4);
+              st_shared_v4(chunk_addr + off, hi[0], hi[1], hi[2], hi[3]);
+              st_shared_v4(chunk_addr + kPlaneBytes + off, lo[0], lo[1], lo[2], lo[3]);
+              if (c == 0) publish_kstep(g);
+            }
+            if constexpr (!kIsBwd) {
+              if (last) {
+                // tail: rgb = sigmoid(W_t (z_43 + h) + b_t), partial dot over my 8 columns
+                float zf[8];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                  const float4 h4 = reinterpret_cast<const float4*>(hrow + col)[i];
+                  const float4 w0 = __ldg(reinterpret_cast<const float4*>(tailw + col) + i);
+                  const float4 w1 = __ldg(reinterpret_cast<const float4*>(tailw + kWidth + col) + i);
+                  const float4 w2 = __ldg(reinterpret_cast<const float4*>(tailw + 2 * kWidth + col) + i);
+                  const float z0 = v[4 * i] + h4.x, z1 = v[4 * i + 1] + h4.y, z2 = v[4 * i + 2] + h4.z, z3 = v[4 * i + 3] + h4.w;
+                  zf[4 * i] = z0; zf[4 * i + 1] = z1; zf[4 * i + 2] = z2; zf[4 * i + 3] = z3;
+                  dot0 = fmaf(z0, w0.x, dot0); dot0 = fmaf(z1, w0.y, dot0); dot0 = fmaf(z2, w0.z, dot0); dot0 = fmaf(z3, w0.w, dot0);
+                  dot1 = fmaf(z0, w1.x, dot1); dot1 = fmaf(z1, w1.y, dot1); dot1 = fmaf(z2, w1.z, dot1); dot1 = fmaf(z3, w1.w, dot1);
+                  dot2 = fmaf(z0, w2.x, dot2); dot2 = fmaf(z1, w2.y, dot2); dot2 = fmaf(z2, w2.z, dot2); dot2 = fmaf(z3, w2.w, dot2);
+                }
+                if (MODE == kFwdTrain && valid) {  // z_43 + h for the tail weight gradient
+                  float* zrow = p.zf_out + grow * kWidth + col;
+                  reinterpret_cast<float4*>(zrow)[0] = make_float4(zf[0], zf[1], zf[2], zf[3]);
+                  reinterpret_cast<float4*>(zrow)[1] = make_float4(zf[4], zf[5], zf[6], zf[7]);
                 }
               }
             }
           }
-          const bool feeds_mma = !last;          // the last epilogue of a tile produces no further GEMM input
-          const bool produces_chunk = feeds_mma || kIsBwd;  // backward's last output (d head pre-activation) is saved for dw
-          if (produces_chunk) {
-            wait_saved(c, false);
-            store_a_half(smem_base + kSmemA + c * kAChunkBytes, row, hf, v);
-            publish(c);
-          }
-          if constexpr (!kIsBwd) {
-            if (last) {
-              // tail: rgb = sigmoid(W_t (z_43 + h) + b_t), partial dot over my 32 columns
-              float zf[32];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 h4 = reinterpret_cast<const float4*>(hrow + col)[i];
-                const float4 w0 = __ldg(reinterpret_cast<const float4*>(tailw + col) + i);
-                const float4 w1 = __ldg(reinterpret_cast<const float4*>(tailw + kWidth + col) + i);
-                const float4 w2 = __ldg(reinterpret_cast<const float4*>(tailw + 2 * kWidth + col) + i);
-                const float z0 = v[4 * i] + h4.x, z1 = v[4 * i + 1] + h4.y, z2 = v[4 * i + 2] + h4.z,
-                            z3 = v[4 * i + 3] + h4.w;
-                zf[4 * i] = z0; zf[4 * i + 1] = z1; zf[4 * i + 2] = z2; zf[4 * i + 3] = z3;
-                dot0 = fmaf(z0, w0.x, dot0); dot0 = fmaf(z1, w0.y, dot0); dot0 = fmaf(z2, w0.z, dot0); dot0 = fmaf(z3, w0.w, dot0);
-                dot1 = fmaf(z0, w1.x, dot1); dot1 = fmaf(z1, w1.y, dot1); dot1 = fmaf(z2, w1.z, dot1); dot1 = fmaf(z3, w1.w, dot1);
-                dot2 = fmaf(z0, w2.x, dot2); dot2 = fmaf(z1, w2.y, dot2); dot2 = fmaf(z2, w2.z, dot2); dot2 = fmaf(z3, w2.w, dot2);
-              }
-              if (MODE == kFwdTrain && valid) {  // z_43 + h for the tail weight gradient
-                float* zrow = p.zf_out + grow * kWidth + col;
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  reinterpret_cast<float4*>(zrow)[i] = make_float4(zf[4 * i], zf[4 * i + 1], zf[4 * i + 2], zf[4 * i + 3]);
-              }
-            }
-          }
+          if (produces_chunk && c > 0) publish(c);
         }
       }
       if constexpr (!kIsBwd) {

@@ -73,6 +73,8 @@ cudaError_t launch_raw2outputs(const float* raw, const float* z_vals, const floa
                                int white_bkgd, float* rgb_map, float* disp_map, float* acc_map, float* weights,
                                float* depth_map, cudaStream_t stream);
 cudaError_t launch_embed(const float* x, float* out, int64_t n, int dim, int L, int style, cudaStream_t stream);
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2, float eps,
+                        float step_size, float inv_bc2_sqrt, cudaStream_t stream);
 cudaError_t launch_umma_selftest(const float* A, const void* images, float* C, cudaStream_t stream);
 
 }  // namespace r2l

@@ -1,0 +1,50 @@
+// Adam on the flat parameter buffer: one HBM-bound pass (reads p, g, m, v; writes p, m, v = 28 B/parameter).
+// Reference: torch.optim.Adam(params, lr=args.lrate, betas=(0.9, 0.999)) at main.py:465 stepping 176 tensors
+// (main.py:1406); same update rule, defaults amsgrad=False, weight_decay=0, maximize=False.  SURVEY.md row N3.
+#include "kernels.cuh"
+
+namespace r2l {
+
+__global__ void __launch_bounds__(256) r2l_adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                       float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                       float beta1, float beta2, float eps, float step_size,
+                                                       float inv_bc2_sqrt) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float* pa = &pp.x; const float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ma[k] = ma[k] + (ga[k] - ma[k]) * (1.f - beta1);                 // exp_avg.lerp_(grad, 1 - beta1)
+      va[k] = va[k] * beta2 + (1.f - beta2) * ga[k] * ga[k];           // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
+      const float denom = sqrtf(va[k]) * inv_bc2_sqrt + eps;           // (sqrt(v) / sqrt(bias_correction2)) + eps
+      pa[k] = pa[k] - step_size * (ma[k] / denom);                     // param.addcdiv_(exp_avg, denom, -lr / bias_correction1)
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  // tail (n is not a multiple of 4: 5,917,187 = 4 * 1,479,296 + 3)
+  for (int64_t i = 4 * n4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gi = g[i];
+    const float mi = m[i] + (gi - m[i]) * (1.f - beta1);
+    const float vi = v[i] * beta2 + (1.f - beta2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] = p[i] - step_size * (mi / (sqrtf(vi) * inv_bc2_sqrt + eps));
+  }
+}
+
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2, float eps,
+                        float step_size, float inv_bc2_sqrt, cudaStream_t stream) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  r2l_adam_kernel<<<sms * 8, 256, 0, stream>>>(p, g, m, v, n, beta1, beta2, eps, step_size, inv_bc2_sqrt);
+  return cudaGetLastError();
+}
+
+}  // namespace r2l

@@ -288,3 +288,23 @@ def test_teacher_render_pipeline_matches_oracle(golden_teacher, teacher):
     rgb, disp, acc, w, depth = nb.raw2outputs(teacher.query(pts, vd), z, rd, 0, True)
     np.testing.assert_allclose(rgb.cpu().numpy(), t["r2o_net_rgb"], rtol=1e-3, atol=1e-4)
     np.testing.assert_allclose(w.cpu().numpy(), t["r2o_net_weights"], rtol=1e-3, atol=1e-5)
+
+
+def test_flat_adam_matches_torch_adam():
+    """r2l_adam_step vs torch.optim.Adam (the reference's optimizer, main.py:465) over 5 steps with a changing lr."""
+    from r2l_b200.optim import FlatAdam
+    torch.manual_seed(0)
+    n = nb.NUM_PARAMS
+    p0 = torch.randn(n, device=DEV) * 0.05
+    a, b = torch.nn.Parameter(p0.clone()), torch.nn.Parameter(p0.clone())
+    oa, ob = FlatAdam([a], lr=5e-4), torch.optim.Adam([b], lr=5e-4)
+    for step in range(5):
+        g = torch.randn(n, device=DEV) * (10.0 ** -(step % 3))
+        for opt, q in ((oa, a), (ob, b)):
+            opt.param_groups[0]["lr"] = 5e-4 * 0.9 ** step
+            q.grad = g.clone()
+            v = q._version
+            opt.step()
+            assert q._version > v
+    assert float((a - b).abs().max()) < 2e-7
+    assert float((oa.state[a]["exp_avg_sq"] - ob.state[b]["exp_avg_sq"]).abs().max() / ob.state[b]["exp_avg_sq"].abs().max()) < 1e-6
