@@ -78,6 +78,17 @@ int r2l_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, 
                     int white_bkgd, float* rgb_map, float* disp_map, float* acc_map, float* weights, float* depth_map,
                     void* stream);
 
+/* Hierarchical resampling on the GPU: sample_pdf (utils/run_nerf_raybased_helpers.py:283-330) on
+ * bins = mid-points of z_vals and weights[..., 1:-1], then the sorted merge torch.sort(cat(z_vals, z_samples))
+ * (utils/create_data.py:503-515).  u[ray*u_stride + j] are the uniforms (u_stride 0 = one shared row, det=True uses
+ * linspace(0,1,n_importance)).  Outputs z_samples[N,n_importance], z_merged[N,n_samples+n_importance] ascending. */
+int r2l_sample_pdf_merge(const float* z_vals, const float* weights, const float* u, int64_t u_stride, int64_t n_rays,
+                         int n_samples, int n_importance, float* z_samples, float* z_merged, void* stream);
+
+/* sample_pdf alone with the reference's own arguments: bins[N,n_bins], weights[N,n_bins-1] -> z_samples[N,n_importance]. */
+int r2l_sample_pdf(const float* bins, const float* weights, const float* u, int64_t u_stride, int64_t n_rays, int n_bins,
+                   int n_importance, float* z_samples, void* stream);
+
 /* Dense positional encoding x[N,dim] -> out[N, dim*(2*n_freqs+1)].
  * style 0: PositionalEmbedder.__call__ (:198-208) layout; style 1: Embedder.embed (:54-55, get_embedder :58-73) layout. */
 int r2l_positional_embed(const float* x, float* out, int64_t n, int dim, int n_freqs, int style, void* stream);
@@ -91,6 +102,9 @@ int r2l_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
  * [0] MMA wait on head A chunks, [1] on body A chunks, [2] on weight stages, [3] producer wait on free stages,
  * [4] MMA-thread total. */
 int r2l_debug_set_stats(long long* stats);
+
+/* Debug: tensor-pipe micro-benchmark; out_cycles[grid] = cycles for `reps` x 48 tcgen05.mma (M128 N256 K16). */
+int r2l_debug_mma_rate(int reps, int grid, long long* out_cycles, void* stream);
 
 /* Debug / test hook: C[128,256] = A[128,256] * W_l^T through one tcgen05 layer step, l = body layer 0..85. */
 int r2l_selftest_layer(const float* A, const void* packed, int layer, float* C, void* stream);

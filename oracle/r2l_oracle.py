@@ -270,3 +270,24 @@ def sample_pdf(bins: np.ndarray, weights: np.ndarray, n_samples: int, u: np.ndar
     denom = np.where(denom < dt(1e-5), np.ones_like(denom), denom)
     t = (u - cdf_g0) / denom
     return bins_g0 + t * (bins_g1 - bins_g0)
+
+
+def render_rays(rays_o, rays_d, viewdirs, near, far, params_coarse, params_fine, n_samples=64, n_importance=128,
+                white_bkgd=True):
+    """render_rays utils/create_data.py:405-544 with perturb = 0, lindisp False, raw_noise_std 0: coarse pass, deterministic
+    inverse-CDF resampling (:503-511), sorted merge (:513-515), fine pass."""
+    dt = rays_o.dtype.type
+    t = torch_linspace(0., 1., n_samples, rays_o.dtype.type)
+    z = np.broadcast_to(dt(near) * (dt(1.) - t) + dt(far) * t, (rays_o.shape[0], n_samples)).astype(rays_o.dtype)
+    pts = rays_o[..., None, :] + rays_d[..., None, :] * z[..., :, None]
+    raw = run_network(pts, viewdirs, params_coarse)
+    rgb0, disp0, acc0, weights, depth0 = raw2outputs(raw, z, rays_d, white_bkgd)
+    z_mid = dt(.5) * (z[..., 1:] + z[..., :-1])
+    u = np.broadcast_to(torch_linspace(0., 1., n_importance, rays_o.dtype.type), (rays_o.shape[0], n_importance))
+    z_samples = sample_pdf(z_mid, weights[..., 1:-1], n_importance, u)
+    z_all = np.sort(np.concatenate([z, z_samples], -1), -1)
+    pts = rays_o[..., None, :] + rays_d[..., None, :] * z_all[..., :, None]
+    raw = run_network(pts, viewdirs, params_fine)
+    rgb, disp, acc, w, depth = raw2outputs(raw, z_all, rays_d, white_bkgd)
+    return {"rgb_map": rgb, "disp_map": disp, "acc_map": acc, "depth_map": depth, "rgb0": rgb0, "disp0": disp0,
+            "acc0": acc0, "z_samples": z_samples, "z_vals": z_all, "weights0": weights}

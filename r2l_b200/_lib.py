@@ -36,10 +36,13 @@ _PROTOTYPES = {
     "r2l_teacher_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "r2l_raw2outputs": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p]),
+    "r2l_sample_pdf_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "r2l_sample_pdf": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "r2l_positional_embed": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "r2l_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int64,
                               c_void_p]),
     "r2l_debug_set_stats": (c_int, [c_void_p]),
+    "r2l_debug_mma_rate": (c_int, [c_int, c_int, c_void_p, c_void_p]),
     "r2l_selftest_layer": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
 }
 

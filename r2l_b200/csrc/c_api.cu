@@ -178,6 +178,26 @@ int r2l_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, 
                                        weights, depth_map, (cudaStream_t)stream), "r2l_raw2outputs");
 }
 
+int r2l_sample_pdf_merge(const float* z_vals, const float* weights, const float* u, int64_t u_stride, int64_t n_rays,
+                         int n_samples, int n_importance, float* z_samples, float* z_merged, void* stream) {
+  if (n_rays == 0) return 0;
+  if (n_rays < 0 || n_samples < 3 || n_importance < 1 || n_samples > 1024 || n_importance > 2048 || u_stride < 0)
+    return fail("r2l_sample_pdf_merge: %s", "bad sizes");
+  if (!z_vals || !weights || !u || !z_samples || !z_merged) return fail("r2l_sample_pdf_merge: %s", "null pointer");
+  return check(r2l::launch_sample_pdf_merge(z_vals, weights, u, u_stride, n_rays, n_samples, n_importance, z_samples, z_merged,
+                                            nullptr, (cudaStream_t)stream), "r2l_sample_pdf_merge");
+}
+
+int r2l_sample_pdf(const float* bins, const float* weights, const float* u, int64_t u_stride, int64_t n_rays, int n_bins,
+                   int n_importance, float* z_samples, void* stream) {
+  if (n_rays == 0) return 0;
+  if (n_rays < 0 || n_bins < 2 || n_importance < 1 || n_bins > 1023 || n_importance > 2048 || u_stride < 0)
+    return fail("r2l_sample_pdf: %s", "bad sizes");
+  if (!bins || !weights || !u || !z_samples) return fail("r2l_sample_pdf: %s", "null pointer");
+  return check(r2l::launch_sample_pdf_merge(nullptr, weights, u, u_stride, n_rays, n_bins + 1, n_importance, z_samples, nullptr,
+                                            bins, (cudaStream_t)stream), "r2l_sample_pdf");
+}
+
 int r2l_positional_embed(const float* x, float* out, int64_t n, int dim, int n_freqs, int style, void* stream) {
   if (n == 0) return 0;
   if (n < 0 || dim <= 0 || n_freqs <= 0 || n_freqs > 24 || (style != 0 && style != 1))
@@ -230,6 +250,11 @@ int r2l_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
 int r2l_debug_set_stats(long long* stats) {
   g_stats = stats;
   return 0;
+}
+
+int r2l_debug_mma_rate(int reps, int grid, long long* out_cycles, void* stream) {
+  if (!out_cycles || reps < 1 || grid < 1) return fail("r2l_debug_mma_rate: %s", "bad arguments");
+  return check(r2l::launch_mma_rate(reps, grid, out_cycles, (cudaStream_t)stream), "r2l_debug_mma_rate");
 }
 
 int r2l_selftest_layer(const float* A, const void* packed, int layer, float* C, void* stream) {

@@ -664,6 +664,68 @@ __global__ void __launch_bounds__(128, 1) r2l_umma_selftest_kernel(const float* 
   if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
+// ----------------------------------------------------------------------------------------------
+// Micro-benchmark (debug): the tensor pipe alone.  Each CTA issues `reps` body-layer MMA patterns (4 chunks x
+// (A_hi W_hi, A_lo W_hi, A_hi W_lo) x 4 k-steps = 48 instructions of M128 N256 K16) on resident operands, no TMA,
+// no epilogue, and reports the cycles.  6144 cycles per layer = the 8192 FLOP/cycle/SM peak.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) r2l_mma_rate_kernel(int reps, long long* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t wbase = smem_base + kABytes;
+  const uint32_t bar_m = smem_base + kABytes + 2 * kWImageBytes;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + kABytes + 2 * kWImageBytes + 16);
+  const int warp = threadIdx.x >> 5;
+  for (uint32_t i = threadIdx.x; i < (kABytes + 2 * kWImageBytes) / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem_gen)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    mbar_init(bar_m, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), 256);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 0) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 256, 0, 0);
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      for (int kc = 0; kc < kAChunks; ++kc) {
+        const uint32_t a_hi = smem_base + kc * kAChunkBytes, a_lo = a_hi + kPlaneBytes;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_bf16(tmem_base, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(wbase + 32 * ks, 16, 1024), idesc, 1u);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_bf16(tmem_base, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw128(wbase + 32 * ks, 16, 1024), idesc, 1u);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_bf16(tmem_base, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(wbase + kWImageBytes + 32 * ks, 16, 1024), idesc, 1u);
+      }
+    }
+    umma_commit(bar_m);
+    mbar_wait(bar_m, 0);
+    out[blockIdx.x] = clock64() - t0;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+cudaError_t launch_mma_rate(int reps, int grid, long long* out, cudaStream_t stream) {
+  const int smem = kABytes + 2 * kWImageBytes + 64 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(r2l_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  r2l_mma_rate_kernel<<<grid, 128, smem, stream>>>(reps, out);
+  return cudaGetLastError();
+}
+
 template <int MODE>
 static cudaError_t launch_chain_mode(const ChainParams& p, int grid, cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(r2l_chain_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -72,9 +72,12 @@ cudaError_t launch_tail_grads(const TailGradParams& p, bool zero_first, cudaStre
 cudaError_t launch_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, int64_t n_rays, int n_samples,
                                int white_bkgd, float* rgb_map, float* disp_map, float* acc_map, float* weights,
                                float* depth_map, cudaStream_t stream);
+cudaError_t launch_sample_pdf_merge(const float* z_vals, const float* weights, const float* u, int64_t u_stride, int64_t n_rays,
+                                    int S, int M, float* z_samples, float* z_merged, const float* bins_in, cudaStream_t stream);
 cudaError_t launch_embed(const float* x, float* out, int64_t n, int dim, int L, int style, cudaStream_t stream);
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2, float eps,
                         float step_size, float inv_bc2_sqrt, cudaStream_t stream);
+cudaError_t launch_mma_rate(int reps, int grid, long long* out, cudaStream_t stream);
 cudaError_t launch_umma_selftest(const float* A, const void* images, float* C, cudaStream_t stream);
 
 }  // namespace r2l

@@ -109,6 +109,96 @@ __global__ void __launch_bounds__(256) r2l_embed_kernel(const float* __restrict_
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Hierarchical resampling between the teacher's coarse and fine passes: inverse-CDF sampling of the coarse
+// weights followed by the sorted merge with the coarse depths, one warp per ray, no host round trip.
+// Reference: sample_pdf utils/run_nerf_raybased_helpers.py:283-330, call site utils/create_data.py:503-515 (which
+// moves the tensors to the CPU and back: SURVEY.md row N1).
+//   z_vals[N,S], weights[N,S] (coarse raw2outputs)  ->  z_samples[N,M], z_merged[N,S+M] (ascending)
+//   u: uniforms, element (ray, j) at u[ray*u_stride + j]  (u_stride = 0: one shared row, e.g. linspace for det=True)
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) r2l_sample_pdf_merge_kernel(const float* __restrict__ z_vals, const float* __restrict__ weights,
+                                                                   const float* __restrict__ u, int64_t u_stride, int64_t n_rays,
+                                                                   int S, int M, float* __restrict__ z_samples,
+                                                                   float* __restrict__ z_merged, const float* __restrict__ bins_in) {
+  extern __shared__ float smem_f[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int per_warp = 2 * S + S + M;
+  float* cdf = smem_f + wib * per_warp;     // [S-1]
+  float* bins = cdf + S;                    // [S-1]  z_vals_mid
+  float* vals = bins + S;                   // [S+M]
+  const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  if (ray >= n_rays) return;
+  // two calling forms: (z_vals[N,S], weights[N,S]) as render_rays has them, or explicit (bins[N,S-1], weights[N,S-2])
+  const float* z = bins_in ? nullptr : z_vals + ray * S;
+  const float* w = bins_in ? weights + ray * (S - 2) : weights + ray * S + 1;   // weights[..., 1:-1]
+  const int nb = S - 2;                     // number of pdf bins; cdf has nb + 1 = S - 1 entries, like z_vals_mid
+  float part = 0.f;
+  for (int b = lane; b < nb; b += 32) part += w[b] + 1e-5f;
+  const float total = warp_sum(part);
+  float carry = 0.f;
+  if (lane == 0) cdf[0] = 0.f;
+  for (int base = 0; base < nb; base += 32) {
+    const int b = base + lane;
+    float v = b < nb ? (w[b] + 1e-5f) / total : 0.f;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const float o = __shfl_up_sync(0xffffffffu, v, d);
+      if (lane >= d) v += o;
+    }
+    if (b < nb) cdf[b + 1] = carry + v;
+    carry += __shfl_sync(0xffffffffu, v, 31);
+  }
+  for (int b = lane; b < S - 1; b += 32) bins[b] = bins_in ? bins_in[ray * (S - 1) + b] : .5f * (z[b + 1] + z[b]);
+  if (z_merged)
+    for (int i = lane; i < S; i += 32) vals[i] = z[i];
+  __syncwarp();
+  const int last = S - 2;                   // cdf.shape[-1] - 1
+  for (int j = lane; j < M; j += 32) {
+    const float uj = u[ray * u_stride + j];
+    int lo = 0, hi = S - 1;                 // searchsorted(cdf, u, right=True): first index with cdf[idx] > u
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (cdf[mid] > uj) hi = mid; else lo = mid + 1;
+    }
+    const int below = max(0, lo - 1), above = min(last, lo);
+    const float c0 = cdf[below], c1 = cdf[above];
+    float denom = c1 - c0;
+    if (denom < 1e-5f) denom = 1.f;
+    const float t = (uj - c0) / denom;
+    const float smp = bins[below] + t * (bins[above] - bins[below]);
+    z_samples[ray * M + j] = smp;
+    vals[S + j] = smp;
+  }
+  __syncwarp();
+  if (!z_merged) return;
+  // sorted merge by rank counting (192 x 192 comparisons per ray, shared-memory broadcasts)
+  const int T = S + M;
+  for (int e = lane; e < T; e += 32) {
+    const float x = vals[e];
+    int rank = 0;
+    for (int k = 0; k < T; ++k) {
+      const float y = vals[k];
+      rank += (y < x) || (y == x && k < e);
+    }
+    z_merged[ray * T + rank] = x;
+  }
+}
+
+cudaError_t launch_sample_pdf_merge(const float* z_vals, const float* weights, const float* u, int64_t u_stride, int64_t n_rays,
+                                    int S, int M, float* z_samples, float* z_merged, const float* bins_in, cudaStream_t stream) {
+  const int warps = 8;
+  const size_t smem = (size_t)warps * (3 * S + M) * sizeof(float);
+  const int64_t blocks = (n_rays + warps - 1) / warps;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(r2l_sample_pdf_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  r2l_sample_pdf_merge_kernel<<<(unsigned)blocks, warps * 32, smem, stream>>>(z_vals, weights, u, u_stride, n_rays, S, M, z_samples,
+                                                                              z_merged, bins_in);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, int64_t n_rays, int n_samples,
                                int white_bkgd, float* rgb_map, float* disp_map, float* acc_map, float* weights,
                                float* depth_map, cudaStream_t stream) {

@@ -282,3 +282,49 @@ def teacher_forward(packed: torch.Tensor, *, pts=None, viewdirs=None, x_embedded
     with torch.cuda.device(pts.device):
         _lib.check(L.r2l_teacher_forward(_ptr(pts), _ptr(viewdirs), None, _ptr(packed), _ptr(raw), n * s, s, _stream()), "r2l_teacher_forward")
     return raw
+
+
+def sample_pdf_merge(z_vals: torch.Tensor, weights: torch.Tensor, n_importance: int, u: torch.Tensor | None = None):
+    """(z_samples[N,M], z_merged[N,S+M]) : inverse-CDF resampling of the coarse weights + sorted merge, on the GPU.
+    u None = deterministic linspace (perturb == 0); else uniforms [N,M] or [M]."""
+    z_vals = _require_cuda_f32(z_vals, "z_vals")
+    n, s = z_vals.shape
+    weights = _require_cuda_f32(weights, "weights", (s,))
+    dev = z_vals.device
+    if u is None:
+        u = torch.linspace(0., 1., steps=n_importance).to(dev)   # evaluated by torch exactly as the reference does
+    u = _require_cuda_f32(u, "u")
+    if u.dim() == 1 and u.shape[0] == n_importance:
+        stride = 0
+    elif tuple(u.shape) == (n, n_importance):
+        stride = n_importance
+    else:
+        raise ValueError(f"u: expected [{n_importance}] or [{n},{n_importance}], got {tuple(u.shape)}")
+    z_samples = torch.empty((n, n_importance), dtype=torch.float32, device=dev)
+    z_merged = torch.empty((n, s + n_importance), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().r2l_sample_pdf_merge(_ptr(z_vals), _ptr(weights), _ptr(u), stride, n, s, n_importance,
+                                                   _ptr(z_samples), _ptr(z_merged), _stream()), "r2l_sample_pdf_merge")
+    return z_samples, z_merged
+
+
+def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, n_importance: int, u: torch.Tensor | None = None) -> torch.Tensor:
+    """sample_pdf with the reference's arguments: bins[N,B], weights[N,B-1] -> samples[N,n_importance]."""
+    bins = _require_cuda_f32(bins, "bins")
+    n, b = bins.shape
+    weights = _require_cuda_f32(weights, "weights", (b - 1,))
+    dev = bins.device
+    if u is None:
+        u = torch.linspace(0., 1., steps=n_importance).to(dev)
+    u = _require_cuda_f32(u, "u")
+    if u.dim() == 1 and u.shape[0] == n_importance:
+        stride = 0
+    elif tuple(u.shape) == (n, n_importance):
+        stride = n_importance
+    else:
+        raise ValueError(f"u: expected [{n_importance}] or [{n},{n_importance}], got {tuple(u.shape)}")
+    out = torch.empty((n, n_importance), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().r2l_sample_pdf(_ptr(bins), _ptr(weights), _ptr(u), stride, n, b, n_importance, _ptr(out), _stream()),
+                   "r2l_sample_pdf")
+    return out

@@ -1,0 +1,96 @@
+"""Teacher volumetric rendering on the GPU: coarse query -> raw2outputs -> inverse-CDF resampling + sorted merge ->
+fine query -> raw2outputs, every stage a kernel of libr2l_b200 and no host round trip in between.
+
+Mirrors `render_rays` / `batchify_rays` / `render` of the reference's pseudo-data generator
+(utils/create_data.py:405-544, :80-94, :97-176; the same functions exist in main.py:624-756) — argument names, returned
+dictionary keys and numerics — for the path BASELINE.json calls "NeRF teacher pseudo-data generation".  The reference
+moves weights to the CPU for sample_pdf (create_data.py:506-511); here it stays on the device."""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from . import nerf_raybased as nb
+
+
+def sample_pdf(bins, weights, N_samples, det=False, pytest=False):
+    """utils/run_nerf_raybased_helpers.py:283-330 on the GPU: bins [N,B], weights [N,B-1] -> samples [N,N_samples]."""
+    if pytest:
+        raise NotImplementedError("r2l_b200 sample_pdf: the numpy-seeded pytest mode is not implemented")
+    u = None if det else torch.rand(list(weights.shape[:-1]) + [N_samples]).to(bins.device)
+    return ops.sample_pdf(bins, weights, N_samples, u)
+
+
+def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False, lindisp=False, perturb=0.,
+                N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0., verbose=False, pytest=False):
+    """Volumetric rendering of a ray batch [N, 8 or 11] = (o, d, near, far[, viewdir]); returns the reference's dict."""
+    if pytest:
+        raise NotImplementedError("r2l_b200 render_rays: the numpy-seeded pytest mode is not implemented")
+    dev = ray_batch.device
+    n_rays = ray_batch.shape[0]
+    rays_o, rays_d = ray_batch[:, 0:3].contiguous(), ray_batch[:, 3:6].contiguous()
+    viewdirs = ray_batch[:, -3:].contiguous() if ray_batch.shape[-1] > 8 else None
+    bounds = torch.reshape(ray_batch[..., 6:8], [-1, 1, 2])
+    near, far = bounds[..., 0], bounds[..., 1]
+    t_vals = torch.linspace(0., 1., steps=N_samples).to(dev)
+    if not lindisp:
+        z_vals = near * (1. - t_vals) + far * (t_vals)
+    else:
+        z_vals = 1. / (1. / near * (1. - t_vals) + 1. / far * (t_vals))
+    z_vals = z_vals.expand([n_rays, N_samples])
+    if perturb > 0.:
+        mids = .5 * (z_vals[..., 1:] + z_vals[..., :-1])
+        upper = torch.cat([mids, z_vals[..., -1:]], -1)
+        lower = torch.cat([z_vals[..., :1], mids], -1)
+        z_vals = lower + (upper - lower) * torch.rand(z_vals.shape).to(dev)
+    z_vals = z_vals.contiguous()
+    pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]
+    raw = network_query_fn(pts, viewdirs, network_fn)
+    rgb_map, disp_map, acc_map, weights, depth_map = nb.raw2outputs(raw, z_vals, rays_d, raw_noise_std, white_bkgd)
+    if N_importance > 0:
+        rgb_map_0, disp_map_0, acc_map_0 = rgb_map, disp_map, acc_map
+        u = None if perturb == 0. else torch.rand(n_rays, N_importance).to(dev)
+        z_samples, z_vals = ops.sample_pdf_merge(z_vals, weights, N_importance, u)     # sample_pdf + sort(cat(...))
+        pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]
+        run_fn = network_fn if network_fine is None else network_fine
+        raw = network_query_fn(pts, viewdirs, run_fn)
+        rgb_map, disp_map, acc_map, weights, depth_map = nb.raw2outputs(raw, z_vals, rays_d, raw_noise_std, white_bkgd)
+    ret = {'rgb_map': rgb_map, 'disp_map': disp_map, 'acc_map': acc_map, 'depth_map': depth_map}
+    if retraw:
+        ret['raw'] = raw
+    if N_importance > 0:
+        ret['rgb0'], ret['disp0'], ret['acc0'] = rgb_map_0, disp_map_0, acc_map_0
+        ret['z_std'] = torch.std(z_samples, dim=-1, unbiased=False)
+    return ret
+
+
+def batchify_rays(rays_flat, chunk=1024 * 32, **kwargs):
+    """Render rays in chunks (utils/create_data.py:80-94)."""
+    parts = {}
+    for i in range(0, rays_flat.shape[0], chunk):
+        for k, v in render_rays(rays_flat[i:i + chunk], **kwargs).items():
+            parts.setdefault(k, []).append(v)
+    return {k: torch.cat(v, 0) for k, v in parts.items()}
+
+
+def render(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
+           c2w_staticcam=None, **kwargs):
+    """Render a ray batch `rays = (rays_o, rays_d)` (utils/create_data.py:97-176).  Pose -> rays (`c2w`) and NDC
+    warping are the caller's job here (get_rays / ndc_rays are host glue outside this path): pass ndc=False."""
+    if c2w is not None or c2w_staticcam is not None or ndc:
+        raise NotImplementedError("r2l_b200 render: pass explicit rays with ndc=False (get_rays / ndc_rays are out of scope)")
+    rays_o, rays_d = rays
+    sh = rays_d.shape
+    viewdirs = None
+    if use_viewdirs:
+        viewdirs = rays_d / torch.norm(rays_d, dim=-1, keepdim=True)
+        viewdirs = torch.reshape(viewdirs, [-1, 3]).float()
+    rays_o = torch.reshape(rays_o, [-1, 3]).float()
+    rays_d = torch.reshape(rays_d, [-1, 3]).float()
+    near, far = near * torch.ones_like(rays_d[..., :1]), far * torch.ones_like(rays_d[..., :1])
+    rays_cat = torch.cat([rays_o, rays_d, near, far] + ([viewdirs] if use_viewdirs else []), -1)
+    all_ret = batchify_rays(rays_cat, chunk, **kwargs)
+    for k in all_ret:
+        all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))
+    k_extract = ['rgb_map', 'disp_map', 'acc_map']
+    return [all_ret[k] for k in k_extract] + [{k: v for k, v in all_ret.items() if k not in k_extract}]
