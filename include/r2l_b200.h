@@ -95,13 +95,18 @@ int r2l_positional_embed(const float* x, float* out, int64_t n, int dim, int n_f
 
 /* One Adam update of a flat fp32 buffer (torch.optim.Adam defaults: no amsgrad / weight decay; main.py:465,:1406).
  * `step` counts from 1.  28 bytes of HBM traffic per parameter in one pass. */
-int r2l_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
-                  float beta2, float eps, int64_t step, void* stream);
+int r2l_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                  double beta2, double eps, int64_t step, void* stream);
 
 /* Debug: device buffer [grid][8] of int64 cycle counters filled by the next r2l_forward calls (NULL = off):
  * [0] MMA wait on head A chunks, [1] on body A chunks, [2] on weight stages, [3] producer wait on free stages,
  * [4] MMA-thread total. */
 int r2l_debug_set_stats(long long* stats);
+
+/* Debug: device buffer [grid][5][96] of clock64 stamps for the first tile of each CTA of the next chain launches:
+ * row 0 MMA thread starts layer l, 1 MMA thread has issued layer l, 2 epilogue sees accumulator l complete,
+ * 3 epilogue published the first k-step of layer l's output, 4 epilogue finished layer l. NULL = off. */
+int r2l_debug_set_trace(long long* trace);
 
 /* Debug: tensor-pipe micro-benchmark; out_cycles[grid] = cycles for `reps` x 48 tcgen05.mma (M128 N256 K16). */
 int r2l_debug_mma_rate(int reps, int grid, long long* out_cycles, void* stream);

@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes
 import os
 import subprocess
-from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+from ctypes import c_char_p, c_double, c_int, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
@@ -39,9 +39,10 @@ _PROTOTYPES = {
     "r2l_sample_pdf_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "r2l_sample_pdf": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "r2l_positional_embed": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
-    "r2l_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int64,
+    "r2l_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_double, c_int64,
                               c_void_p]),
     "r2l_debug_set_stats": (c_int, [c_void_p]),
+    "r2l_debug_set_trace": (c_int, [c_void_p]),
     "r2l_debug_mma_rate": (c_int, [c_int, c_int, c_void_p, c_void_p]),
     "r2l_selftest_layer": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
 }

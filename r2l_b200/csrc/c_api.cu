@@ -9,6 +9,7 @@
 namespace {
 thread_local char g_err[512] = "";
 long long* g_stats = nullptr;  // debug cycle counters, see r2l_debug_set_stats
+long long* g_trace = nullptr;  // debug time stamps, see r2l_debug_set_trace
 
 int fail(const char* fmt, const char* detail) {
   snprintf(g_err, sizeof(g_err), fmt, detail);
@@ -91,6 +92,7 @@ int r2l_forward(int input_kind, const float* in0, const float* in1, const float*
   p.n_rays = n_rays;
   p.num_tiles = num_tiles(n_rays);
   p.stats = g_stats;
+  p.trace = g_trace;
   return check(r2l::launch_chain(r2l::kFwdInfer, p, fwd_grid(n_rays), (cudaStream_t)stream), "r2l_forward");
 }
 
@@ -121,6 +123,7 @@ int r2l_forward_train(int input_kind, const float* in0, const float* in1, const 
   p.n_rays = n_rays;
   p.num_tiles = num_tiles(n_rays);
   p.stats = g_stats;
+  p.trace = g_trace;
   return check(r2l::launch_chain(r2l::kFwdTrain, p, fwd_grid(n_rays), (cudaStream_t)stream), "r2l_forward_train");
 }
 
@@ -148,6 +151,7 @@ int r2l_backward(int input_kind, const void* packed, const float* rgb, const flo
   p.num_tiles = num_tiles(n_rays);
   p.input_kind = input_kind;
   p.stats = g_stats;
+  p.trace = g_trace;
   if (int rc = check(r2l::launch_chain(r2l::kBwd, p, fwd_grid(n_rays), st), "r2l_backward(chain)")) return rc;
   r2l::DwParams d;
   d.fwd_saved = p.fwd_saved;
@@ -234,21 +238,28 @@ int r2l_teacher_forward(const float* pts, const float* viewdirs, const float* x_
   return check(r2l::launch_teacher(p, fwd_grid(n_points), (cudaStream_t)stream), "r2l_teacher_forward");
 }
 
-int r2l_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
-                  float beta2, float eps, int64_t step, void* stream) {
+int r2l_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                  double beta2, double eps, int64_t step, void* stream) {
   if (n == 0) return 0;
   if (!params || !grads || !exp_avg || !exp_avg_sq) return fail("r2l_adam_step: %s", "null pointer");
   if (n < 0 || step < 1) return fail("r2l_adam_step: %s", "bad n or step (steps count from 1)");
   if (misaligned(params) || misaligned(grads) || misaligned(exp_avg) || misaligned(exp_avg_sq))
     return fail("r2l_adam_step: %s", "buffers must be 16-byte aligned");
-  const double bc1 = 1.0 - std::pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - std::pow((double)beta2, (double)step);
-  return check(r2l::launch_adam(params, grads, exp_avg, exp_avg_sq, n, beta1, beta2, eps, (float)((double)lr / bc1),
-                                (float)(1.0 / std::sqrt(bc2)), (cudaStream_t)stream), "r2l_adam_step");
+  // hyper-parameters arrive as doubles and are combined in double exactly as torch.optim.Adam does on the host
+  const double bc1 = 1.0 - std::pow(beta1, (double)step);
+  const double bc2 = 1.0 - std::pow(beta2, (double)step);
+  return check(r2l::launch_adam(params, grads, exp_avg, exp_avg_sq, n, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
+                                (float)eps, (float)(lr / bc1), (float)(1.0 / std::sqrt(bc2)), (cudaStream_t)stream),
+               "r2l_adam_step");
 }
 
 int r2l_debug_set_stats(long long* stats) {
   g_stats = stats;
+  return 0;
+}
+
+int r2l_debug_set_trace(long long* trace) {
+  g_trace = trace;
   return 0;
 }
 

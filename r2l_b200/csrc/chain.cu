@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
           const bool fresh = to_h || (!kIsBwd && l == 0);
           const bool ring = !kIsBwd && l == 0;   // head: A chunks recycle through the 4 slots
           const uint32_t d = tmem_base + (to_h ? kTmemH : kTmemZ);
+          const bool tr = p.trace != nullptr && tile == (int)blockIdx.x;
           for (int kc = 0; kc < nkc; ++kc) {
             const uint32_t slot = kc & 3;
             const uint32_t a_hi = smem_base + kSmemA + slot * kAChunkBytes;
@@ -200,6 +201,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
                 wait_a(kBarA0Sub + ks, 4 + ks);
+                if (tr && kc == 0 && ks == 0) p.trace[((int64_t)blockIdx.x * 5 + 0) * 96 + l] = clock64();
                 umma_bf16(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b_hi + 32 * ks, 16, 1024), idesc,
                           (fresh && kc == 0 && ks == 0) ? 0u : 1u);
                 umma_bf16(d, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw128(b_hi + 32 * ks, 16, 1024), idesc, 1u);
@@ -240,6 +242,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
             if (ring) umma_commit(bar(kBarAEmpty + slot));
           }
           umma_commit(bar(kBarAccFull));
+          if (tr) p.trace[((int64_t)blockIdx.x * 5 + 1) * 96 + l] = clock64();
         }
         if constexpr (kIsBwd) {
           // the last backward epilogue publishes 4 more chunks (d head pre-activation, consumed only by the
@@ -463,6 +466,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
         mbar_wait(bar(kBarAccFull), acc_phase);
         acc_phase ^= 1u;
         tc_fence_after_sync();
+        const bool tr = p.trace != nullptr && tile == (int)blockIdx.x && warp == 4 && lane == 0;
+        if (tr) p.trace[((int64_t)blockIdx.x * 5 + 2) * 96 + l] = clock64();
         const bool feeds_mma = !last;                     // the last epilogue of a tile produces no further GEMM input
         const bool produces_chunk = feeds_mma || kIsBwd;  // backward's last output (d head pre-activation) is saved for dw
         for (int c = 0; c < kAChunks; ++c) {
@@ -529,7 +534,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
               const uint32_t off = row * 128u + (((2u * g + hf) ^ (row & 7u)) << 4);
               st_shared_v4(chunk_addr + off, hi[0], hi[1], hi[2], hi[3]);
               st_shared_v4(chunk_addr + kPlaneBytes + off, lo[0], lo[1], lo[2], lo[3]);
-              if (c == 0) publish_kstep(g);
+              if (c == 0) {
+                publish_kstep(g);
+                if (tr && g == 0) p.trace[((int64_t)blockIdx.x * 5 + 3) * 96 + l] = clock64();
+              }
             }
             if constexpr (!kIsBwd) {
               if (last) {
@@ -557,6 +565,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
           }
           if (produces_chunk && c > 0) publish(c);
         }
+        if (tr) p.trace[((int64_t)blockIdx.x * 5 + 4) * 96 + l] = clock64();
       }
       if constexpr (!kIsBwd) {
         // combine the two column halves of each ray, sigmoid, store

@@ -20,6 +20,7 @@ struct ChainParams {
   float* rgb;             // forward out [N,3]
   float* scratch;         // [gridDim.x][128][256] fp32: head output (fwd) / dL/dz_43 (bwd) for the outer skip
   long long* stats;       // optional [gridDim.x][8] cycle counters (debug), nullptr in production
+  long long* trace;       // optional [gridDim.x][5][96] clock64 stamps of the first tile's layers (debug)
   // training
   uint8_t* saved;         // out: operand images this pass stores, [tile][chunk][32 KiB]
   float* zf_out;          // kFwdTrain out: z_43 + h, [N,256] fp32
@@ -75,7 +76,7 @@ cudaError_t launch_raw2outputs(const float* raw, const float* z_vals, const floa
 cudaError_t launch_sample_pdf_merge(const float* z_vals, const float* weights, const float* u, int64_t u_stride, int64_t n_rays,
                                     int S, int M, float* z_samples, float* z_merged, const float* bins_in, cudaStream_t stream);
 cudaError_t launch_embed(const float* x, float* out, int64_t n, int dim, int L, int style, cudaStream_t stream);
-cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2, float eps,
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float w1, float beta2, float w2, float eps,
                         float step_size, float inv_bc2_sqrt, cudaStream_t stream);
 cudaError_t launch_mma_rate(int reps, int grid, long long* out, cudaStream_t stream);
 cudaError_t launch_umma_selftest(const float* A, const void* images, float* C, cudaStream_t stream);

@@ -7,8 +7,8 @@ namespace r2l {
 
 __global__ void __launch_bounds__(256) r2l_adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                        float* __restrict__ m, float* __restrict__ v, int64_t n,
-                                                       float beta1, float beta2, float eps, float step_size,
-                                                       float inv_bc2_sqrt) {
+                                                       float w1, float beta2, float w2, float eps, float step_size,
+                                                       float inv_bc2_sqrt) {   // w1 = 1 - beta1, w2 = 1 - beta2
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n4 = n >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -19,8 +19,8 @@ __global__ void __launch_bounds__(256) r2l_adam_kernel(float* __restrict__ p, co
     float* pa = &pp.x; const float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      ma[k] = ma[k] + (ga[k] - ma[k]) * (1.f - beta1);                 // exp_avg.lerp_(grad, 1 - beta1)
-      va[k] = va[k] * beta2 + (1.f - beta2) * ga[k] * ga[k];           // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
+      ma[k] = ma[k] + (ga[k] - ma[k]) * w1;                 // exp_avg.lerp_(grad, 1 - beta1)
+      va[k] = __fmaf_rn(w2 * ga[k], ga[k], va[k] * beta2);           // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
       const float denom = sqrtf(va[k]) * inv_bc2_sqrt + eps;           // (sqrt(v) / sqrt(bias_correction2)) + eps
       pa[k] = pa[k] - step_size * (ma[k] / denom);                     // param.addcdiv_(exp_avg, denom, -lr / bias_correction1)
     }
@@ -31,19 +31,19 @@ __global__ void __launch_bounds__(256) r2l_adam_kernel(float* __restrict__ p, co
   // tail (n is not a multiple of 4: 5,917,187 = 4 * 1,479,296 + 3)
   for (int64_t i = 4 * n4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float gi = g[i];
-    const float mi = m[i] + (gi - m[i]) * (1.f - beta1);
-    const float vi = v[i] * beta2 + (1.f - beta2) * gi * gi;
+    const float mi = m[i] + (gi - m[i]) * w1;
+    const float vi = __fmaf_rn(w2 * gi, gi, v[i] * beta2);
     m[i] = mi; v[i] = vi;
     p[i] = p[i] - step_size * (mi / (sqrtf(vi) * inv_bc2_sqrt + eps));
   }
 }
 
-cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2, float eps,
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float w1, float beta2, float w2, float eps,
                         float step_size, float inv_bc2_sqrt, cudaStream_t stream) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  r2l_adam_kernel<<<sms * 8, 256, 0, stream>>>(p, g, m, v, n, beta1, beta2, eps, step_size, inv_bc2_sqrt);
+  r2l_adam_kernel<<<sms * 8, 256, 0, stream>>>(p, g, m, v, n, w1, beta2, w2, eps, step_size, inv_bc2_sqrt);
   return cudaGetLastError();
 }
 
