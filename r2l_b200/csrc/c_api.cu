@@ -2,6 +2,7 @@
 #include <cstdio>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 
 #include "../../include/r2l_b200.h"
 #include "kernels.cuh"
@@ -26,6 +27,27 @@ int sm_count() {
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
   return n;
 }
+// side stream + events per device for the concurrent dW launch of r2l_backward
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+std::mutex g_side_mutex;
+SideStream g_side[64];
+SideStream* side_stream() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(g_side_mutex);
+  SideStream& s = g_side[dev];
+  if (!s.stream) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  return &s;
+}
+constexpr size_t kReadyBytes = 512;   // 87 int counters, padded
+
 int num_tiles(int64_t n_rays) { return (int)((n_rays + r2l::kTileM - 1) / r2l::kTileM); }
 int fwd_grid(int64_t n_rays) {
   const int sms = sm_count();
@@ -47,7 +69,7 @@ size_t r2l_fwd_workspace_bytes(int64_t n_rays) {
   if (sms <= 0) sms = 148;
   const int t = num_tiles(n_rays);
   const int g = t < sms ? t : sms;
-  return (size_t)(g > 0 ? g : 1) * r2l::kTileM * r2l::kWidth * sizeof(float);
+  return (size_t)(g > 0 ? g : 1) * r2l::kTileM * r2l::kWidth * sizeof(float) + kReadyBytes;
 }
 
 int r2l_pack_weights(const float* params, void* packed, void* stream) {
@@ -152,7 +174,11 @@ int r2l_backward(int input_kind, const void* packed, const float* rgb, const flo
   p.input_kind = input_kind;
   p.stats = g_stats;
   p.trace = g_trace;
-  if (int rc = check(r2l::launch_chain(r2l::kBwd, p, fwd_grid(n_rays), st), "r2l_backward(chain)")) return rc;
+  // When the chain grid (one CTA per tile) and the 90 weight-gradient CTAs fit on the GPU together, run them
+  // concurrently: dw.cu starts on each layer as soon as every tile has stored that layer's dY operand.
+  const int grid = fwd_grid(n_rays);
+  SideStream* side = (grid + 90 <= sm_count()) ? side_stream() : nullptr;
+  int* ready = reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + r2l_fwd_workspace_bytes(n_rays) - kReadyBytes);
   r2l::DwParams d;
   d.fwd_saved = p.fwd_saved;
   d.bwd_saved = p.saved;
@@ -160,7 +186,21 @@ int r2l_backward(int input_kind, const void* packed, const float* rgb, const flo
   d.num_tiles = p.num_tiles;
   d.input_kind = input_kind;
   d.accumulate = 0;
-  if (int rc = check(r2l::launch_dw(d, st), "r2l_backward(dw)")) return rc;
+  d.ready = nullptr;
+  if (side) {
+    if (int rc = check(cudaMemsetAsync(ready, 0, kReadyBytes, st), "r2l_backward(memset)")) return rc;
+    p.ready = ready;
+    d.ready = ready;
+    if (int rc = check(cudaEventRecord(side->fork, st), "r2l_backward(fork)")) return rc;
+    if (int rc = check(cudaStreamWaitEvent(side->stream, side->fork, 0), "r2l_backward(fork wait)")) return rc;
+    if (int rc = check(r2l::launch_chain(r2l::kBwd, p, grid, st), "r2l_backward(chain)")) return rc;
+    if (int rc = check(r2l::launch_dw(d, side->stream), "r2l_backward(dw)")) return rc;
+    if (int rc = check(cudaEventRecord(side->join, side->stream), "r2l_backward(join)")) return rc;
+    if (int rc = check(cudaStreamWaitEvent(st, side->join, 0), "r2l_backward(join wait)")) return rc;
+  } else {
+    if (int rc = check(r2l::launch_chain(r2l::kBwd, p, grid, st), "r2l_backward(chain)")) return rc;
+    if (int rc = check(r2l::launch_dw(d, st), "r2l_backward(dw)")) return rc;
+  }
   r2l::TailGradParams t;
   t.zf = zf;
   t.rgb = rgb;

@@ -272,8 +272,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
       // epilogue rewrites a slot exactly 4 chunks after it published it, so this lag can never deadlock.
       uint32_t a_phase = 0;
       int64_t issued = 0;
+      const bool signal = kIsBwd && p.ready != nullptr;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         uint8_t* dst = p.saved + (int64_t)tile * kSavedChunksPerTile * kAChunkBytes;
+        int signalled = 0;   // operand groups (4 chunks = one layer's dY) of this tile already announced
         for (int i = 0; i < kSavedChunksPerTile; ++i, ++issued) {
           const uint32_t slot = i & 3;   // first chunks cycle the ring; body chunk c lives in slot c
           mbar_wait(bar(slot == 0 ? kBarA0Sub + 3 : kBarAFull + slot), (a_phase >> slot) & 1u);
@@ -284,6 +286,16 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
             bulk_wait_read<3>();         // store (issued - 3) has read its slot
             mbar_arrive(bar(kBarASaved + ((slot + 1) & 3)));
           }
+          if (signal && slot == 3) {
+            // everything but the 4 stores just issued has landed in global memory: announce those groups so the
+            // weight-gradient kernel (running concurrently on idle SMs) may start on their layers
+            bulk_wait_all<4>();
+            for (; signalled < (i >> 2); ++signalled) flag_release_add(p.ready + signalled);
+          }
+        }
+        if (signal) {
+          bulk_wait_all<0>();
+          for (; signalled < kSavedChunksPerTile / 4; ++signalled) flag_release_add(p.ready + signalled);
         }
       }
       // drain: release the last three slots in issue order, then wait for the writes to land

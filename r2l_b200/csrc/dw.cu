@@ -71,6 +71,17 @@ __global__ void __launch_bounds__(kDwThreads, 1) r2l_dw_kernel(const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {
+      if (p.ready != nullptr) {
+        // concurrent mode: the backward chain kernel is still running on other SMs; wait until every tile has stored
+        // the dY operand of this unit's layer (group index = position of that layer in the backward sweep)
+        const int group = is_head ? kBodyLayers : (kBodyLayers - 1 - layer);
+        unsigned ns = 64;
+        while (flag_acquire_load(p.ready + group) < p.num_tiles) {
+          __nanosleep(ns);
+          if (ns < 2048) ns <<= 1;
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy acquire -> async-proxy (TMA) reads
+      }
       for (int it = 0; it < num_stages_total; ++it) {
         const uint32_t s = it % kDwStages, ph = (it / kDwStages) & 1u;
         const int tile = it >> 2, qr = it & 3;

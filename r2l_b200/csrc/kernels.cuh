@@ -27,6 +27,8 @@ struct ChainParams {
   const uint8_t* fwd_saved;  // kBwd in: the forward pass's `saved`
   const float* rgb_in;    // kBwd in: forward rgb [N,3]
   const float* grad_rgb;  // kBwd in: dL/d rgb [N,3]
+  int* ready;             // kBwd out (optional): [87] counters, ready[g] += 1 when this CTA's tile has stored operand group g
+                          // (g = 0: dL/dz_43, g = 1 + j: output of backward epilogue j); lets dw.cu run concurrently
   int64_t n_rays;
   int num_tiles;
   int input_kind;
@@ -43,6 +45,7 @@ struct DwParams {
   int num_tiles;
   int input_kind;         // kInputX: head features in natural order, else fused-PE order
   int accumulate;
+  const int* ready;       // optional: wait until ready[group of this unit] == num_tiles before streaming (see ChainParams)
 };
 
 struct TailGradParams {

@@ -97,6 +97,17 @@ __device__ __forceinline__ void bulk_wait_all() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// cross-kernel readiness flags (a producer kernel's bulk stores -> a consumer kernel's bulk loads)
+__device__ __forceinline__ void flag_release_add(int* flag) {
+  asm volatile("fence.proxy.async;" ::: "memory");          // async-proxy global writes -> generic proxy
+  asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(flag) : "memory");
+}
+__device__ __forceinline__ int flag_acquire_load(const int* flag) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+  return v;
+}
+
 // ----------------------------------------------------------------------------------------------
 // TMEM allocation (one full warp executes these)
 // ----------------------------------------------------------------------------------------------
