@@ -51,7 +51,10 @@ int r2l_forward(int input_kind, const float* in0, const float* in1, const float*
  *   fwd_saved : r2l_train_fwd_saved_bytes(n) bytes; the bf16 hi/lo input operand of every Linear
  *   bwd_saved : r2l_train_bwd_saved_bytes(n) bytes; the bf16 hi/lo output-gradient operand of every Linear
  *   grads     : [R2L_NUM_PARAMS] fp32 in state_dict order, OVERWRITTEN with dL/dparams given grad_rgb = dL/drgb
- * `workspace` as in r2l_forward.  The three kernels of r2l_backward are enqueued back to back on `stream`. */
+ * `workspace`: r2l_bwd_workspace_bytes(n) bytes.  r2l_backward enqueues three kernels on `stream`; when the chain
+ * grid leaves >= 90 SMs idle the weight-gradient kernel runs concurrently on an internal side stream (joined back
+ * into `stream` before the call returns control of the stream order). */
+size_t r2l_bwd_workspace_bytes(int64_t n_rays);   /* workspace of r2l_backward (>= the forward's) */
 size_t r2l_train_fwd_saved_bytes(int64_t n_rays);
 size_t r2l_train_bwd_saved_bytes(int64_t n_rays);
 int r2l_forward_train(int input_kind, const float* in0, const float* in1, const float* t_rand, const float* z_lo,
@@ -105,7 +108,8 @@ int r2l_debug_set_stats(long long* stats);
 
 /* Debug: device buffer [grid][5][96] of clock64 stamps for the first tile of each CTA of the next chain launches:
  * row 0 MMA thread starts layer l, 1 MMA thread has issued layer l, 2 epilogue sees accumulator l complete,
- * 3 epilogue published the first k-step of layer l's output, 4 epilogue finished layer l. NULL = off. */
+ * 3 epilogue published the first k-step of layer l's output, 4 epilogue finished layer l; followed by [90][4]
+ * %globaltimer stamps of the weight-gradient kernel (start, flag seen, -, end).  NULL = off. */
 int r2l_debug_set_trace(long long* trace);
 
 /* Debug: tensor-pipe micro-benchmark; out_cycles[grid] = cycles for `reps` x 48 tcgen05.mma (M128 N256 K16). */

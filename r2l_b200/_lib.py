@@ -25,6 +25,7 @@ _PROTOTYPES = {
     "r2l_pack_weights": (c_int, [c_void_p, c_void_p, c_void_p]),
     "r2l_forward": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                             c_void_p, c_size_t, c_int64, c_void_p]),
+    "r2l_bwd_workspace_bytes": (c_size_t, [c_int64]),
     "r2l_train_fwd_saved_bytes": (c_size_t, [c_int64]),
     "r2l_train_bwd_saved_bytes": (c_size_t, [c_int64]),
     "r2l_forward_train": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -46,7 +46,9 @@ SideStream* side_stream() {
   }
   return &s;
 }
-constexpr size_t kReadyBytes = 512;   // 87 int counters, padded
+constexpr size_t kReadyBytes = 1024;  // 87 readiness counters + 90 reduction tickets (ints), padded
+constexpr int kDwSplits = 4;          // ray-tile ranges per weight-gradient unit in the concurrent mode
+constexpr size_t kDwPartialBytes = (size_t)90 * kDwSplits * (256 * 256 + 256) * sizeof(float);
 
 int num_tiles(int64_t n_rays) { return (int)((n_rays + r2l::kTileM - 1) / r2l::kTileM); }
 int fwd_grid(int64_t n_rays) {
@@ -118,6 +120,8 @@ int r2l_forward(int input_kind, const float* in0, const float* in1, const float*
   return check(r2l::launch_chain(r2l::kFwdInfer, p, fwd_grid(n_rays), (cudaStream_t)stream), "r2l_forward");
 }
 
+size_t r2l_bwd_workspace_bytes(int64_t n_rays) { return r2l_fwd_workspace_bytes(n_rays) + kDwPartialBytes; }
+
 size_t r2l_train_fwd_saved_bytes(int64_t n_rays) {
   return (size_t)num_tiles(n_rays) * r2l::kFwdSavedChunks * r2l::kAChunkBytes;
 }
@@ -157,7 +161,7 @@ int r2l_backward(int input_kind, const void* packed, const float* rgb, const flo
   if (!packed || !rgb || !grad_rgb || !zf || !fwd_saved || !bwd_saved || !grads || !workspace)
     return fail("r2l_backward: %s", "null pointer");
   if (input_kind < 0 || input_kind > 2) return fail("r2l_backward: %s", "unknown input_kind");
-  if (workspace_bytes < r2l_fwd_workspace_bytes(n_rays)) return fail("r2l_backward: %s", "workspace too small");
+  if (workspace_bytes < r2l_bwd_workspace_bytes(n_rays)) return fail("r2l_backward: %s", "workspace too small (see r2l_bwd_workspace_bytes)");
   if (misaligned(packed) || misaligned(workspace) || misaligned(fwd_saved) || misaligned(bwd_saved) || misaligned(zf) || misaligned(grads))
     return fail("r2l_backward: %s", "buffers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
@@ -187,10 +191,17 @@ int r2l_backward(int input_kind, const void* packed, const float* rgb, const flo
   d.input_kind = input_kind;
   d.accumulate = 0;
   d.ready = nullptr;
+  d.splits = 1;
+  d.partials = nullptr;
+  d.tickets = nullptr;
+  d.times = g_trace ? g_trace + 148 * 5 * 96 : nullptr;   // the dW stamps follow the chain kernel's trace rows
   if (side) {
     if (int rc = check(cudaMemsetAsync(ready, 0, kReadyBytes, st), "r2l_backward(memset)")) return rc;
     p.ready = ready;
     d.ready = ready;
+    d.splits = p.num_tiles >= 2 * kDwSplits ? kDwSplits : 1;
+    d.partials = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + r2l_fwd_workspace_bytes(n_rays));
+    d.tickets = ready + 128;
     if (int rc = check(cudaEventRecord(side->fork, st), "r2l_backward(fork)")) return rc;
     if (int rc = check(cudaStreamWaitEvent(side->stream, side->fork, 0), "r2l_backward(fork wait)")) return rc;
     if (int rc = check(r2l::launch_chain(r2l::kBwd, p, grid, st), "r2l_backward(chain)")) return rc;

@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
         }
       }
       if (p.stats) {
+        p.stats[blockIdx.x * 8 + 5] = global_timer_ns();
         p.stats[blockIdx.x * 8 + 0] = t_a_head;
         p.stats[blockIdx.x * 8 + 1] = t_a_body;
         p.stats[blockIdx.x * 8 + 2] = t_w;

@@ -13,6 +13,10 @@
 //   warp 2     TMEM allocator: two fp32 accumulators [128 x 256] (output rows 0-127 and 128-255) = 512 columns
 //   warps 4-7  bias gradient: column sums of dY straight from the staged smem tiles; then the epilogue
 //              (TMEM -> registers -> global)
+// Split mode (p.splits > 1, used when the kernel overlaps the backward chain on otherwise idle SMs): each unit is cut
+// into `splits` ray-tile ranges so that the pieces finishing after the chain are short; a piece writes its partial
+// dW / db to scratch and the LAST piece of a unit to arrive (atomic ticket) sums the partials in fixed order - the
+// result does not depend on which piece was last.  CTAs are ordered by the time their layer becomes available.
 // Autograd equivalent in the reference: the weight/bias gradients torch.autograd produces for every
 // nn.Linear of NeRF_v3_2 (model/nerf_raybased.py:500,:453-456) under loss.backward() (main.py:1404).
 #include "kernels.cuh"
@@ -43,14 +47,19 @@ __global__ void __launch_bounds__(kDwThreads, 1) r2l_dw_kernel(const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int unit = blockIdx.x;
-  const bool is_head = unit >= kBodyLayers;
-  const int layer = unit;                 // body layer 0..85 when !is_head
-  const int hg = unit - kBodyLayers;      // head feature group 0..3 (256 encoded features each)
+  // CTA order = order in which the backward sweep releases the layers: body layer 85 first ... layer 0, then the head
+  const int splits = p.splits > 1 ? p.splits : 1;
+  const int ob = blockIdx.x / splits, split = blockIdx.x % splits;
+  const bool is_head = ob >= kBodyLayers;
+  const int layer = kBodyLayers - 1 - ob;  // body layer 0..85 when !is_head
+  const int hg = ob - kBodyLayers;         // head feature group 0..3 (256 encoded features each)
+  const int unit = is_head ? ob : layer;   // index used by the debug stamps
+  const int tile_lo = (int)((int64_t)p.num_tiles * split / splits);
+  const int tile_hi = (int)((int64_t)p.num_tiles * (split + 1) / splits);
   // chunk offsets inside a tile's saved images (see chain.cu for the order they are written in)
   const int x_chunk0 = is_head ? 4 * hg : kSamples + 4 * layer;
   const int dy_chunk0 = is_head ? kAChunks + 4 * (kBodyLayers - 1) : kAChunks + 4 * (kBodyLayers - 2 - layer);
-  const int num_stages_total = p.num_tiles * (kTileM / kDwRowsPerStage);
+  const int num_stages_total = (tile_hi - tile_lo) * (kTileM / kDwRowsPerStage);
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kDwStages; ++s) {
@@ -71,10 +80,11 @@ __global__ void __launch_bounds__(kDwThreads, 1) r2l_dw_kernel(const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {
+      if (p.times) p.times[unit * 4 + 0] = global_timer_ns();
       if (p.ready != nullptr) {
         // concurrent mode: the backward chain kernel is still running on other SMs; wait until every tile has stored
         // the dY operand of this unit's layer (group index = position of that layer in the backward sweep)
-        const int group = is_head ? kBodyLayers : (kBodyLayers - 1 - layer);
+        const int group = is_head ? kBodyLayers : ob;
         unsigned ns = 64;
         while (flag_acquire_load(p.ready + group) < p.num_tiles) {
           __nanosleep(ns);
@@ -82,9 +92,10 @@ __global__ void __launch_bounds__(kDwThreads, 1) r2l_dw_kernel(const __grid_cons
         }
         asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy acquire -> async-proxy (TMA) reads
       }
+      if (p.times) p.times[unit * 4 + 1] = global_timer_ns();
       for (int it = 0; it < num_stages_total; ++it) {
         const uint32_t s = it % kDwStages, ph = (it / kDwStages) & 1u;
-        const int tile = it >> 2, qr = it & 3;
+        const int tile = tile_lo + (it >> 2), qr = it & 3;
         mbar_wait(bar_empty(s), ph ^ 1u);
         mbar_arrive_expect_tx(bar_full(s), kDwStageBytes);
         const uint8_t* dy = p.bwd_saved + ((int64_t)tile * kBwdSavedChunks + dy_chunk0) * kAChunkBytes + qr * kDwPiece;
@@ -144,8 +155,18 @@ __global__ void __launch_bounds__(kDwThreads, 1) r2l_dw_kernel(const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_empty(s));
     }
+    // where the results go: straight into the gradient buffer, or (split mode) into this piece's scratch slot
+    constexpr int kUnitFloats = kWidth * kWidth + kWidth;            // dW [256][256] + db [256]
+    float* part = splits > 1 ? p.partials + ((int64_t)ob * splits + split) * kUnitFloats : nullptr;
+    auto head_feature = [&](int col) {
+      const int chunk = 4 * hg + (col >> 6), slot = col & 63;
+      return p.input_kind == kInputX ? (64 * chunk + slot < kInDim ? 64 * chunk + slot : -1) : fused_slot_to_feature(chunk, slot);
+    };
     // bias gradient (head groups all compute the same sum; group 0 writes it)
-    if (!is_head || hg == 0) {
+    if (part) {
+      part[kWidth * kWidth + 2 * t] = s0;
+      part[kWidth * kWidth + 2 * t + 1] = s1;
+    } else if (!is_head || hg == 0) {
       float* db = p.grads + (is_head ? kOffHeadB : off_body_b(layer)) + 2 * t;
       if (p.accumulate) { db[0] += s0; db[1] += s1; } else { db[0] = s0; db[1] = s1; }
     }
@@ -160,27 +181,54 @@ __global__ void __launch_bounds__(kDwThreads, 1) r2l_dw_kernel(const __grid_cons
         uint32_t r[32];
         tmem_ld32(tmem_row + 256u * half + 32u * c8, r);
         tmem_ld_wait();
-        if (!is_head) {
-          float4* dst = reinterpret_cast<float4*>(p.grads + off_body_w(layer) + (int64_t)o * kWidth + 32 * c8);
+        if (part || !is_head) {
+          float4* dst = reinterpret_cast<float4*>((part ? part : p.grads + off_body_w(layer)) + (int64_t)o * kWidth + 32 * c8);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float4 v = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
                                    __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-            if (p.accumulate) { const float4 a = dst[i]; v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
+            if (!part && p.accumulate) { const float4 a = dst[i]; v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
             dst[i] = v;
           }
         } else {
           float* dst = p.grads + kOffHeadW + (int64_t)o * kInDim;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const int col = 32 * c8 + i;            // column inside this 256-feature group
-            const int chunk = 4 * hg + (col >> 6);  // K-chunk of the head GEMM
-            const int slot = col & 63;
-            const int feat = p.input_kind == kInputX ? (64 * chunk + slot < kInDim ? 64 * chunk + slot : -1)
-                                                      : fused_slot_to_feature(chunk, slot);
+            const int feat = head_feature(32 * c8 + i);
             if (feat >= 0) {
               const float v = __uint_as_float(r[i]);
               if (p.accumulate) dst[feat] += v; else dst[feat] = v;
+            }
+          }
+        }
+      }
+    }
+    if (part) {
+      // ticket: the last piece of this unit to finish reduces all partials in index order (deterministic result)
+      __threadfence();
+      named_bar_sync(2, 128);
+      int* ticket_smem = reinterpret_cast<int*>(smem_gen + kDwSmemBar + 96);
+      if (t == 0) *ticket_smem = atomicAdd(p.tickets + ob, 1);
+      named_bar_sync(2, 128);
+      if (*ticket_smem == splits - 1) {
+        __threadfence();
+        const float* base = p.partials + (int64_t)ob * splits * kUnitFloats;
+        for (int idx = (int)t; idx < kUnitFloats; idx += 128) {
+          float acc = 0.f;
+          for (int sp = 0; sp < splits; ++sp) acc += __ldcg(base + (int64_t)sp * kUnitFloats + idx);
+          if (idx >= kWidth * kWidth) {
+            if (!is_head || hg == 0) {
+              float* db = p.grads + (is_head ? kOffHeadB : off_body_b(layer)) + (idx - kWidth * kWidth);
+              *db = p.accumulate ? *db + acc : acc;
+            }
+          } else if (!is_head) {
+            float* w = p.grads + off_body_w(layer) + idx;
+            *w = p.accumulate ? *w + acc : acc;
+          } else {
+            const int feat = head_feature(idx & (kWidth - 1));
+            if (feat >= 0) {
+              float* w = p.grads + kOffHeadW + (int64_t)(idx >> 8) * kInDim + feat;
+              *w = p.accumulate ? *w + acc : acc;
             }
           }
         }
@@ -192,6 +240,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) r2l_dw_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after_sync();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (p.times && threadIdx.x == 0) p.times[unit * 4 + 3] = global_timer_ns();
 }
 
 // tail.0.weight / tail.0.bias gradients: dW_t[c,j] = sum_n dlogit[n,c] (z_43 + h)[n,j]; 768+3 outputs, CUDA cores.
@@ -231,7 +280,7 @@ __global__ void __launch_bounds__(256) r2l_tail_grad_kernel(const __grid_constan
 cudaError_t launch_dw(const DwParams& p, cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(r2l_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDwSmemBytes);
   if (e != cudaSuccess) return e;
-  r2l_dw_kernel<<<kDwUnits, kDwThreads, kDwSmemBytes, stream>>>(p);
+  r2l_dw_kernel<<<kDwUnits * (p.splits > 1 ? p.splits : 1), kDwThreads, kDwSmemBytes, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -45,6 +45,10 @@ struct DwParams {
   int num_tiles;
   int input_kind;         // kInputX: head features in natural order, else fused-PE order
   int accumulate;
+  int splits;             // >1: each unit is cut into ray-tile ranges, partial results in `partials`, last piece reduces
+  float* partials;        // [90][splits][256*256 + 256] scratch (split mode)
+  int* tickets;           // [90] zeroed counters (split mode)
+  long long* times;       // optional debug: [unit][4] globaltimer stamps (start, flag seen, MMAs done, end)
   const int* ready;       // optional: wait until ready[group of this unit] == num_tiles before streaming (see ChainParams)
 };
 

@@ -97,6 +97,12 @@ __device__ __forceinline__ void bulk_wait_all() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
+__device__ __forceinline__ long long global_timer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // cross-kernel readiness flags (a producer kernel's bulk stores -> a consumer kernel's bulk loads)
 __device__ __forceinline__ void flag_release_add(int* flag) {
   asm volatile("fence.proxy.async;" ::: "memory");          // async-proxy global writes -> generic proxy

@@ -202,7 +202,7 @@ def backward(packed: torch.Tensor, ctx: TrainContext, grad_rgb: torch.Tensor, gr
         raise ValueError("grads: expected a contiguous float32 CUDA tensor of NUM_PARAMS elements")
     with torch.cuda.device(dev):
         bwd_saved = _pooled(dev, "bwd", int(L.r2l_train_bwd_saved_bytes(ctx.n)))
-        wbytes = int(L.r2l_fwd_workspace_bytes(ctx.n))
+        wbytes = int(L.r2l_bwd_workspace_bytes(ctx.n))
         ws = _workspace(dev, wbytes)
         _lib.check(L.r2l_backward(ctx.kind, _ptr(packed), _ptr(ctx.rgb), _ptr(grad_rgb), _ptr(ctx.zf),
                                   _ptr(ctx.fwd_saved), _ptr(bwd_saved), _ptr(grads), _ptr(ws), wbytes, ctx.n,
