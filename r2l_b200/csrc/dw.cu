@@ -213,22 +213,48 @@ __global__ void __launch_bounds__(kDwThreads, 1) r2l_dw_kernel(const __grid_cons
       if (*ticket_smem == splits - 1) {
         __threadfence();
         const float* base = p.partials + (int64_t)ob * splits * kUnitFloats;
-        for (int idx = (int)t; idx < kUnitFloats; idx += 128) {
-          float acc = 0.f;
-          for (int sp = 0; sp < splits; ++sp) acc += __ldcg(base + (int64_t)sp * kUnitFloats + idx);
-          if (idx >= kWidth * kWidth) {
-            if (!is_head || hg == 0) {
-              float* db = p.grads + (is_head ? kOffHeadB : off_body_b(layer)) + (idx - kWidth * kWidth);
-              *db = p.accumulate ? *db + acc : acc;
+        // float4 per thread, 4 independent vectors per iteration: 16 L2 loads in flight per thread (latency-bound loop)
+        constexpr int kVecs = kUnitFloats / 4;   // 16448
+        for (int v0 = (int)t; v0 < kVecs; v0 += 4 * 128) {
+          float4 acc[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int sp = 0; sp < splits; ++sp) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int v = v0 + 128 * j;
+              if (v < kVecs) {
+                const float4 x = __ldcg(reinterpret_cast<const float4*>(base + (int64_t)sp * kUnitFloats) + v);
+                acc[j].x += x.x; acc[j].y += x.y; acc[j].z += x.z; acc[j].w += x.w;
+              }
             }
-          } else if (!is_head) {
-            float* w = p.grads + off_body_w(layer) + idx;
-            *w = p.accumulate ? *w + acc : acc;
-          } else {
-            const int feat = head_feature(idx & (kWidth - 1));
-            if (feat >= 0) {
-              float* w = p.grads + kOffHeadW + (int64_t)(idx >> 8) * kInDim + feat;
-              *w = p.accumulate ? *w + acc : acc;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int v = v0 + 128 * j;
+            if (v >= kVecs) continue;
+            const int idx = 4 * v;
+            const float a[4] = {acc[j].x, acc[j].y, acc[j].z, acc[j].w};
+            if (idx >= kWidth * kWidth) {
+              if (!is_head || hg == 0) {
+                float* db = p.grads + (is_head ? kOffHeadB : off_body_b(layer)) + (idx - kWidth * kWidth);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) db[e] = p.accumulate ? db[e] + a[e] : a[e];
+              }
+            } else if (!is_head) {
+              float4* w = reinterpret_cast<float4*>(p.grads + off_body_w(layer) + idx);
+              float4 o4 = acc[j];
+              if (p.accumulate) { const float4 c4 = *w; o4.x += c4.x; o4.y += c4.y; o4.z += c4.z; o4.w += c4.w; }
+              *w = o4;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int feat = head_feature((idx + e) & (kWidth - 1));
+                if (feat >= 0) {
+                  float* w = p.grads + kOffHeadW + (int64_t)((idx + e) >> 8) * kInDim + feat;
+                  *w = p.accumulate ? *w + a[e] : a[e];
+                }
+              }
             }
           }
         }
