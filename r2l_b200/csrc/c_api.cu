@@ -47,7 +47,7 @@ SideStream* side_stream() {
   return &s;
 }
 constexpr size_t kReadyBytes = 1024;  // 87 readiness counters + 90 reduction tickets (ints), padded
-constexpr int kDwSplits = 4;          // ray-tile ranges per weight-gradient unit in the concurrent mode
+constexpr int kDwSplits = 8;          // ray-tile ranges per weight-gradient unit in the concurrent mode
 constexpr size_t kDwPartialBytes = (size_t)90 * kDwSplits * (256 * 256 + 256) * sizeof(float);
 
 int num_tiles(int64_t n_rays) { return (int)((n_rays + r2l::kTileM - 1) / r2l::kTileM); }

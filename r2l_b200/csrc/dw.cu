@@ -203,57 +203,67 @@ __global__ void __launch_bounds__(kDwThreads, 1) r2l_dw_kernel(const __grid_cons
         }
       }
     }
-    if (part) {
-      // ticket: the last piece of this unit to finish reduces all partials in index order (deterministic result)
+    if (part) __threadfence();   // partial sums visible before this CTA takes its ticket (below, whole CTA)
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (splits > 1) {
+    // ticket: the last piece of this unit to finish reduces all partials in index order (deterministic result),
+    // with the whole CTA and 8 independent float4 loads per thread in flight (the loop is L2-latency bound)
+    constexpr int kUnitFloats = kWidth * kWidth + kWidth;
+    int* ticket_smem = reinterpret_cast<int*>(smem_gen + kDwSmemBar + 96);
+    if (threadIdx.x == 0) *ticket_smem = atomicAdd(p.tickets + ob, 1);
+    __syncthreads();
+    if (*ticket_smem == splits - 1) {
       __threadfence();
-      named_bar_sync(2, 128);
-      int* ticket_smem = reinterpret_cast<int*>(smem_gen + kDwSmemBar + 96);
-      if (t == 0) *ticket_smem = atomicAdd(p.tickets + ob, 1);
-      named_bar_sync(2, 128);
-      if (*ticket_smem == splits - 1) {
-        __threadfence();
-        const float* base = p.partials + (int64_t)ob * splits * kUnitFloats;
-        // float4 per thread, 4 independent vectors per iteration: 16 L2 loads in flight per thread (latency-bound loop)
-        constexpr int kVecs = kUnitFloats / 4;   // 16448
-        for (int v0 = (int)t; v0 < kVecs; v0 += 4 * 128) {
-          float4 acc[4];
+      auto head_feature = [&](int col) {
+        const int chunk = 4 * hg + (col >> 6), slot = col & 63;
+        return p.input_kind == kInputX ? (64 * chunk + slot < kInDim ? 64 * chunk + slot : -1) : fused_slot_to_feature(chunk, slot);
+      };
+      const float* base = p.partials + (int64_t)ob * splits * kUnitFloats;
+      constexpr int kVecs = kUnitFloats / 4;   // 16448
+      constexpr int kU = 8;
+      for (int v0 = (int)threadIdx.x; v0 < kVecs; v0 += kU * kDwThreads) {
+        float4 acc[kU];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int sp = 0; sp < splits; ++sp) {
+        for (int j = 0; j < kU; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int sp = 0; sp < splits; ++sp) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int v = v0 + 128 * j;
-              if (v < kVecs) {
-                const float4 x = __ldcg(reinterpret_cast<const float4*>(base + (int64_t)sp * kUnitFloats) + v);
-                acc[j].x += x.x; acc[j].y += x.y; acc[j].z += x.z; acc[j].w += x.w;
-              }
+          for (int j = 0; j < kU; ++j) {
+            const int v = v0 + kDwThreads * j;
+            if (v < kVecs) {
+              const float4 x = __ldcg(reinterpret_cast<const float4*>(base + (int64_t)sp * kUnitFloats) + v);
+              acc[j].x += x.x; acc[j].y += x.y; acc[j].z += x.z; acc[j].w += x.w;
             }
           }
+        }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int v = v0 + 128 * j;
-            if (v >= kVecs) continue;
-            const int idx = 4 * v;
-            const float a[4] = {acc[j].x, acc[j].y, acc[j].z, acc[j].w};
-            if (idx >= kWidth * kWidth) {
-              if (!is_head || hg == 0) {
-                float* db = p.grads + (is_head ? kOffHeadB : off_body_b(layer)) + (idx - kWidth * kWidth);
+        for (int j = 0; j < kU; ++j) {
+          const int v = v0 + kDwThreads * j;
+          if (v >= kVecs) continue;
+          const int idx = 4 * v;
+          const float a[4] = {acc[j].x, acc[j].y, acc[j].z, acc[j].w};
+          if (idx >= kWidth * kWidth) {
+            if (!is_head || hg == 0) {
+              float* db = p.grads + (is_head ? kOffHeadB : off_body_b(layer)) + (idx - kWidth * kWidth);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) db[e] = p.accumulate ? db[e] + a[e] : a[e];
-              }
-            } else if (!is_head) {
-              float4* w = reinterpret_cast<float4*>(p.grads + off_body_w(layer) + idx);
-              float4 o4 = acc[j];
-              if (p.accumulate) { const float4 c4 = *w; o4.x += c4.x; o4.y += c4.y; o4.z += c4.z; o4.w += c4.w; }
-              *w = o4;
-            } else {
+              for (int e = 0; e < 4; ++e) db[e] = p.accumulate ? db[e] + a[e] : a[e];
+            }
+          } else if (!is_head) {
+            float4* w = reinterpret_cast<float4*>(p.grads + off_body_w(layer) + idx);
+            float4 o4 = acc[j];
+            if (p.accumulate) { const float4 c4 = *w; o4.x += c4.x; o4.y += c4.y; o4.z += c4.z; o4.w += c4.w; }
+            *w = o4;
+          } else {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int feat = head_feature((idx + e) & (kWidth - 1));
-                if (feat >= 0) {
-                  float* w = p.grads + kOffHeadW + (int64_t)((idx + e) >> 8) * kInDim + feat;
-                  *w = p.accumulate ? *w + a[e] : a[e];
-                }
+            for (int e = 0; e < 4; ++e) {
+              const int feat = head_feature((idx + e) & (kWidth - 1));
+              if (feat >= 0) {
+                float* w = p.grads + kOffHeadW + (int64_t)((idx + e) >> 8) * kInDim + feat;
+                *w = p.accumulate ? *w + a[e] : a[e];
               }
             }
           }
@@ -261,11 +271,6 @@ __global__ void __launch_bounds__(kDwThreads, 1) r2l_dw_kernel(const __grid_cons
       }
     }
   }
-
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
   if (p.times && threadIdx.x == 0) p.times[unit * 4 + 3] = global_timer_ns();
 }
 
