@@ -17,8 +17,9 @@
 //   warp 2      TMEM allocator (512 columns: Z [0,256) = residual stream / running gradient,
 //               H [256,512) = block hidden / its gradient)
 //   warp 3      (train / bwd) operand-image store warp: smem A chunk -> HBM via bulk async stores
-//   warps 4-11  epilogue / encoder: two threads per ray (column halves). They build the first A operand
-//               (positional encoding, or dL/dz_43) and after every layer turn the fp32 accumulator into the
+//   warps 4-19  epilogue / encoder: FOUR threads per ray (16 warps = 4 per SM sub-partition, so that TMEM-read and
+//               fence latencies of one warp hide behind the arithmetic of the others). They build the first A
+//               operand (positional encoding, or dL/dz_43) and after every layer turn the fp32 accumulator into the
 //               next layer's bf16 hi/lo A operand in shared memory (bias/ReLU or mask, split, 128B swizzle).
 //
 // TMEM residency of the residual stream: Z holds z_k - sum_{j<k} b2_j (forward) or g_k (backward) in fp32;
@@ -31,8 +32,8 @@
 namespace r2l {
 
 constexpr int kNumWStages = 3;
-constexpr int kChainThreads = 384;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;
+constexpr int kChainThreads = (4 + kEpiWarps) * 32;   // 640
 constexpr uint32_t kSmemA = 0;
 constexpr uint32_t kSmemW = kABytes;                                  // 131072
 constexpr uint32_t kSmemBar = kSmemW + kNumWStages * kWImageBytes;    // 229376
@@ -57,12 +58,13 @@ enum : uint32_t {
   kBarCount = kBarA0Sub + 4
 };
 
-template <int HF>
-__device__ __forceinline__ void encode_half(const float (&x)[3], float (&out)[32]) {
+// Quarter QT of a fused-order K chunk: 16 slots = 8 (sin, cos) pairs; the last quarter ends with x0,x1,x2,0.
+template <int QT>
+__device__ __forceinline__ void encode_quarter(const float (&x)[3], float (&out)[16]) {
   // fused feature order of layout.cuh: slot 2p = sin, 2p+1 = cos, pair p = coordinate*10 + frequency
 #pragma unroll
-  for (int i = 0; i < (HF == 0 ? 16 : 14); ++i) {
-    const int p = HF * 16 + i;
+  for (int i = 0; i < (QT < 3 ? 8 : 6); ++i) {
+    const int p = QT * 8 + i;
     const int c = p / kFreqs, f = p % kFreqs;
     const float arg = __fmul_rn(x[c], static_cast<float>(1 << f));  // exact: power-of-two scale
     float s, co;
@@ -70,26 +72,22 @@ __device__ __forceinline__ void encode_half(const float (&x)[3], float (&out)[32
     out[2 * i] = s;
     out[2 * i + 1] = co;
   }
-  if (HF == 1) {
-    out[28] = x[0];
-    out[29] = x[1];
-    out[30] = x[2];
-    out[31] = 0.f;
+  if (QT == 3) {
+    out[12] = x[0];
+    out[13] = x[1];
+    out[14] = x[2];
+    out[15] = 0.f;
   }
 }
 
-// Write 32 consecutive K-values of one row into an A chunk (both planes).
-__device__ __forceinline__ void store_a_half(uint32_t a_chunk_addr, uint32_t row, uint32_t hf,
-                                             const float (&v)[32]) {
+// One 16-byte operand unit (8 consecutive K-values of one row), both planes.
+__device__ __forceinline__ void store_a_unit(uint32_t a_chunk_addr, uint32_t row, uint32_t unit, const float* v) {
+  uint32_t hi[4], lo[4];
 #pragma unroll
-  for (int jj = 0; jj < 4; ++jj) {
-    uint32_t hi[4], lo[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) split2(v[8 * jj + 2 * e], v[8 * jj + 2 * e + 1], hi[e], lo[e]);
-    const uint32_t off = row * 128u + (((4u * hf + jj) ^ (row & 7u)) << 4);
-    st_shared_v4(a_chunk_addr + off, hi[0], hi[1], hi[2], hi[3]);
-    st_shared_v4(a_chunk_addr + kPlaneBytes + off, lo[0], lo[1], lo[2], lo[3]);
-  }
+  for (int e = 0; e < 4; ++e) split2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+  const uint32_t off = row * 128u + ((unit ^ (row & 7u)) << 4);
+  st_shared_v4(a_chunk_addr + off, hi[0], hi[1], hi[2], hi[3]);
+  st_shared_v4(a_chunk_addr + kPlaneBytes + off, lo[0], lo[1], lo[2], lo[3]);
 }
 
 template <int MODE>
@@ -279,7 +277,14 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
         int signalled = 0;   // operand groups (4 chunks = one layer's dY) of this tile already announced
         for (int i = 0; i < kSavedChunksPerTile; ++i, ++issued) {
           const uint32_t slot = i & 3;   // first chunks cycle the ring; body chunk c lives in slot c
-          mbar_wait(bar(slot == 0 ? kBarA0Sub + 3 : kBarAFull + slot), (a_phase >> slot) & 1u);
+          if (slot == 0) {
+            // k-steps 0/2 and 1/3 of slot 0 are written by different warps: the chunk is complete when the last
+            // k-step of both groups has been published
+            mbar_wait(bar(kBarA0Sub + 2), a_phase & 1u);
+            mbar_wait(bar(kBarA0Sub + 3), a_phase & 1u);
+          } else {
+            mbar_wait(bar(kBarAFull + slot), (a_phase >> slot) & 1u);
+          }
           a_phase ^= 1u << slot;
           bulk_s2g(dst + (int64_t)i * kAChunkBytes, smem_base + kSmemA + slot * kAChunkBytes, kAChunkBytes);
           bulk_commit();
@@ -309,7 +314,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
     // ======================= encoder / epilogue =======================
     const uint32_t ew = warp - 4;
     const uint32_t q = ew & 3u;       // TMEM lane quarter (== warp % 4)
-    const uint32_t hf = ew >> 2;      // column half inside each 64-wide chunk
+    const uint32_t qt = ew >> 2;      // which quarter of a row's columns this thread works on (0..3)
     const uint32_t row = q * 32u + lane;
     const uint32_t tmem_row = tmem_base + ((q * 32u) << 16);
     const float* cumbias = reinterpret_cast<const float*>(p.packed + kPackOffCumBias);
@@ -321,26 +326,26 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
     uint32_t acc_phase = 0;
     uint32_t saved_phase = 0;   // per-slot parity of kBarASaved
     (void)cumbias; (void)headb; (void)b1; (void)tailb; (void)tail_smem;
+    // Epilogue column ownership inside a 64-column chunk: k-steps g0 = qt>>1 and g0+2, and inside each k-step the
+    // 8-column unit u = qt&1, i.e. the 16-byte operand units 2g+u.  K-steps 0/2 belong to the warps with qt in {0,1},
+    // k-steps 1/3 to qt in {2,3}: the first 16 columns of a layer's output are ready after 8 warps did 8 columns each.
+    const uint32_t g0 = qt >> 1, uu = qt & 1u;
 
-    // publish one A chunk: make the generic-proxy writes visible to the tensor core, then signal
-    auto publish = [&](uint32_t slot) {          // a whole 64-column chunk
+    // kBarA0Sub[ks] counts all 16 warps: owners arrive when their part of k-step ks is written, the others at once.
+    auto arrive_sub = [&](uint32_t ks) { if (lane == 0) mbar_arrive(bar(kBarA0Sub + ks)); };
+    auto make_visible = [&]() {   // generic-proxy smem writes -> tensor core (async proxy), TMEM reads ordered
       fence_proxy_async_smem();
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) {
-        if (slot == 0) {
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) mbar_arrive(bar(kBarA0Sub + ks));
-        } else {
-          mbar_arrive(bar(kBarAFull + slot));
-        }
-      }
     };
-    auto publish_kstep = [&](uint32_t ks) {      // 16 columns of slot 0
-      fence_proxy_async_smem();
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(kBarA0Sub + ks));
+    auto publish = [&](uint32_t slot) {          // this warp's part of a whole 64-column chunk is written
+      make_visible();
+      if (slot == 0) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) arrive_sub(ks);
+      } else if (lane == 0) {
+        mbar_arrive(bar(kBarAFull + slot));
+      }
     };
     // before rewriting a slot in save modes: the store warp must have copied the previous content out
     auto wait_saved = [&](uint32_t slot, bool first_use) {
@@ -356,7 +361,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
       const bool valid = grow < p.n_rays;
 
       if constexpr (!kIsBwd) {
-        // ---- head A operand: 16 chunks through the 4-slot A ring ----
+        // ---- head A operand: 16 chunks through the 4-slot A ring; thread (row, qt) writes slots 16 qt .. 16 qt + 15 ----
         float o[3] = {0.f, 0.f, 0.f}, dd[3] = {0.f, 0.f, 0.f};
         if (p.input_kind == kInputRays && valid) {
 #pragma unroll
@@ -367,11 +372,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
         }
         for (int c = 0; c < kSamples; ++c) {
           const uint32_t slot = c & 3;
-          float f[32];
+          float f[16];
           if (p.input_kind == kInputX) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int feat = 64 * c + 32 * (int)hf + i;
+            for (int i = 0; i < 16; ++i) {
+              const int feat = 64 * c + 16 * (int)qt + i;
               f[i] = (valid && feat < kInDim) ? __ldg(p.in0 + grow * kInDim + feat) : 0.f;
             }
           } else {
@@ -388,11 +393,16 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
                 for (int k = 0; k < 3; ++k) x[k] = __fadd_rn(o[k], __fmul_rn(dd[k], z));  // :124
               }
             }
-            if (hf == 0) encode_half<0>(x, f); else encode_half<1>(x, f);
+            if (qt == 0) encode_quarter<0>(x, f);
+            else if (qt == 1) encode_quarter<1>(x, f);
+            else if (qt == 2) encode_quarter<2>(x, f);
+            else encode_quarter<3>(x, f);
           }
           if (c >= 4) mbar_wait(bar(kBarAEmpty + slot), ((c >> 2) - 1) & 1u);
           wait_saved(slot, first_tile && c < 4);
-          store_a_half(smem_base + kSmemA + slot * kAChunkBytes, row, hf, f);
+          const uint32_t chunk_addr = smem_base + kSmemA + slot * kAChunkBytes;
+          store_a_unit(chunk_addr, row, 2 * qt, &f[0]);
+          store_a_unit(chunk_addr, row, 2 * qt + 1, &f[8]);
           publish(slot);
         }
       } else {
@@ -406,11 +416,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
           }
         }
         for (int c = 0; c < kAChunks; ++c) {
-          const uint32_t col = 64u * c + 32u * hf;
-          float v[32];
-          uint32_t r[32];
+          const uint32_t col = 64u * c + 16u * qt;   // 16 consecutive columns per thread here
+          float v[16];
+          uint32_t r[16];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 4; ++i) {
             const float4 w0 = __ldg(reinterpret_cast<const float4*>(tailw + col) + i);
             const float4 w1 = __ldg(reinterpret_cast<const float4*>(tailw + kWidth + col) + i);
             const float4 w2 = __ldg(reinterpret_cast<const float4*>(tailw + 2 * kWidth + col) + i);
@@ -420,14 +430,17 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
             v[4 * i + 3] = fmaf(dl[2], w2.w, fmaf(dl[1], w1.w, dl[0] * w0.w));
           }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(v[i]);
-          tmem_st32(tmem_row + kTmemZ + col, r);
+          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(v[i]);
+          tmem_st8(tmem_row + kTmemZ + col, &r[0]);
+          tmem_st8(tmem_row + kTmemZ + col + 8, &r[8]);
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
+          for (int i = 0; i < 4; ++i)
             reinterpret_cast<float4*>(hrow + col)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           tmem_st_wait();
           wait_saved(c, first_tile);
-          store_a_half(smem_base + kSmemA + c * kAChunkBytes, row, hf, v);
+          const uint32_t chunk_addr = smem_base + kSmemA + c * kAChunkBytes;
+          store_a_unit(chunk_addr, row, 2 * qt, &v[0]);
+          store_a_unit(chunk_addr, row, 2 * qt + 1, &v[8]);
           publish(c);
         }
       }
@@ -452,26 +465,23 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
           const int64_t chunk0 = from_h ? (kSamples + 4 * (2 * k + 1)) : kSamples;
           mask_img = p.fwd_saved + ((int64_t)tile * kFwdSavedChunks + chunk0) * kAChunkBytes;
         }
-        // Column ownership inside a 64-column chunk is interleaved per k-step: thread (row, hf) owns the 8 columns
-        // 16 g + 8 hf .. +8 of every k-step g = 0..3, i.e. exactly one 16-byte unit (2 g + hf) of the swizzled
-        // operand row.  Chunk 0 is published k-step by k-step so that the next GEMM starts after 16 columns.
-        // Its bias / mask sit on the critical path between two GEMMs: fetch them while the MMAs still run.
-        float4 bq[8];
-        uint4 mq[4];
+        // side data of a chunk (bias / ReLU mask of my two 8-column units); chunk 0's is fetched while the MMAs run
+        float4 bq[4];
+        uint4 mq[2];
         auto load_side = [&](int c) {
           if constexpr (!kIsBwd) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const float4* b4 = reinterpret_cast<const float4*>(bias + 64 * c + 16 * g + 8 * hf);
-              bq[2 * g] = __ldg(b4);
-              bq[2 * g + 1] = __ldg(b4 + 1);
+            for (int h = 0; h < 2; ++h) {
+              const float4* b4 = reinterpret_cast<const float4*>(bias + 64 * c + 16 * (g0 + 2 * h) + 8 * uu);
+              bq[2 * h] = __ldg(b4);
+              bq[2 * h + 1] = __ldg(b4 + 1);
             }
           } else {
             if (masked) {
               const uint8_t* plane = mask_img + (int64_t)c * kAChunkBytes;
 #pragma unroll
-              for (int g = 0; g < 4; ++g)
-                mq[g] = __ldg(reinterpret_cast<const uint4*>(plane + row * 128u + (((2u * g + hf) ^ (row & 7u)) << 4)));
+              for (int h = 0; h < 2; ++h)
+                mq[h] = __ldg(reinterpret_cast<const uint4*>(plane + row * 128u + (((2u * (g0 + 2 * h) + uu) ^ (row & 7u)) << 4)));
             }
           }
         };
@@ -484,29 +494,31 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
         const bool feeds_mma = !last;                     // the last epilogue of a tile produces no further GEMM input
         const bool produces_chunk = feeds_mma || kIsBwd;  // backward's last output (d head pre-activation) is saved for dw
         for (int c = 0; c < kAChunks; ++c) {
-          // TMEM reads are issued one k-step ahead: tcgen05.wait::ld waits for everything outstanding, so group g is
-          // consumed while only group g+1 is in flight (the first 16 columns never wait for the whole 64-column read)
-          uint32_t r[32];
-          const uint32_t tacc = tmem_row + (from_h ? kTmemH : kTmemZ) + 64u * c + 8u * hf;
-          tmem_ld8(tacc, &r[0]);
+          uint32_t r[16];
+          const uint32_t tacc = tmem_row + (from_h ? kTmemH : kTmemZ) + 64u * c + 8u * uu;
+          tmem_ld8(tacc + 16u * g0, &r[0]);
+          tmem_ld8(tacc + 16u * (g0 + 2), &r[8]);
           if (c > 0) load_side(c);
-          if (produces_chunk) wait_saved(c, false);
+          if (produces_chunk) {
+            wait_saved(c, false);
+            if (c == 0) { arrive_sub(1 - g0); arrive_sub(3 - g0); }   // the k-steps of chunk 0 I do not write
+          }
+          tmem_ld_wait();
           const uint32_t chunk_addr = smem_base + kSmemA + c * kAChunkBytes;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            tmem_ld_wait();
-            if (g < 3) tmem_ld8(tacc + 16u * (g + 1), &r[8 * (g + 1)]);
-            const uint32_t col = 64u * c + 16u * g + 8u * hf;
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t g = g0 + 2 * h;
+            const uint32_t col = 64u * c + 16u * g + 8u * uu;
             float v[8];
             if constexpr (!kIsBwd) {
-              v[0] = __uint_as_float(r[8 * g + 0]) + bq[2 * g].x;
-              v[1] = __uint_as_float(r[8 * g + 1]) + bq[2 * g].y;
-              v[2] = __uint_as_float(r[8 * g + 2]) + bq[2 * g].z;
-              v[3] = __uint_as_float(r[8 * g + 3]) + bq[2 * g].w;
-              v[4] = __uint_as_float(r[8 * g + 4]) + bq[2 * g + 1].x;
-              v[5] = __uint_as_float(r[8 * g + 5]) + bq[2 * g + 1].y;
-              v[6] = __uint_as_float(r[8 * g + 6]) + bq[2 * g + 1].z;
-              v[7] = __uint_as_float(r[8 * g + 7]) + bq[2 * g + 1].w;
+              v[0] = __uint_as_float(r[8 * h + 0]) + bq[2 * h].x;
+              v[1] = __uint_as_float(r[8 * h + 1]) + bq[2 * h].y;
+              v[2] = __uint_as_float(r[8 * h + 2]) + bq[2 * h].z;
+              v[3] = __uint_as_float(r[8 * h + 3]) + bq[2 * h].w;
+              v[4] = __uint_as_float(r[8 * h + 4]) + bq[2 * h + 1].x;
+              v[5] = __uint_as_float(r[8 * h + 5]) + bq[2 * h + 1].y;
+              v[6] = __uint_as_float(r[8 * h + 6]) + bq[2 * h + 1].z;
+              v[7] = __uint_as_float(r[8 * h + 7]) + bq[2 * h + 1].w;
               if (relu) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -523,16 +535,16 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
               }
             } else {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * g + i]);
+              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * h + i]);
               if (last) {  // + dL/dz_43 through the outer skip
-                const float4 g0 = reinterpret_cast<const float4*>(hrow + col)[0];
-                const float4 g1 = reinterpret_cast<const float4*>(hrow + col)[1];
-                v[0] += g0.x; v[1] += g0.y; v[2] += g0.z; v[3] += g0.w;
-                v[4] += g1.x; v[5] += g1.y; v[6] += g1.z; v[7] += g1.w;
+                const float4 s0 = reinterpret_cast<const float4*>(hrow + col)[0];
+                const float4 s1 = reinterpret_cast<const float4*>(hrow + col)[1];
+                v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w;
+                v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
               }
               if (masked) {
                 // ReLU mask from the hi plane of the saved forward operand (a > 0  <=>  bf16 hi != 0; a >= 0 always)
-                const uint32_t w[4] = {mq[g].x, mq[g].y, mq[g].z, mq[g].w};
+                const uint32_t w[4] = {mq[h].x, mq[h].y, mq[h].z, mq[h].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   if ((w[e] & 0x00007FFFu) == 0u) v[2 * e] = 0.f;
@@ -541,14 +553,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
               }
             }
             if (produces_chunk) {
-              uint32_t hi[4], lo[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) split2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
-              const uint32_t off = row * 128u + (((2u * g + hf) ^ (row & 7u)) << 4);
-              st_shared_v4(chunk_addr + off, hi[0], hi[1], hi[2], hi[3]);
-              st_shared_v4(chunk_addr + kPlaneBytes + off, lo[0], lo[1], lo[2], lo[3]);
+              store_a_unit(chunk_addr, row, 2 * g + uu, v);
               if (c == 0) {
-                publish_kstep(g);
+                make_visible();
+                arrive_sub(g);
                 if (tr && g == 0) p.trace[((int64_t)blockIdx.x * 5 + 3) * 96 + l] = clock64();
               }
             }
@@ -581,22 +589,28 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
         if (tr) p.trace[((int64_t)blockIdx.x * 5 + 4) * 96 + l] = clock64();
       }
       if constexpr (!kIsBwd) {
-        // combine the two column halves of each ray, sigmoid, store
+        // combine the four column-quarter partial sums of each ray through TMEM (the H region is idle here, and the
+        // four threads of a ray share its TMEM lane): fixed summation order, no shared memory needed
+        uint32_t w4[4] = {__float_as_uint(dot0), __float_as_uint(dot1), __float_as_uint(dot2), 0u};
+        tmem_st4(tmem_row + kTmemH + 4u * qt, w4);
+        tmem_st_wait();
         tc_fence_before_sync();
-        if (hf == 1) {
-          tail_smem[row * 3 + 0] = dot0;
-          tail_smem[row * 3 + 1] = dot1;
-          tail_smem[row * 3 + 2] = dot2;
-        }
         named_bar_sync(1, kEpiWarps * 32);
-        if (hf == 0 && valid) {
-          const float s0 = dot0 + tail_smem[row * 3 + 0] + __ldg(tailb + 0);
-          const float s1 = dot1 + tail_smem[row * 3 + 1] + __ldg(tailb + 1);
-          const float s2 = dot2 + tail_smem[row * 3 + 2] + __ldg(tailb + 2);
-          p.rgb[grow * 3 + 0] = 1.f / (1.f + expf(-s0));
-          p.rgb[grow * 3 + 1] = 1.f / (1.f + expf(-s1));
-          p.rgb[grow * 3 + 2] = 1.f / (1.f + expf(-s2));
+        tc_fence_after_sync();
+        if (qt == 0) {
+          uint32_t a[16];
+          tmem_ld16(tmem_row + kTmemH, a);
+          tmem_ld_wait();
+          if (valid) {
+            const float s0 = ((__uint_as_float(a[0]) + __uint_as_float(a[4])) + __uint_as_float(a[8])) + __uint_as_float(a[12]) + __ldg(tailb + 0);
+            const float s1 = ((__uint_as_float(a[1]) + __uint_as_float(a[5])) + __uint_as_float(a[9])) + __uint_as_float(a[13]) + __ldg(tailb + 1);
+            const float s2 = ((__uint_as_float(a[2]) + __uint_as_float(a[6])) + __uint_as_float(a[10])) + __uint_as_float(a[14]) + __ldg(tailb + 2);
+            p.rgb[grow * 3 + 0] = 1.f / (1.f + expf(-s0));
+            p.rgb[grow * 3 + 1] = 1.f / (1.f + expf(-s1));
+            p.rgb[grow * 3 + 2] = 1.f / (1.f + expf(-s2));
+          }
         }
+        tc_fence_before_sync();
       }
     }
   }
@@ -636,11 +650,11 @@ __global__ void __launch_bounds__(128, 1) r2l_umma_selftest_kernel(const float* 
   }
   // A operand: every thread splits its own row
   for (int c = 0; c < kAChunks; ++c) {
-    for (uint32_t hf = 0; hf < 2; ++hf) {
-      float v[32];
+    for (uint32_t unit = 0; unit < 8; ++unit) {
+      float v[8];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = A[row * kWidth + 64 * c + 32 * hf + i];
-      store_a_half(smem_base + c * kAChunkBytes, row, hf, v);
+      for (int i = 0; i < 8; ++i) v[i] = A[row * kWidth + 64 * c + 8 * unit + i];
+      store_a_unit(smem_base + c * kAChunkBytes, row, unit, v);
     }
   }
   fence_proxy_async_smem();

@@ -9,12 +9,15 @@ dev = torch.device("cuda:0")
 packed = ops.pack_weights(init_flat_params(0).to(dev))
 n = 4096
 o = torch.randn(n, 3, device=dev) * 0.5; d = torch.randn(n, 3, device=dev); z = orc.sampler_z_vals(2.0, 6.0).tolist()
-for _ in range(3): ops.forward(packed, rays_o=o, rays_d=d, z_vals=z)
-trace = torch.zeros(148 * 5 * 96, dtype=torch.int64, device=dev)
+mode = sys.argv[1] if len(sys.argv) > 1 else "infer"
+run = (lambda: ops.forward(packed, rays_o=o, rays_d=d, z_vals=z)) if mode == "infer" else (lambda: ops.forward_train(packed, rays_o=o, rays_d=d, z_vals=z))
+for _ in range(3): run()
+trace = torch.zeros(148 * 5 * 96 + 360, dtype=torch.int64, device=dev)
 _lib.lib().r2l_debug_set_trace(ctypes.c_void_p(trace.data_ptr()))
-ops.forward(packed, rays_o=o, rays_d=d, z_vals=z); torch.cuda.synchronize()
+run(); torch.cuda.synchronize()
 _lib.lib().r2l_debug_set_trace(None)
-t = trace.view(148, 5, 96).cpu().numpy().astype(np.int64)[3]   # CTA 3
+print("mode:", mode)
+t = trace[:148 * 5 * 96].view(148, 5, 96).cpu().numpy().astype(np.int64)[3]   # CTA 3
 start, issued, accdone, pub0, epidone = t
 L = 87
 print("layer: MMA-start  issued-at  acc-complete  first-publish  epilogue-done   (cycles relative to layer-1 start)")
