@@ -322,7 +322,7 @@ int r2l_debug_mma_rate(int reps, int grid, long long* out_cycles, void* stream) 
 int r2l_selftest_layer(const float* A, const void* packed, int layer, float* C, void* stream) {
   if (!A || !packed || !C) return fail("r2l_selftest_layer: %s", "null pointer");
   if (layer < 0 || layer >= r2l::kBodyLayers) return fail("r2l_selftest_layer: %s", "layer out of range");
-  const uint8_t* images = static_cast<const uint8_t*>(packed) + (int64_t)(r2l::kImgBody + r2l::kStepsPerLayer * layer) * r2l::kWStepBytes;
+  const uint8_t* images = static_cast<const uint8_t*>(packed) + (int64_t)(r2l::kImgBody + 8 * layer) * r2l::kWImageBytes;
   return check(r2l::launch_umma_selftest(A, images, C, (cudaStream_t)stream), "r2l_selftest_layer");
 }
 

@@ -31,12 +31,12 @@
 
 namespace r2l {
 
-constexpr int kNumWStages = 6;   // 6 x 16 KiB step images
+constexpr int kNumWStages = 3;
 constexpr int kEpiWarps = 16;
 constexpr int kChainThreads = (4 + kEpiWarps) * 32;   // 640
 constexpr uint32_t kSmemA = 0;
 constexpr uint32_t kSmemW = kABytes;                                  // 131072
-constexpr uint32_t kSmemBar = kSmemW + kNumWStages * kWStepBytes;     // 229376
+constexpr uint32_t kSmemBar = kSmemW + kNumWStages * kWImageBytes;    // 229376
 constexpr uint32_t kSmemTail = kSmemBar + 256;                        // 128 x 3 floats
 constexpr uint32_t kSmemUsed = kSmemTail + kTileM * 3 * 4;            // 231168
 constexpr uint32_t kChainSmemBytes = kSmemUsed + 1024;                // + alignment slack
@@ -47,8 +47,8 @@ constexpr uint32_t kTmemH = 256;
 
 // barrier slots (8 bytes each) inside kSmemBar
 enum : uint32_t {
-  kBarWFull = 0,                          // [6] weight step image landed       (TMA tx -> MMA)
-  kBarWEmpty = kBarWFull + kNumWStages,   // [6] weight slot consumed           (MMA commit -> producer)
+  kBarWFull = 0,                          // [3] weight image landed            (TMA tx -> MMA)
+  kBarWEmpty = kBarWFull + kNumWStages,   // [3] weight slot consumed           (MMA commit -> producer)
   kBarAFull = kBarWEmpty + kNumWStages,   // [4] A chunk written                (8 epilogue warps -> MMA, store warp)
   kBarAEmpty = kBarAFull + kAChunks,      // [4] A chunk consumed (head ring)    (MMA commit -> encoder)
   kBarASaved = kBarAEmpty + kAChunks,     // [4] A chunk copied out to HBM       (store warp -> epilogue)
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
   constexpr bool kSave = MODE != kFwdInfer;
   constexpr int kFirstChunks = kIsBwd ? kAChunks : kSamples;   // A chunks built before the first GEMM
   constexpr int kLayers = kIsBwd ? kBodyLayers : kBodyLayers + 1;  // GEMMs per tile
-  constexpr int kImagesPerTile = kIsBwd ? kStepsPerLayer * kBodyLayers : 64 + kStepsPerLayer * kBodyLayers;
+  constexpr int kImagesPerTile = kIsBwd ? 8 * kBodyLayers : 32 + 8 * kBodyLayers;
   // chunks saved per tile: forward 16 (PE) + 86*4 ; backward 4 (g_43) + 86*4
   constexpr int kSavedChunksPerTile = kFirstChunks + 4 * kBodyLayers;
 
@@ -138,8 +138,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
     // ======================= weight producer =======================
     if (lane == 0) {
       const uint8_t* head_images =
-          p.packed + (int64_t)(p.input_kind == kInputX ? kImgHeadNatural : kImgHeadFused) * kWStepBytes;
-      const uint8_t* body_images = p.packed + (int64_t)(kIsBwd ? kImgBodyT : kImgBody) * kWStepBytes;
+          p.packed + (int64_t)(p.input_kind == kInputX ? kImgHeadNatural : kImgHeadFused) * kWImageBytes;
+      const uint8_t* body_images = p.packed + (int64_t)(kIsBwd ? kImgBodyT : kImgBody) * kWImageBytes;
       uint32_t it = 0;
       long long t_wait = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -148,11 +148,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
           const long long t0 = p.stats ? clock64() : 0;
           mbar_wait(bar(kBarWEmpty + ws), ph ^ 1u);
           if (p.stats) t_wait += clock64() - t0;
-          mbar_arrive_expect_tx(bar(kBarWFull + ws), kWStepBytes);
+          mbar_arrive_expect_tx(bar(kBarWFull + ws), kWImageBytes);
           const uint8_t* src;
-          if (kIsBwd) src = body_images + (int64_t)i * kWStepBytes;
-          else src = i < 64 ? head_images + (int64_t)i * kWStepBytes : body_images + (int64_t)(i - 64) * kWStepBytes;
-          bulk_g2s(smem_base + kSmemW + ws * kWStepBytes, src, kWStepBytes, bar(kBarWFull + ws));
+          if (kIsBwd) src = body_images + (int64_t)i * kWImageBytes;
+          else src = i < 32 ? head_images + (int64_t)i * kWImageBytes : body_images + (int64_t)(i - 32) * kWImageBytes;
+          bulk_g2s(smem_base + kSmemW + ws * kWImageBytes, src, kWImageBytes, bar(kBarWFull + ws));
         }
       }
       if (p.stats) p.stats[blockIdx.x * 8 + 3] = t_wait;
@@ -191,24 +191,51 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
               a_phase ^= 1u << bit;
               tc_fence_after_sync();
             };
-            // one 16 KiB step image (hi + lo planes of 16 input features) per k-step: A_hi W_hi + A_lo W_hi + A_hi W_lo,
-            // then the ring slot goes back to the producer.  Slot 0 of the A ring is consumed per published k-step.
-            if (slot != 0) wait_a(kBarAFull + slot, slot);
+            if (slot == 0) {
+              // k-step granular: the hi-image MMAs of a k-step are issued as soon as its 16 columns are published;
+              // the W_hi slot is released after them, the lo-image MMAs follow (same issue order as the other chunks)
+              wait_w(it);
+              const uint32_t b_hi = smem_base + kSmemW + (it % kNumWStages) * kWImageBytes;
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              if (slot == 0) {
+              for (int ks = 0; ks < 4; ++ks) {
                 wait_a(kBarA0Sub + ks, 4 + ks);
                 if (tr && kc == 0 && ks == 0) p.trace[((int64_t)blockIdx.x * 5 + 0) * 96 + l] = clock64();
+                umma_bf16(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b_hi + 32 * ks, 16, 1024), idesc,
+                          (fresh && kc == 0 && ks == 0) ? 0u : 1u);
+                umma_bf16(d, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw128(b_hi + 32 * ks, 16, 1024), idesc, 1u);
               }
-              wait_w(it);
-              const uint32_t b_hi = smem_base + kSmemW + (it % kNumWStages) * kWStepBytes;
-              const uint32_t b_lo = b_hi + kWPlaneBytes;
-              umma_bf16(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw32(b_hi, 256), idesc,
-                        (fresh && kc == 0 && ks == 0) ? 0u : 1u);
-              umma_bf16(d, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw32(b_hi, 256), idesc, 1u);
-              umma_bf16(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw32(b_lo, 256), idesc, 1u);
               umma_commit(bar(kBarWEmpty + it % kNumWStages));
               ++it;
+              wait_w(it);
+              const uint32_t b_lo = smem_base + kSmemW + (it % kNumWStages) * kWImageBytes;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma_bf16(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b_lo + 32 * ks, 16, 1024), idesc, 1u);
+              umma_commit(bar(kBarWEmpty + it % kNumWStages));
+              ++it;
+            } else {
+              wait_a(kBarAFull + slot, slot);
+              {  // W_hi image: A_hi*W_hi + A_lo*W_hi
+                wait_w(it);
+                const uint32_t b = smem_base + kSmemW + (it % kNumWStages) * kWImageBytes;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_bf16(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b + 32 * ks, 16, 1024), idesc, 1u);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_bf16(d, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw128(b + 32 * ks, 16, 1024), idesc, 1u);
+                umma_commit(bar(kBarWEmpty + it % kNumWStages));
+                ++it;
+              }
+              {  // W_lo image: A_hi*W_lo
+                wait_w(it);
+                const uint32_t b = smem_base + kSmemW + (it % kNumWStages) * kWImageBytes;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_bf16(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b + 32 * ks, 16, 1024), idesc, 1u);
+                umma_commit(bar(kBarWEmpty + it % kNumWStages));
+                ++it;
+              }
             }
             if (ring) umma_commit(bar(kBarAEmpty + slot));
           }
@@ -596,7 +623,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
 
 // ----------------------------------------------------------------------------------------------
 // Single-layer self test: C[128,256] = A[128,256] * W^T using exactly the operand images, descriptors
-// and TMEM read-back the chain kernel uses. `images` = the layer's 16 consecutive 16 KiB step images.
+// and TMEM read-back the chain kernel uses. `images` = 8 consecutive 32 KiB images (4 chunks x {hi,lo}).
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 1) r2l_umma_selftest_kernel(const float* __restrict__ A,
                                                                   const uint8_t* __restrict__ images,
@@ -638,18 +665,24 @@ __global__ void __launch_bounds__(128, 1) r2l_umma_selftest_kernel(const float* 
 
   if (threadIdx.x == 0) {
     constexpr uint32_t idesc = umma_idesc_bf16(128, 256, 0, 0);
-    for (int step = 0; step < kStepsPerLayer; ++step) {
-      const int kc = step >> 2, ks = step & 3;
-      mbar_arrive_expect_tx(bar_w, kWStepBytes);
-      bulk_g2s(wbase, images + (int64_t)step * kWStepBytes, kWStepBytes, bar_w);
-      mbar_wait(bar_w, step & 1);
+    for (int kc = 0; kc < kAChunks; ++kc) {
+      mbar_arrive_expect_tx(bar_w, 2 * kWImageBytes);
+      bulk_g2s(wbase, images + (int64_t)(2 * kc) * kWImageBytes, kWImageBytes, bar_w);
+      bulk_g2s(wbase + kWImageBytes, images + (int64_t)(2 * kc + 1) * kWImageBytes, kWImageBytes, bar_w);
+      mbar_wait(bar_w, kc & 1);
       tc_fence_after_sync();
       const uint32_t a_hi = smem_base + kc * kAChunkBytes, a_lo = a_hi + kPlaneBytes;
-      umma_bf16(tmem_base, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw32(wbase, 256), idesc, step == 0 ? 0u : 1u);
-      umma_bf16(tmem_base, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw32(wbase, 256), idesc, 1u);
-      umma_bf16(tmem_base, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw32(wbase + kWPlaneBytes, 256), idesc, 1u);
+      for (int ks = 0; ks < 4; ++ks)
+        umma_bf16(tmem_base, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(wbase + 32 * ks, 16, 1024),
+                  idesc, (kc == 0 && ks == 0) ? 0u : 1u);
+      for (int ks = 0; ks < 4; ++ks)
+        umma_bf16(tmem_base, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw128(wbase + 32 * ks, 16, 1024),
+                  idesc, 1u);
+      for (int ks = 0; ks < 4; ++ks)
+        umma_bf16(tmem_base, umma_desc_sw128(a_hi + 32 * ks, 16, 1024),
+                  umma_desc_sw128(wbase + kWImageBytes + 32 * ks, 16, 1024), idesc, 1u);
       umma_commit(bar_m);
-      mbar_wait(bar_m, step & 1);
+      mbar_wait(bar_m, kc & 1);
     }
   }
   tc_fence_before_sync();
@@ -702,12 +735,14 @@ __global__ void __launch_bounds__(128, 1) r2l_mma_rate_kernel(int reps, long lon
       for (int kc = 0; kc < kAChunks; ++kc) {
         const uint32_t a_hi = smem_base + kc * kAChunkBytes, a_lo = a_hi + kPlaneBytes;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint32_t b_hi = wbase + ks * kWStepBytes, b_lo = b_hi + kWPlaneBytes;
-          umma_bf16(tmem_base, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw32(b_hi, 256), idesc, 1u);
-          umma_bf16(tmem_base, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw32(b_hi, 256), idesc, 1u);
-          umma_bf16(tmem_base, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw32(b_lo, 256), idesc, 1u);
-        }
+        for (int ks = 0; ks < 4; ++ks)
+          umma_bf16(tmem_base, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(wbase + 32 * ks, 16, 1024), idesc, 1u);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_bf16(tmem_base, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw128(wbase + 32 * ks, 16, 1024), idesc, 1u);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_bf16(tmem_base, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(wbase + kWImageBytes + 32 * ks, 16, 1024), idesc, 1u);
       }
     }
     umma_commit(bar_m);

@@ -39,28 +39,21 @@ constexpr int kPlaneBytes = kTileM * 128;        // one bf16 plane (hi or lo) of
 constexpr int kAChunkBytes = 2 * kPlaneBytes;    // hi + lo
 constexpr int kAChunks = 4;                      // 256 / 64
 constexpr int kABytes = kAChunks * kAChunkBytes; // 131072: whole [128 x 256] A operand, hi+lo
-constexpr int kWImageBytes = kWidth * 128;       // 32768: [256 n x 64 k] bf16, one plane (teacher kernel's weight images)
+constexpr int kWImageBytes = kWidth * 128;       // 32768: [256 n x 64 k] bf16, one plane
 
-// ---- packed weight stream ----
-// One "step image" per UMMA k-step (16 input features): [256 n x 16 k] bf16 hi plane (8 KiB) followed by the lo plane
-// (8 KiB), each in the UMMA K-major SWIZZLE_32B shared-memory byte order (32-byte rows, 8-row atoms of 256 B).
-// A 16 KiB image is consumed by three tcgen05.mma (A_hi W_hi, A_lo W_hi, A_hi W_lo) and its ring slot is free again
-// after 384 tensor-core cycles, so six slots cover the bulk-copy latency that three 32 KiB slots could not.
-// Image order = consumption order of the chain kernels (4 step images per 64-feature K chunk):
-//   head (fused-PE feature order) : 16 chunks x 4 steps            images [0, 64)
-//   head (natural feature order)  : 16 chunks x 4 steps            images [64, 128)
-//   body layer l = 0..85          : 4 chunks x 4 steps             images [128 + 16 l, 128 + 16 l + 16)
+// ---- packed weight stream (bf16 planes, UMMA K-major SWIZZLE_128B images of 32 KiB) ----
+// image order = consumption order of the forward chain kernel:
+//   head (fused-PE feature order) : 16 chunks x {hi, lo}            images [0, 32)
+//   head (natural feature order)  : 16 chunks x {hi, lo}            images [32, 64)
+//   body layer l = 0..85          : 4 chunks x {hi, lo}             images [64 + 8 l, 64 + 8 l + 8)
 // then the transposed body weights in the order the backward chain consumes them:
-//   for k = 42..0: W2_k^T (16 steps), W1_k^T (16 steps)            images [1504, 1504 + 1376)
-constexpr int kWPlaneBytes = kWidth * 32;          // 8192: [256 n x 16 k] bf16
-constexpr int kWStepBytes = 2 * kWPlaneBytes;      // 16384: hi + lo
-constexpr int kStepsPerLayer = 16;
+//   for k = 42..0: W2_k^T (4 x {hi,lo}), W1_k^T (4 x {hi,lo})       images [752, 752 + 688)
 constexpr int kImgHeadFused = 0;
-constexpr int kImgHeadNatural = 64;
-constexpr int kImgBody = 128;
-constexpr int kImgBodyT = kImgBody + kStepsPerLayer * kBodyLayers;   // 1504
-constexpr int kNumImages = kImgBodyT + kStepsPerLayer * kBodyLayers; // 2880
-constexpr int64_t kPackedImagesBytes = (int64_t)kNumImages * kWStepBytes;  // 47,185,920
+constexpr int kImgHeadNatural = 32;
+constexpr int kImgBody = 64;
+constexpr int kImgBodyT = kImgBody + 8 * kBodyLayers;   // 752
+constexpr int kNumImages = kImgBodyT + 8 * kBodyLayers; // 1440
+constexpr int64_t kPackedImagesBytes = (int64_t)kNumImages * kWImageBytes;  // 47,185,920
 // fp32 side tables appended after the images
 //   cumbias[44][256] : cumbias[k] = sum_{j<k} b2_j  (the residual stream lives un-biased in TMEM)
 //   headb[256], b1[43][256], tailw[3][256], tailb[4]
@@ -83,11 +76,6 @@ __host__ __device__ inline int fused_slot_to_feature(int s, int slot) {
   }
   if (slot < 63) return (3 * s + (slot - 60)) * kEmbed + 2 * kFreqs;
   return -1;
-}
-
-// byte offset of element (row, k), k < 16, inside one [rows x 16] bf16 K-major SWIZZLE_32B plane
-__host__ __device__ inline uint32_t sw32_offset(uint32_t row, uint32_t k) {
-  return (row >> 3) * 256u + (row & 7u) * 32u + ((((k >> 3) ^ ((row >> 2) & 1u)) << 4) | ((k & 7u) << 1));
 }
 
 // byte offset of element (row, k) inside one [rows x 64] bf16 K-major SWIZZLE_128B plane

@@ -5,45 +5,44 @@
 
 namespace r2l {
 
-// One thread = one 16-byte unit (8 consecutive k) of one n-row of one step image (both planes).
+// One thread = one 16-byte swizzle unit (8 consecutive k) of one (n-row) of one image PAIR (hi+lo).
 __global__ void __launch_bounds__(256) pack_images_kernel(const float* __restrict__ params,
                                                           uint8_t* __restrict__ packed) {
-  const int img = blockIdx.y;                               // step image
-  const int unit = blockIdx.x * blockDim.x + threadIdx.x;   // 0 .. 511
-  const int n = unit >> 1, u = unit & 1;
+  const int ip = blockIdx.y;                                 // image pair
+  const int unit = blockIdx.x * blockDim.x + threadIdx.x;    // 0 .. 2047
+  const int n = unit >> 3, j = unit & 7;
   float v[8];
-  if (img < kImgBody) {
-    const bool fused = img < kImgHeadNatural;
-    const int step = fused ? img : img - kImgHeadNatural;   // 0..63
-    const int chunk = step >> 2, ks = step & 3;
+  if (ip < 32) {
+    const bool fused = ip < 16;
+    const int chunk = fused ? ip : ip - 16;
     const float* w = params + kOffHeadW + (int64_t)n * kInDim;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int t = 16 * ks + 8 * u + e;                    // slot inside the 64-wide chunk
+      const int t = 8 * j + e;
       const int f = fused ? fused_slot_to_feature(chunk, t) : (64 * chunk + t < kInDim ? 64 * chunk + t : -1);
       v[e] = f >= 0 ? __ldg(w + f) : 0.f;
     }
-  } else if (img < kImgBodyT) {
-    const int l = (img - kImgBody) / kStepsPerLayer, step = (img - kImgBody) % kStepsPerLayer;
-    const float* w = params + off_body_w(l) + (int64_t)n * kWidth + 16 * step + 8 * u;
+  } else if (ip < 32 + 4 * kBodyLayers) {
+    const int l = (ip - 32) >> 2, c = (ip - 32) & 3;
+    const float* w = params + off_body_w(l) + (int64_t)n * kWidth + 64 * c + 8 * j;
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = __ldg(w + e);
   } else {
-    const int idx = img - kImgBodyT;
-    const int q = idx / kStepsPerLayer, step = idx % kStepsPerLayer;
+    const int idx = ip - 32 - 4 * kBodyLayers;
+    const int q = idx >> 2, c = idx & 3;
     const int blk = (kBlocks - 1) - (q >> 1);
     const int l = 2 * blk + ((q & 1) ? 0 : 1);   // W2 of the block first, then W1
     const float* w = params + off_body_w(l) + n;  // B[n][kk] = W[kk][n]
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = __ldg(w + (int64_t)(16 * step + 8 * u + e) * kWidth);
+    for (int e = 0; e < 8; ++e) v[e] = __ldg(w + (int64_t)(64 * c + 8 * j + e) * kWidth);
   }
   uint32_t hi[4], lo[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) split2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
-  const uint32_t off = sw32_offset(n, 8 * u);
-  uint8_t* dst = packed + (int64_t)img * kWStepBytes;
-  *reinterpret_cast<uint4*>(dst + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  *reinterpret_cast<uint4*>(dst + kWPlaneBytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  const uint32_t off = sw128_offset(n, 8 * j);
+  uint8_t* img = packed + (int64_t)(2 * ip) * kWImageBytes;
+  *reinterpret_cast<uint4*>(img + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(img + kWImageBytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 __global__ void __launch_bounds__(256) pack_tables_kernel(const float* __restrict__ params,
@@ -67,7 +66,7 @@ __global__ void __launch_bounds__(256) pack_tables_kernel(const float* __restric
 }
 
 cudaError_t launch_pack(const float* params, void* packed, cudaStream_t stream) {
-  dim3 grid(512 / 256, kNumImages);
+  dim3 grid(2048 / 256, kNumImages / 2);
   pack_images_kernel<<<grid, 256, 0, stream>>>(params, static_cast<uint8_t*>(packed));
   pack_tables_kernel<<<1, 256, 0, stream>>>(params, static_cast<uint8_t*>(packed));
   return cudaGetLastError();

@@ -150,13 +150,6 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 
-// K-major SWIZZLE_32B operand: 32-byte rows (16 bf16 of K), 8-row atoms of 256 B; SBO = distance between atoms.
-__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr, uint32_t sbo_bytes) {
-  const uint32_t lo = ((smem_addr >> 4) & 0x3FFFu) | (1u << 16);
-  const uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (6u << 29);   // layout type 6 = SWIZZLE_32B
-  return (static_cast<uint64_t>(hi) << 32) | lo;
-}
-
 // Instruction descriptor (32 bit) for kind::f16, BF16 x BF16 -> FP32.
 //   [4,6) D fmt (1 = f32)  [7,10) A fmt (1 = bf16)  [10,13) B fmt (1 = bf16)
 //   [15] A major (0 = K, 1 = MN)  [16] B major  [17,23) N >> 3  [24,29) M >> 4

@@ -20,21 +20,19 @@ print("pack ok", packed.numel(), flush=True)
 
 # ---- pack check: decode image of body layer 3 chunk 1 and compare hi+lo with W ----
 P = packed.cpu().numpy()
-def decode_plane(b):  # [256 n][16 k] bf16 plane in K-major SWIZZLE_32B order
-    raw = np.frombuffer(b, dtype=np.uint16).reshape(32, 8, 2, 8)  # atom, row in atom, 16B unit position, elem
-    out = np.zeros((256, 16), np.float32)
+def decode_image(img_bytes):  # [256 n][64 k] from swizzled bf16 plane
+    raw = np.frombuffer(img_bytes, dtype=np.uint16).reshape(256, 8, 8)  # row, 16B-unit position, elem
+    out = np.zeros((256, 64), np.float32)
     for n in range(256):
-        r = n % 8
-        for pos in range(2):
-            u = pos ^ ((r >> 2) & 1)
-            out[n, 8 * u:8 * u + 8] = (raw[n // 8, r, pos].astype(np.uint32) << 16).view(np.float32)
+        for pos in range(8):
+            j = pos ^ (n & 7)
+            out[n, 8 * j:8 * j + 8] = (raw[n, pos].astype(np.uint32) << 16).view(np.float32)
     return out
-l, c, ks = 3, 1, 2
-base = (128 + 16 * l + 4 * c + ks) * 16384
-hi = decode_plane(P[base:base + 8192].tobytes()); lo = decode_plane(P[base + 8192:base + 16384].tobytes())
+l, c = 3, 1
+base = (64 + 8 * l + 2 * c) * 32768
+hi = decode_image(P[base:base + 32768].tobytes()); lo = decode_image(P[base + 32768:base + 65536].tobytes())
 W = orc.unflatten_params(flat_np)["body"][l][0]
-ref = W[:, 64 * c + 16 * ks:64 * c + 16 * ks + 16]
-print("pack image err", np.abs(hi + lo - ref).max(), "hi-only err", np.abs(hi - ref).max(), flush=True)
+print("pack image err", np.abs(hi + lo - W[:, 64 * c:64 * c + 64]).max(), "hi-only err", np.abs(hi - W[:, 64 * c:64 * c + 64]).max(), flush=True)
 
 # ---- single-layer UMMA self test ----
 torch.manual_seed(5)
