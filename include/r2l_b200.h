@@ -106,6 +106,10 @@ int r2l_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
  * [4] MMA-thread total. */
 int r2l_debug_set_stats(long long* stats);
 
+/* 1: run the forward / backward chain kernels as CTA pairs (tcgen05 cta_group::2, two 128-ray tiles per SM pair, weights
+ * split across the pair); 0: one CTA per tile.  Process-wide; buffers sized by the *_bytes queries fit both. */
+int r2l_set_pair_mode(int on);
+
 /* Debug: device buffer [grid][5][96] of clock64 stamps for the first tile of each CTA of the next chain launches:
  * row 0 MMA thread starts layer l, 1 MMA thread has issued layer l, 2 epilogue sees accumulator l complete,
  * 3 epilogue published the first k-step of layer l's output, 4 epilogue finished layer l; followed by [90][4]

@@ -11,6 +11,7 @@ namespace {
 thread_local char g_err[512] = "";
 long long* g_stats = nullptr;  // debug cycle counters, see r2l_debug_set_stats
 long long* g_trace = nullptr;  // debug time stamps, see r2l_debug_set_trace
+int g_pair = 0;                // 1: run the chain kernels as CTA pairs (cta_group::2), see r2l_set_pair_mode
 
 int fail(const char* fmt, const char* detail) {
   snprintf(g_err, sizeof(g_err), fmt, detail);
@@ -54,7 +55,15 @@ int num_tiles(int64_t n_rays) { return (int)((n_rays + r2l::kTileM - 1) / r2l::k
 int fwd_grid(int64_t n_rays) {
   const int sms = sm_count();
   const int t = num_tiles(n_rays);
+  if (g_pair) {   // CTA pairs: an even grid, one pair per two tiles
+    const int pairs = (t + 1) / 2, max_pairs = sms / 2;
+    return 2 * (pairs < max_pairs ? pairs : max_pairs);
+  }
   return t < sms ? t : sms;
+}
+int even_tiles(int64_t n_rays) { return (num_tiles(n_rays) + 1) & ~1; }   // pair mode may run one dummy tile
+cudaError_t launch_chain_any(int mode, const r2l::ChainParams& p, int grid, cudaStream_t stream) {
+  return g_pair ? r2l::launch_chain_pair(mode, p, grid, stream) : r2l::launch_chain(mode, p, grid, stream);
 }
 }  // namespace
 
@@ -69,7 +78,7 @@ size_t r2l_fwd_workspace_bytes(int64_t n_rays) {
   // head-output scratch: one [128,256] fp32 tile per resident CTA (sized for the largest grid we launch)
   int sms = sm_count();
   if (sms <= 0) sms = 148;
-  const int t = num_tiles(n_rays);
+  const int t = even_tiles(n_rays);
   const int g = t < sms ? t : sms;
   return (size_t)(g > 0 ? g : 1) * r2l::kTileM * r2l::kWidth * sizeof(float) + kReadyBytes;
 }
@@ -117,16 +126,16 @@ int r2l_forward(int input_kind, const float* in0, const float* in1, const float*
   p.num_tiles = num_tiles(n_rays);
   p.stats = g_stats;
   p.trace = g_trace;
-  return check(r2l::launch_chain(r2l::kFwdInfer, p, fwd_grid(n_rays), (cudaStream_t)stream), "r2l_forward");
+  return check(launch_chain_any(r2l::kFwdInfer, p, fwd_grid(n_rays), (cudaStream_t)stream), "r2l_forward");
 }
 
 size_t r2l_bwd_workspace_bytes(int64_t n_rays) { return r2l_fwd_workspace_bytes(n_rays) + kDwPartialBytes; }
 
 size_t r2l_train_fwd_saved_bytes(int64_t n_rays) {
-  return (size_t)num_tiles(n_rays) * r2l::kFwdSavedChunks * r2l::kAChunkBytes;
+  return (size_t)even_tiles(n_rays) * r2l::kFwdSavedChunks * r2l::kAChunkBytes;
 }
 size_t r2l_train_bwd_saved_bytes(int64_t n_rays) {
-  return (size_t)num_tiles(n_rays) * r2l::kBwdSavedChunks * r2l::kAChunkBytes;
+  return (size_t)even_tiles(n_rays) * r2l::kBwdSavedChunks * r2l::kAChunkBytes;
 }
 
 int r2l_forward_train(int input_kind, const float* in0, const float* in1, const float* t_rand, const float* z_lo,
@@ -150,7 +159,7 @@ int r2l_forward_train(int input_kind, const float* in0, const float* in1, const 
   p.num_tiles = num_tiles(n_rays);
   p.stats = g_stats;
   p.trace = g_trace;
-  return check(r2l::launch_chain(r2l::kFwdTrain, p, fwd_grid(n_rays), (cudaStream_t)stream), "r2l_forward_train");
+  return check(launch_chain_any(r2l::kFwdTrain, p, fwd_grid(n_rays), (cudaStream_t)stream), "r2l_forward_train");
 }
 
 int r2l_backward(int input_kind, const void* packed, const float* rgb, const float* grad_rgb, const float* zf,
@@ -204,12 +213,12 @@ int r2l_backward(int input_kind, const void* packed, const float* rgb, const flo
     d.tickets = ready + 128;
     if (int rc = check(cudaEventRecord(side->fork, st), "r2l_backward(fork)")) return rc;
     if (int rc = check(cudaStreamWaitEvent(side->stream, side->fork, 0), "r2l_backward(fork wait)")) return rc;
-    if (int rc = check(r2l::launch_chain(r2l::kBwd, p, grid, st), "r2l_backward(chain)")) return rc;
+    if (int rc = check(launch_chain_any(r2l::kBwd, p, grid, st), "r2l_backward(chain)")) return rc;
     if (int rc = check(r2l::launch_dw(d, side->stream), "r2l_backward(dw)")) return rc;
     if (int rc = check(cudaEventRecord(side->join, side->stream), "r2l_backward(join)")) return rc;
     if (int rc = check(cudaStreamWaitEvent(st, side->join, 0), "r2l_backward(join wait)")) return rc;
   } else {
-    if (int rc = check(r2l::launch_chain(r2l::kBwd, p, grid, st), "r2l_backward(chain)")) return rc;
+    if (int rc = check(launch_chain_any(r2l::kBwd, p, grid, st), "r2l_backward(chain)")) return rc;
     if (int rc = check(r2l::launch_dw(d, st), "r2l_backward(dw)")) return rc;
   }
   r2l::TailGradParams t;
@@ -306,6 +315,11 @@ int r2l_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
 
 int r2l_debug_set_stats(long long* stats) {
   g_stats = stats;
+  return 0;
+}
+
+int r2l_set_pair_mode(int on) {
+  g_pair = on ? 1 : 0;
   return 0;
 }
 

@@ -75,6 +75,7 @@ cudaError_t launch_teacher_pack(const float* params, void* packed, cudaStream_t 
 cudaError_t launch_teacher(const TeacherParams& p, int grid, cudaStream_t stream);
 cudaError_t launch_pack(const float* params, void* packed, cudaStream_t stream);
 cudaError_t launch_chain(int mode, const ChainParams& p, int grid, cudaStream_t stream);
+cudaError_t launch_chain_pair(int mode, const ChainParams& p, int grid, cudaStream_t stream);   // grid even: CTA pairs
 cudaError_t launch_dw(const DwParams& p, cudaStream_t stream);
 cudaError_t launch_tail_grads(const TailGradParams& p, bool zero_first, cudaStream_t stream);
 cudaError_t launch_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, int64_t n_rays, int n_samples,
