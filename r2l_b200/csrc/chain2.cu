@@ -3,13 +3,13 @@
 // Two CTAs of a cluster (one SM pair) walk two neighbouring 128-ray tiles through the network together and issue every
 // GEMM as ONE tcgen05.mma.cta_group::2 (M = 256: 128 rays per CTA, N = 256): each CTA stages only ITS half of every
 // weight image (128 of the 256 output features), so
-//   * the same 96 KiB of shared memory hold a 6-stage weight ring instead of 3 stages (the ~1.0 k cycles per layer the
-//     single-CTA kernel waits for weight stages disappear), and
+//   * the same 96 KiB of shared memory hold a 6-stage weight ring instead of 3 stages, and
 //   * L2 -> SM weight traffic per SM halves (42 -> 21 B/cycle at full tensor rate).
-// Differences to chain.cu: the leader CTA (cluster rank 0) issues the MMAs for both; the peer's warp 1 relays "my
-// weight half landed" to the leader; every epilogue warp of both CTAs arrives on the LEADER's operand barriers (remote
-// mbarrier arrive) and, in the training modes, on a local barrier for its CTA's store warp; tcgen05.commit multicasts
-// to both CTAs.
+// Differences to chain.cu: the leader CTA (cluster rank 0) issues the MMAs for both and waits, for every operand event,
+// on its own local barrier AND on a "peer" barrier; in the peer CTA two forwarding threads (warp 1: weight halves,
+// warp 2: A-operand chunks) watch the local barriers and re-signal them to the leader with one remote mbarrier arrive
+// each, so the 16 epilogue warps of both CTAs only ever touch cheap CTA-local barriers.  tcgen05.commit multicasts to
+// the barriers of both CTAs.
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -24,7 +24,7 @@ constexpr uint32_t kSmemA = 0;
 constexpr uint32_t kSmemW = kABytes;                                  // 131072
 constexpr uint32_t kSmemBar = kSmemW + kNumWStages * kWHalfBytes;     // 229376
 constexpr uint32_t kSmemTail = kSmemBar + 384;                        // 128 x 3 floats
-constexpr uint32_t kSmemUsed = kSmemTail + kTileM * 3 * 4;            // 231296
+constexpr uint32_t kSmemUsed = kSmemTail + kTileM * 3 * 4;            // 231168
 constexpr uint32_t kChainSmemBytes = kSmemUsed + 1024;                // + alignment slack
 static_assert(kChainSmemBytes <= 232448, "exceeds the 227 KiB dynamic shared memory limit");
 
@@ -39,11 +39,12 @@ enum : uint32_t {
   kBarAEmpty = kBarAFull + kAChunks,      // [4] A chunk consumed (head ring)    (MMA commit -> encoder)
   kBarASaved = kBarAEmpty + kAChunks,     // [4] A chunk copied out to HBM       (store warp -> epilogue)
   kBarAccFull = kBarASaved + kAChunks,    //     accumulator of a layer complete (MMA commit -> epilogue)
-  kBarWPeer = kBarAccFull + 1,            // [6] leader only: the peer CTA's half of the weight image landed (relay)
-  kBarALocal = kBarWPeer + kNumWStages,   // [4] A chunk of THIS CTA complete (16 local warps -> local store warp)
-  kBarA0Sub = kBarALocal + kAChunks,            // [4] slot 0 is published per 16-column k-step (kBarAFull[0] is unused):
+  kBarA0Sub = kBarAccFull + 1,            // [4] slot 0 is published per 16-column k-step (kBarAFull[0] is unused):
                                           //     the first GEMM instructions of a layer start after 1/16 of the epilogue
-  kBarCount = kBarA0Sub + 4
+  kBarWPeer = kBarA0Sub + 4,              // [6] leader: the peer CTA's half of weight stage s landed        (peer warp 1)
+  kBarAPeer = kBarWPeer + kNumWStages,    // [8] leader: the peer CTA published k-step ks of slot 0 (index ks) or the whole
+                                          //     chunk in slot s (index 4 + s)                                  (peer warp 2)
+  kBarCount = kBarAPeer + 8
 };
 static_assert(8 * kBarCount + 8 <= 384, "barrier block overflow");
 
@@ -109,14 +110,14 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_pair_kernel(const 
       mbar_init(bar(kBarWEmpty + i), 1);
     }
     for (int i = 0; i < kAChunks; ++i) {
-      mbar_init(bar(kBarAFull + i), 2 * kEpiWarps);   // both CTAs' epilogue warps (used in the leader)
+      mbar_init(bar(kBarAFull + i), kEpiWarps);
       mbar_init(bar(kBarAEmpty + i), 1);
       mbar_init(bar(kBarASaved + i), 1);
-      mbar_init(bar(kBarA0Sub + i), 2 * kEpiWarps);
-      mbar_init(bar(kBarALocal + i), kEpiWarps);
+      mbar_init(bar(kBarA0Sub + i), kEpiWarps);
     }
-    for (int i = 0; i < kNumWStages; ++i) mbar_init(bar(kBarWPeer + i), 1);
     mbar_init(bar(kBarAccFull), 1);
+    for (int i = 0; i < kNumWStages; ++i) mbar_init(bar(kBarWPeer + i), 1);
+    for (int i = 0; i < 8; ++i) mbar_init(bar(kBarAPeer + i), 1);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -128,6 +129,34 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_pair_kernel(const 
   cluster_sync_all();       // the peer's barriers are initialised before anything arrives on them remotely
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 2 && rank == 1 && lane == 0) {
+    // ======================= peer: forward "A operand event" to the leader =======================
+    // Mirrors the order in which the leader's MMA thread consumes the operand barriers.
+    uint32_t a_phase = 0;
+    auto forward = [&](uint32_t local_bar, uint32_t bit, uint32_t peer_index) {
+      mbar_wait(bar(local_bar), (a_phase >> bit) & 1u);
+      a_phase ^= 1u << bit;
+      mbar_arrive_cluster(mapa_cluster(bar(kBarAPeer + peer_index), 0));
+    };
+    for (int pt = pair_id; pt < num_ptiles; pt += num_pairs) {
+      for (int l = 0; l < kLayers; ++l) {
+        const int nkc = (!kIsBwd && l == 0) ? kSamples : kAChunks;
+        for (int kc = 0; kc < nkc; ++kc) {
+          const uint32_t slot = kc & 3;
+          if (slot == 0) {
+            for (uint32_t ks = 0; ks < 4; ++ks) forward(kBarA0Sub + ks, 4 + ks, ks);
+          } else {
+            forward(kBarAFull + slot, slot, 4 + slot);
+          }
+        }
+      }
+      if constexpr (kIsBwd) {   // the extra chunks of the last backward epilogue (see the MMA issuer)
+        for (uint32_t ks = 0; ks < 4; ++ks) forward(kBarA0Sub + ks, 4 + ks, ks);
+        for (uint32_t slot = 1; slot < kAChunks; ++slot) forward(kBarAFull + slot, slot, 4 + slot);
+      }
+    }
+  }
 
   if (warp == 0) {
     // ======================= weight producer =======================
@@ -154,7 +183,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_pair_kernel(const 
       if (p.stats) p.stats[blockIdx.x * 8 + 3] = t_wait;
     }
   } else if (warp == 1 && rank == 1) {
-    // ======================= peer: relay "my weight half landed" to the leader =======================
+    // ======================= peer: forward "my weight half landed" to the leader =======================
     if (lane == 0) {
       const int per_tile = kIsBwd ? 8 * kBodyLayers : 32 + 8 * kBodyLayers;
       uint32_t it = 0;
@@ -197,7 +226,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_pair_kernel(const 
             };
             auto wait_a = [&](uint32_t barrier, uint32_t bit) {
               const long long t0 = p.stats ? clock64() : 0;
-              mbar_wait_cluster(bar(barrier), (a_phase >> bit) & 1u);
+              mbar_wait(bar(barrier), (a_phase >> bit) & 1u);                                     // my CTA's epilogue
+              mbar_wait_cluster(bar(kBarAPeer + (bit >= 4 ? bit - 4 : 4 + bit)), (a_phase >> bit) & 1u);   // the peer's
               if (p.stats) { if (l == 0) t_a_head += clock64() - t0; else t_a_body += clock64() - t0; }
               a_phase ^= 1u << bit;
               tc_fence_after_sync();
@@ -257,11 +287,13 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_pair_kernel(const 
           // the last backward epilogue publishes 4 more chunks (d head pre-activation, consumed only by the
           // store warp): step over those phases so the parity bookkeeping stays aligned for the next tile
           for (uint32_t ks = 0; ks < 4; ++ks) {
-            mbar_wait_cluster(bar(kBarA0Sub + ks), (a_phase >> (4 + ks)) & 1u);
+            mbar_wait(bar(kBarA0Sub + ks), (a_phase >> (4 + ks)) & 1u);
+            mbar_wait_cluster(bar(kBarAPeer + ks), (a_phase >> (4 + ks)) & 1u);
             a_phase ^= 1u << (4 + ks);
           }
           for (uint32_t slot = 1; slot < kAChunks; ++slot) {
-            mbar_wait_cluster(bar(kBarAFull + slot), (a_phase >> slot) & 1u);
+            mbar_wait(bar(kBarAFull + slot), (a_phase >> slot) & 1u);
+            mbar_wait_cluster(bar(kBarAPeer + 4 + slot), (a_phase >> slot) & 1u);
             a_phase ^= 1u << slot;
           }
         }
@@ -289,7 +321,14 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_pair_kernel(const 
         int signalled = 0;   // operand groups (4 chunks = one layer's dY) of this tile already announced
         for (int i = 0; i < kSavedChunksPerTile; ++i, ++issued) {
           const uint32_t slot = i & 3;   // first chunks cycle the ring; body chunk c lives in slot c
-          mbar_wait(bar(kBarALocal + slot), (a_phase >> slot) & 1u);   // all 16 local warps finished this chunk
+          if (slot == 0) {
+            // k-steps 0/2 and 1/3 of slot 0 are written by different warps: the chunk is complete when the last
+            // k-step of both groups has been published
+            mbar_wait(bar(kBarA0Sub + 2), a_phase & 1u);
+            mbar_wait(bar(kBarA0Sub + 3), a_phase & 1u);
+          } else {
+            mbar_wait(bar(kBarAFull + slot), (a_phase >> slot) & 1u);
+          }
           a_phase ^= 1u << slot;
           bulk_s2g(dst + (int64_t)i * kAChunkBytes, smem_base + kSmemA + slot * kAChunkBytes, kAChunkBytes);
           bulk_commit();
@@ -337,8 +376,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_pair_kernel(const 
     const uint32_t g0 = qt >> 1, uu = qt & 1u;
 
     // kBarA0Sub[ks] counts all 16 warps: owners arrive when their part of k-step ks is written, the others at once.
-    auto arrive_sub = [&](uint32_t ks) { if (lane == 0) mbar_arrive_cluster(mapa_cluster(bar(kBarA0Sub + ks), 0)); };
-    auto arrive_local = [&](uint32_t slot) { if (kSave && lane == 0) mbar_arrive(bar(kBarALocal + slot)); };
+    auto arrive_sub = [&](uint32_t ks) { if (lane == 0) mbar_arrive(bar(kBarA0Sub + ks)); };
     auto make_visible = [&]() {   // generic-proxy smem writes -> tensor core (async proxy), TMEM reads ordered
       fence_proxy_async_smem();
       tc_fence_before_sync();
@@ -350,9 +388,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_pair_kernel(const 
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) arrive_sub(ks);
       } else if (lane == 0) {
-        mbar_arrive_cluster(mapa_cluster(bar(kBarAFull + slot), 0));
+        mbar_arrive(bar(kBarAFull + slot));
       }
-      arrive_local(slot);
     };
     // before rewriting a slot in save modes: the store warp must have copied the previous content out
     auto wait_saved = [&](uint32_t slot, bool first_use) {
@@ -593,7 +630,6 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_pair_kernel(const 
             }
           }
           if (produces_chunk && c > 0) publish(c);
-          if (produces_chunk && c == 0) arrive_local(0);   // (make_visible ran with the last k-step publish)
         }
         if (tr) p.trace[((int64_t)blockIdx.x * 5 + 4) * 96 + l] = clock64();
       }

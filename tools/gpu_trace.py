@@ -10,6 +10,9 @@ packed = ops.pack_weights(init_flat_params(0).to(dev))
 n = 4096
 o = torch.randn(n, 3, device=dev) * 0.5; d = torch.randn(n, 3, device=dev); z = orc.sampler_z_vals(2.0, 6.0).tolist()
 mode = sys.argv[1] if len(sys.argv) > 1 else "infer"
+pair = len(sys.argv) > 2 and sys.argv[2] == "pair"
+_lib.lib().r2l_set_pair_mode(1 if pair else 0)
+cta = 2 if pair else 3
 run = (lambda: ops.forward(packed, rays_o=o, rays_d=d, z_vals=z)) if mode == "infer" else (lambda: ops.forward_train(packed, rays_o=o, rays_d=d, z_vals=z))
 for _ in range(3): run()
 trace = torch.zeros(148 * 5 * 96 + 360, dtype=torch.int64, device=dev)
@@ -17,7 +20,7 @@ _lib.lib().r2l_debug_set_trace(ctypes.c_void_p(trace.data_ptr()))
 run(); torch.cuda.synchronize()
 _lib.lib().r2l_debug_set_trace(None)
 print("mode:", mode)
-t = trace[:148 * 5 * 96].view(148, 5, 96).cpu().numpy().astype(np.int64)[3]   # CTA 3
+t = trace[:148 * 5 * 96].view(148, 5, 96).cpu().numpy().astype(np.int64)[cta]
 start, issued, accdone, pub0, epidone = t
 L = 87
 print("layer: MMA-start  issued-at  acc-complete  first-publish  epilogue-done   (cycles relative to layer-1 start)")
