@@ -5,11 +5,10 @@
 // weight image (128 of the 256 output features), so
 //   * the same 96 KiB of shared memory hold a 6-stage weight ring instead of 3 stages, and
 //   * L2 -> SM weight traffic per SM halves (42 -> 21 B/cycle at full tensor rate).
-// Differences to chain.cu: the leader CTA (cluster rank 0) issues the MMAs for both and waits, for every operand event,
-// on its own local barrier AND on a "peer" barrier; in the peer CTA two forwarding threads (warp 1: weight halves,
-// warp 2: A-operand chunks) watch the local barriers and re-signal them to the leader with one remote mbarrier arrive
-// each, so the 16 epilogue warps of both CTAs only ever touch cheap CTA-local barriers.  tcgen05.commit multicasts to
-// the barriers of both CTAs.
+// Differences to chain.cu: the leader CTA (cluster rank 0) issues the MMAs for both; its operand barriers count the
+// epilogue warps of BOTH CTAs (the peer's warps arrive remotely, signal-only: their smem writes were already published to
+// the async proxy by fence.proxy.async); the peer's warp 1 forwards "my weight half landed"; each CTA keeps local
+// copies of the operand barriers for its own store warp in the training modes; tcgen05.commit multicasts to both CTAs.
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -42,9 +41,10 @@ enum : uint32_t {
   kBarA0Sub = kBarAccFull + 1,            // [4] slot 0 is published per 16-column k-step (kBarAFull[0] is unused):
                                           //     the first GEMM instructions of a layer start after 1/16 of the epilogue
   kBarWPeer = kBarA0Sub + 4,              // [6] leader: the peer CTA's half of weight stage s landed        (peer warp 1)
-  kBarAPeer = kBarWPeer + kNumWStages,    // [8] leader: the peer CTA published k-step ks of slot 0 (index ks) or the whole
-                                          //     chunk in slot s (index 4 + s)                                  (peer warp 2)
-  kBarCount = kBarAPeer + 8
+  kBarAMma = kBarWPeer + kNumWStages,     // [8] leader: MMA-facing operand barriers, 32 arrivals = the 16 epilogue warps of BOTH
+                                          //     CTAs (index ks: k-step ks of slot 0; index 4 + s: the whole chunk in slot s).
+                                          //     kBarAFull / kBarA0Sub stay CTA-local (16 arrivals) for each CTA's store warp.
+  kBarCount = kBarAMma + 8
 };
 static_assert(8 * kBarCount + 8 <= 384, "barrier block overflow");
 
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_pair_kernel(const 
     }
     mbar_init(bar(kBarAccFull), 1);
     for (int i = 0; i < kNumWStages; ++i) mbar_init(bar(kBarWPeer + i), 1);
-    for (int i = 0; i < 8; ++i) mbar_init(bar(kBarAPeer + i), 1);
+    for (int i = 0; i < 8; ++i) mbar_init(bar(kBarAMma + i), 2 * kEpiWarps);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -129,34 +129,6 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_pair_kernel(const 
   cluster_sync_all();       // the peer's barriers are initialised before anything arrives on them remotely
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
-
-  if (warp == 2 && rank == 1 && lane == 0) {
-    // ======================= peer: forward "A operand event" to the leader =======================
-    // Mirrors the order in which the leader's MMA thread consumes the operand barriers.
-    uint32_t a_phase = 0;
-    auto forward = [&](uint32_t local_bar, uint32_t bit, uint32_t peer_index) {
-      mbar_wait(bar(local_bar), (a_phase >> bit) & 1u);
-      a_phase ^= 1u << bit;
-      mbar_arrive_cluster(mapa_cluster(bar(kBarAPeer + peer_index), 0));
-    };
-    for (int pt = pair_id; pt < num_ptiles; pt += num_pairs) {
-      for (int l = 0; l < kLayers; ++l) {
-        const int nkc = (!kIsBwd && l == 0) ? kSamples : kAChunks;
-        for (int kc = 0; kc < nkc; ++kc) {
-          const uint32_t slot = kc & 3;
-          if (slot == 0) {
-            for (uint32_t ks = 0; ks < 4; ++ks) forward(kBarA0Sub + ks, 4 + ks, ks);
-          } else {
-            forward(kBarAFull + slot, slot, 4 + slot);
-          }
-        }
-      }
-      if constexpr (kIsBwd) {   // the extra chunks of the last backward epilogue (see the MMA issuer)
-        for (uint32_t ks = 0; ks < 4; ++ks) forward(kBarA0Sub + ks, 4 + ks, ks);
-        for (uint32_t slot = 1; slot < kAChunks; ++slot) forward(kBarAFull + slot, slot, 4 + slot);
-      }
-    }
-  }
 
   if (warp == 0) {
     // ======================= weight producer =======================
@@ -191,7 +163,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_pair_kernel(const 
         for (int i = 0; i < per_tile; ++i, ++it) {
           const uint32_t ws = it % kNumWStages;
           mbar_wait(bar(kBarWFull + ws), (it / kNumWStages) & 1u);
-          mbar_arrive_cluster(mapa_cluster(bar(kBarWPeer + ws), 0));
+          mbar_arrive_cluster_relaxed(mapa_cluster(bar(kBarWPeer + ws), 0));
         }
       }
     }
@@ -226,8 +198,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_pair_kernel(const 
             };
             auto wait_a = [&](uint32_t barrier, uint32_t bit) {
               const long long t0 = p.stats ? clock64() : 0;
-              mbar_wait(bar(barrier), (a_phase >> bit) & 1u);                                     // my CTA's epilogue
-              mbar_wait_cluster(bar(kBarAPeer + (bit >= 4 ? bit - 4 : 4 + bit)), (a_phase >> bit) & 1u);   // the peer's
+              (void)barrier;   // the 32-arrival MMA-facing barrier of this event
+              mbar_wait_cluster(bar(kBarAMma + (bit >= 4 ? bit - 4 : 4 + bit)), (a_phase >> bit) & 1u);
               if (p.stats) { if (l == 0) t_a_head += clock64() - t0; else t_a_body += clock64() - t0; }
               a_phase ^= 1u << bit;
               tc_fence_after_sync();
@@ -287,13 +259,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_pair_kernel(const 
           // the last backward epilogue publishes 4 more chunks (d head pre-activation, consumed only by the
           // store warp): step over those phases so the parity bookkeeping stays aligned for the next tile
           for (uint32_t ks = 0; ks < 4; ++ks) {
-            mbar_wait(bar(kBarA0Sub + ks), (a_phase >> (4 + ks)) & 1u);
-            mbar_wait_cluster(bar(kBarAPeer + ks), (a_phase >> (4 + ks)) & 1u);
+            mbar_wait_cluster(bar(kBarAMma + ks), (a_phase >> (4 + ks)) & 1u);
             a_phase ^= 1u << (4 + ks);
           }
           for (uint32_t slot = 1; slot < kAChunks; ++slot) {
-            mbar_wait(bar(kBarAFull + slot), (a_phase >> slot) & 1u);
-            mbar_wait_cluster(bar(kBarAPeer + 4 + slot), (a_phase >> slot) & 1u);
+            mbar_wait_cluster(bar(kBarAMma + 4 + slot), (a_phase >> slot) & 1u);
             a_phase ^= 1u << slot;
           }
         }
@@ -376,7 +346,16 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_pair_kernel(const 
     const uint32_t g0 = qt >> 1, uu = qt & 1u;
 
     // kBarA0Sub[ks] counts all 16 warps: owners arrive when their part of k-step ks is written, the others at once.
-    auto arrive_sub = [&](uint32_t ks) { if (lane == 0) mbar_arrive(bar(kBarA0Sub + ks)); };
+    auto arrive_mma = [&](uint32_t idx) {   // leader: local arrive; peer: signal-only remote arrive on the leader's barrier
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(bar(kBarAMma + idx));
+        else mbar_arrive_cluster_relaxed(mapa_cluster(bar(kBarAMma + idx), 0));
+      }
+    };
+    auto arrive_sub = [&](uint32_t ks) {
+      arrive_mma(ks);
+      if (kSave && lane == 0) mbar_arrive(bar(kBarA0Sub + ks));
+    };
     auto make_visible = [&]() {   // generic-proxy smem writes -> tensor core (async proxy), TMEM reads ordered
       fence_proxy_async_smem();
       tc_fence_before_sync();
@@ -387,8 +366,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_pair_kernel(const 
       if (slot == 0) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) arrive_sub(ks);
-      } else if (lane == 0) {
-        mbar_arrive(bar(kBarAFull + slot));
+      } else {
+        arrive_mma(4 + slot);
+        if (kSave && lane == 0) mbar_arrive(bar(kBarAFull + slot));
       }
     };
     // before rewriting a slot in save modes: the store warp must have copied the previous content out

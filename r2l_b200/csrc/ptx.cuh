@@ -74,6 +74,11 @@ __device__ __forceinline__ uint32_t mapa_cluster(uint32_t local_addr, uint32_t r
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Signal only (no cumulative release at cluster scope, which costs the issuing warp hundreds of cycles): used after
+// the data it announces has already been made visible by fence.proxy.async + a CTA-scope release/acquire chain.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
