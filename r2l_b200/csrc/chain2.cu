@@ -7,7 +7,8 @@
 //   * L2 -> SM weight traffic per SM halves (42 -> 21 B/cycle at full tensor rate).
 // Differences to chain.cu: the leader CTA (cluster rank 0) issues the MMAs for both; its operand barriers count the
 // epilogue warps of BOTH CTAs (the peer's warps arrive remotely, signal-only: their smem writes were already published to
-// the async proxy by fence.proxy.async); the peer's warp 1 forwards "my weight half landed"; each CTA keeps local
+// the async proxy by fence.proxy.async, so the leader waits with ordinary CTA-scope try_wait: a cluster-scope acquire
+// costs ~180 cycles per wait even when the phase has long completed); the peer's warp 1 forwards "my weight half landed"; each CTA keeps local
 // copies of the operand barriers for its own store warp in the training modes; tcgen05.commit multicasts to both CTAs.
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -192,14 +193,14 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_pair_kernel(const 
             auto wait_w = [&](uint32_t i) {
               const long long t0 = p.stats ? clock64() : 0;
               mbar_wait(bar(kBarWFull + i % kNumWStages), (i / kNumWStages) & 1u);            // my half
-              mbar_wait_cluster(bar(kBarWPeer + i % kNumWStages), (i / kNumWStages) & 1u);    // the peer's half
+              mbar_wait(bar(kBarWPeer + i % kNumWStages), (i / kNumWStages) & 1u);    // the peer's half
               if (p.stats) t_w += clock64() - t0;
               tc_fence_after_sync();
             };
             auto wait_a = [&](uint32_t barrier, uint32_t bit) {
               const long long t0 = p.stats ? clock64() : 0;
               (void)barrier;   // the 32-arrival MMA-facing barrier of this event
-              mbar_wait_cluster(bar(kBarAMma + (bit >= 4 ? bit - 4 : 4 + bit)), (a_phase >> bit) & 1u);
+              mbar_wait(bar(kBarAMma + (bit >= 4 ? bit - 4 : 4 + bit)), (a_phase >> bit) & 1u);
               if (p.stats) { if (l == 0) t_a_head += clock64() - t0; else t_a_body += clock64() - t0; }
               a_phase ^= 1u << bit;
               tc_fence_after_sync();
@@ -259,11 +260,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_pair_kernel(const 
           // the last backward epilogue publishes 4 more chunks (d head pre-activation, consumed only by the
           // store warp): step over those phases so the parity bookkeeping stays aligned for the next tile
           for (uint32_t ks = 0; ks < 4; ++ks) {
-            mbar_wait_cluster(bar(kBarAMma + ks), (a_phase >> (4 + ks)) & 1u);
+            mbar_wait(bar(kBarAMma + ks), (a_phase >> (4 + ks)) & 1u);
             a_phase ^= 1u << (4 + ks);
           }
           for (uint32_t slot = 1; slot < kAChunks; ++slot) {
-            mbar_wait_cluster(bar(kBarAMma + 4 + slot), (a_phase >> slot) & 1u);
+            mbar_wait(bar(kBarAMma + 4 + slot), (a_phase >> slot) & 1u);
             a_phase ^= 1u << slot;
           }
         }
