@@ -185,6 +185,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
+    if os.environ.get("R2L_PAIR_MODE") is not None:   # experiment switch: 0 / 1 / -1 (default)
+        from r2l_b200 import _lib as _l
+        _l.lib().r2l_set_pair_mode(int(os.environ["R2L_PAIR_MODE"]))
 
     ro, rd, tg = synthetic_rays(BATCH, seed=rank)
     h_ro, h_rd, h_tg = (torch.from_numpy(a).pin_memory() for a in (ro, rd, tg))

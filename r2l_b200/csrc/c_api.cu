@@ -11,7 +11,8 @@ namespace {
 thread_local char g_err[512] = "";
 long long* g_stats = nullptr;  // debug cycle counters, see r2l_debug_set_stats
 long long* g_trace = nullptr;  // debug time stamps, see r2l_debug_set_trace
-int g_pair = 0;                // 1: run the chain kernels as CTA pairs (cta_group::2), see r2l_set_pair_mode
+int g_pair = -1;               // chain kernels as CTA pairs (cta_group::2): 1 always, 0 never, -1 training kernels only
+bool use_pair(int mode) { return g_pair == 1 || (g_pair < 0 && mode != r2l::kFwdInfer); }
 
 int fail(const char* fmt, const char* detail) {
   snprintf(g_err, sizeof(g_err), fmt, detail);
@@ -52,10 +53,10 @@ constexpr int kDwSplits = 8;          // ray-tile ranges per weight-gradient uni
 constexpr size_t kDwPartialBytes = (size_t)90 * kDwSplits * (256 * 256 + 256) * sizeof(float);
 
 int num_tiles(int64_t n_rays) { return (int)((n_rays + r2l::kTileM - 1) / r2l::kTileM); }
-int fwd_grid(int64_t n_rays) {
+int fwd_grid(int64_t n_rays, int mode) {
   const int sms = sm_count();
   const int t = num_tiles(n_rays);
-  if (g_pair) {   // CTA pairs: an even grid, one pair per two tiles
+  if (use_pair(mode)) {   // CTA pairs: an even grid, one pair per two tiles
     const int pairs = (t + 1) / 2, max_pairs = sms / 2;
     return 2 * (pairs < max_pairs ? pairs : max_pairs);
   }
@@ -63,7 +64,7 @@ int fwd_grid(int64_t n_rays) {
 }
 int even_tiles(int64_t n_rays) { return (num_tiles(n_rays) + 1) & ~1; }   // pair mode may run one dummy tile
 cudaError_t launch_chain_any(int mode, const r2l::ChainParams& p, int grid, cudaStream_t stream) {
-  return g_pair ? r2l::launch_chain_pair(mode, p, grid, stream) : r2l::launch_chain(mode, p, grid, stream);
+  return use_pair(mode) ? r2l::launch_chain_pair(mode, p, grid, stream) : r2l::launch_chain(mode, p, grid, stream);
 }
 }  // namespace
 
@@ -126,7 +127,7 @@ int r2l_forward(int input_kind, const float* in0, const float* in1, const float*
   p.num_tiles = num_tiles(n_rays);
   p.stats = g_stats;
   p.trace = g_trace;
-  return check(launch_chain_any(r2l::kFwdInfer, p, fwd_grid(n_rays), (cudaStream_t)stream), "r2l_forward");
+  return check(launch_chain_any(r2l::kFwdInfer, p, fwd_grid(n_rays, r2l::kFwdInfer), (cudaStream_t)stream), "r2l_forward");
 }
 
 size_t r2l_bwd_workspace_bytes(int64_t n_rays) { return r2l_fwd_workspace_bytes(n_rays) + kDwPartialBytes; }
@@ -159,7 +160,7 @@ int r2l_forward_train(int input_kind, const float* in0, const float* in1, const 
   p.num_tiles = num_tiles(n_rays);
   p.stats = g_stats;
   p.trace = g_trace;
-  return check(launch_chain_any(r2l::kFwdTrain, p, fwd_grid(n_rays), (cudaStream_t)stream), "r2l_forward_train");
+  return check(launch_chain_any(r2l::kFwdTrain, p, fwd_grid(n_rays, r2l::kFwdTrain), (cudaStream_t)stream), "r2l_forward_train");
 }
 
 int r2l_backward(int input_kind, const void* packed, const float* rgb, const float* grad_rgb, const float* zf,
@@ -189,7 +190,7 @@ int r2l_backward(int input_kind, const void* packed, const float* rgb, const flo
   p.trace = g_trace;
   // When the chain grid (one CTA per tile) and the 90 weight-gradient CTAs fit on the GPU together, run them
   // concurrently: dw.cu starts on each layer as soon as every tile has stored that layer's dY operand.
-  const int grid = fwd_grid(n_rays);
+  const int grid = fwd_grid(n_rays, r2l::kBwd);
   SideStream* side = (grid + 90 <= sm_count()) ? side_stream() : nullptr;
   int* ready = reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + r2l_fwd_workspace_bytes(n_rays) - kReadyBytes);
   r2l::DwParams d;
@@ -318,8 +319,8 @@ int r2l_debug_set_stats(long long* stats) {
   return 0;
 }
 
-int r2l_set_pair_mode(int on) {
-  g_pair = on ? 1 : 0;
+int r2l_set_pair_mode(int mode) {
+  g_pair = mode < 0 ? -1 : (mode ? 1 : 0);
   return 0;
 }
 
