@@ -62,6 +62,11 @@ int fwd_grid(int64_t n_rays, int mode) {
   }
   return t < sms ? t : sms;
 }
+int plain_grid(int64_t n_units) {   // one CTA per 128-unit tile, at most one per SM (single-CTA kernels)
+  const int sms = sm_count();
+  const int t = num_tiles(n_units);
+  return t < sms ? t : sms;
+}
 int even_tiles(int64_t n_rays) { return (num_tiles(n_rays) + 1) & ~1; }   // pair mode may run one dummy tile
 cudaError_t launch_chain_any(int mode, const r2l::ChainParams& p, int grid, cudaStream_t stream) {
   return use_pair(mode) ? r2l::launch_chain_pair(mode, p, grid, stream) : r2l::launch_chain(mode, p, grid, stream);
@@ -296,7 +301,7 @@ int r2l_teacher_forward(const float* pts, const float* viewdirs, const float* x_
   p.n_points = n_points;
   p.samples_per_ray = samples_per_ray > 0 ? samples_per_ray : 1;
   p.num_tiles = num_tiles(n_points);
-  return check(r2l::launch_teacher(p, fwd_grid(n_points), (cudaStream_t)stream), "r2l_teacher_forward");
+  return check(r2l::launch_teacher(p, plain_grid(n_points), (cudaStream_t)stream), "r2l_teacher_forward");
 }
 
 int r2l_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
