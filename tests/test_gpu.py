@@ -360,3 +360,29 @@ def test_teacher_render_rays_vs_oracle(teacher):
     np.testing.assert_allclose(rgb.cpu().numpy(), ref["rgb_map"], rtol=1e-3, atol=5e-4)
     np.testing.assert_allclose(acc.cpu().numpy(), ref["acc_map"], rtol=1e-3, atol=5e-4)
     assert set(extras) == {"depth_map", "rgb0", "disp0", "acc0", "z_std"}
+
+
+def test_cta_pair_kernels_match_single_cta(flat_seed0, packed):
+    """The cta_group::2 (CTA-pair) chain kernels compute exactly what the single-CTA kernels compute: bit-identical
+    forward (odd and even tile counts), gradients equal to fp32 round-off."""
+    from r2l_b200 import _lib
+    L = _lib.lib()
+    z = orc.sampler_z_vals(2.0, 6.0).tolist()
+    try:
+        for n in (100, 129, 1000, 20001):
+            torch.manual_seed(n)
+            o, d = (torch.randn(n, 3) * 0.5).to(DEV), torch.randn(n, 3).to(DEV)
+            L.r2l_set_pair_mode(0); a = ops.forward(packed, rays_o=o, rays_d=d, z_vals=z)
+            L.r2l_set_pair_mode(1); b = ops.forward(packed, rays_o=o, rays_d=d, z_vals=z)
+            assert torch.equal(a, b)
+        n = 1100   # 9 tiles: the last pair runs a dummy tile
+        torch.manual_seed(3)
+        o, d, t = (torch.randn(n, 3) * 0.5).to(DEV), torch.randn(n, 3).to(DEV), torch.rand(n, 3).to(DEV)
+        grads = []
+        for mode in (0, 1):
+            L.r2l_set_pair_mode(mode)
+            rgb, ctx = ops.forward_train(packed, rays_o=o, rays_d=d, z_vals=z)
+            grads.append(ops.backward(packed, ctx, (2.0 / (3 * n)) * (rgb - t)).clone())
+        assert float((grads[0] - grads[1]).norm() / grads[0].norm()) < 1e-6
+    finally:
+        L.r2l_set_pair_mode(-1)
