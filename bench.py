@@ -259,7 +259,7 @@ def run_ours(args):
         del ctx
     k_ms /= reps
     achieved_tflops = BATCH * FWD_FLOP_PER_RAY / (k_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "r2l_chain_pair_kernel<kFwdTrain> (4096 rays, 16 CTA pairs, cta_group::2)", "achieved": achieved_tflops,
+    roofline = {"bound": "tensor", "kernel": "r2l_chain_kernel<kFwdTrain, PAIR> (4096 rays, 16 CTA pairs, cta_group::2)", "achieved": achieved_tflops,
                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved_tflops / peaks["bf16_tflops"],
                 "traffic": 358.7e6, "traffic_source": "profiles/r1_summary.md: dram read+write of the forward train kernel at 4096 rays (ncu --set full)", "peak_source": peaks["source"], "kernel_ms": k_ms,
                 "note": "algorithmic fp32 FLOPs; the kernel issues 3x that as bf16 MMAs (hi*hi+lo*hi+hi*lo) to meet the 1e-3 fp32 parity bar, and a 4096-ray batch fills 32 of 148 SMs"}

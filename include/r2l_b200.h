@@ -106,9 +106,11 @@ int r2l_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
  * [4] MMA-thread total. */
 int r2l_debug_set_stats(long long* stats);
 
-/* Chain kernels as CTA pairs (tcgen05 cta_group::2: two 128-ray tiles per SM pair, each CTA stages half of every weight
- * image): 1 = always, 0 = never, -1 = default = the training kernels only (measured: +4 % on the train step, -10 % on
- * inference).  Results are identical in both forms.  Process-wide; buffers sized by the *_bytes queries fit both. */
+/* Launch form of the chain kernels (r2l_b200/csrc/chain.cu): 0 = single CTA per 128-ray tile, 1 = CTA pair (tcgen05
+ * cta_group::2, M = 256) with one tile per CTA, 2 = CTA pair sharing one tile (cta_group::2, M = 128, 64 rays per CTA:
+ * half the latency per layer, the form for small batches), -1 = default = chosen per call (form 2 for the training
+ * kernels and for inference batches that leave SM pairs idle, form 0 otherwise).  Forms 0 and 1 give bit-identical
+ * results, form 2 differs by fp32 round-off.  Process-wide; buffers sized by the *_bytes queries fit every form. */
 int r2l_set_pair_mode(int mode);
 
 /* Debug: device buffer [grid][5][96] of clock64 stamps for the first tile of each CTA of the next chain launches:
@@ -117,8 +119,12 @@ int r2l_set_pair_mode(int mode);
  * %globaltimer stamps of the weight-gradient kernel (start, flag seen, -, end).  NULL = off. */
 int r2l_debug_set_trace(long long* trace);
 
-/* Debug: tensor-pipe micro-benchmark; out_cycles[grid] = cycles for `reps` x 48 tcgen05.mma (M128 N256 K16). */
-int r2l_debug_mma_rate(int reps, int grid, long long* out_cycles, void* stream);
+/* Debug: tensor-pipe micro-benchmark; out_cycles[grid] = cycles for `reps` x 48 tcgen05.mma (N256 K16) in the MMA shape of
+ * launch form `form` (0: M128 cta_group::1; 1: M256 cta_group::2; 2: M128 cta_group::2; forms 1, 2: grid even, the leader of
+ * pair i writes out_cycles[2 i]).  variant: bit 0 = non-zero operands (zeros otherwise); variant >> 1 = issue pattern (0: chunk by
+ * chunk, products grouped; form 2 only: 1 = the chain kernel's operand addresses and issue order, 2 = its addresses, products
+ * grouped, 3 = as 1 with a tcgen05.fence::after_thread_sync in front of every MMA pair). */
+int r2l_debug_mma_rate(int form, int variant, int reps, int grid, long long* out_cycles, void* stream);
 
 /* Debug / test hook: C[128,256] = A[128,256] * W_l^T through one tcgen05 layer step, l = body layer 0..85. */
 int r2l_selftest_layer(const float* A, const void* packed, int layer, float* C, void* stream);

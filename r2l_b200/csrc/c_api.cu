@@ -11,8 +11,7 @@ namespace {
 thread_local char g_err[512] = "";
 long long* g_stats = nullptr;  // debug cycle counters, see r2l_debug_set_stats
 long long* g_trace = nullptr;  // debug time stamps, see r2l_debug_set_trace
-int g_pair = -1;               // chain kernels as CTA pairs (cta_group::2): 1 always, 0 never, -1 training kernels only
-bool use_pair(int mode) { return g_pair == 1 || (g_pair < 0 && mode != r2l::kFwdInfer); }
+int g_form = -1;               // launch form of the chain kernels (chain.cu): 0 single, 1 pair, 2 half, -1 = chosen per call
 
 int fail(const char* fmt, const char* detail) {
   snprintf(g_err, sizeof(g_err), fmt, detail);
@@ -53,11 +52,21 @@ constexpr int kDwSplits = 8;          // ray-tile ranges per weight-gradient uni
 constexpr size_t kDwPartialBytes = (size_t)90 * kDwSplits * (256 * 256 + 256) * sizeof(float);
 
 int num_tiles(int64_t n_rays) { return (int)((n_rays + r2l::kTileM - 1) / r2l::kTileM); }
+// Which launch form a chain kernel takes.  Two SMs that share a tile (half form) finish it in about half the time, so it
+// wins whenever there are SM pairs to spare, and it keeps the per-layer latency low for the training step; with more
+// tiles than SM pairs every SM has work either way and the forms run at the same rate, so inference on whole images
+// keeps the cluster-free single form.
+int chain_form(int mode, int64_t n_rays) {
+  if (g_form >= 0) return g_form;
+  if (mode != r2l::kFwdInfer) return r2l::kFormHalf;
+  return num_tiles(n_rays) <= sm_count() / 2 ? r2l::kFormHalf : r2l::kFormSingle;
+}
 int fwd_grid(int64_t n_rays, int mode) {
   const int sms = sm_count();
   const int t = num_tiles(n_rays);
-  if (use_pair(mode)) {   // CTA pairs: an even grid, one pair per two tiles
-    const int pairs = (t + 1) / 2, max_pairs = sms / 2;
+  const int form = chain_form(mode, n_rays);
+  if (form != r2l::kFormSingle) {   // CTA pairs: an even grid; pair form: one pair per two tiles, half form: one pair per tile
+    const int pairs = form == r2l::kFormHalf ? t : (t + 1) / 2, max_pairs = sms / 2;
     return 2 * (pairs < max_pairs ? pairs : max_pairs);
   }
   return t < sms ? t : sms;
@@ -69,7 +78,7 @@ int plain_grid(int64_t n_units) {   // one CTA per 128-unit tile, at most one pe
 }
 int even_tiles(int64_t n_rays) { return (num_tiles(n_rays) + 1) & ~1; }   // pair mode may run one dummy tile
 cudaError_t launch_chain_any(int mode, const r2l::ChainParams& p, int grid, cudaStream_t stream) {
-  return use_pair(mode) ? r2l::launch_chain_pair(mode, p, grid, stream) : r2l::launch_chain(mode, p, grid, stream);
+  return r2l::launch_chain(mode, chain_form(mode, p.n_rays), p, grid, stream);
 }
 }  // namespace
 
@@ -84,7 +93,7 @@ size_t r2l_fwd_workspace_bytes(int64_t n_rays) {
   // head-output scratch: one [128,256] fp32 tile per resident CTA (sized for the largest grid we launch)
   int sms = sm_count();
   if (sms <= 0) sms = 148;
-  const int t = even_tiles(n_rays);
+  const int t = 2 * num_tiles(n_rays);   // the half form runs two CTAs per tile, each with its own scratch rows
   const int g = t < sms ? t : sms;
   return (size_t)(g > 0 ? g : 1) * r2l::kTileM * r2l::kWidth * sizeof(float) + kReadyBytes;
 }
@@ -196,13 +205,14 @@ int r2l_backward(int input_kind, const void* packed, const float* rgb, const flo
   // When the chain grid (one CTA per tile) and the 90 weight-gradient CTAs fit on the GPU together, run them
   // concurrently: dw.cu starts on each layer as soon as every tile has stored that layer's dY operand.
   const int grid = fwd_grid(n_rays, r2l::kBwd);
-  SideStream* side = (grid + 90 <= sm_count()) ? side_stream() : nullptr;
+  SideStream* side = (grid + 64 <= sm_count()) ? side_stream() : nullptr;
   int* ready = reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + r2l_fwd_workspace_bytes(n_rays) - kReadyBytes);
   r2l::DwParams d;
   d.fwd_saved = p.fwd_saved;
   d.bwd_saved = p.saved;
   d.grads = grads;
   d.num_tiles = p.num_tiles;
+  d.ready_target = p.num_tiles * (chain_form(r2l::kBwd, n_rays) == r2l::kFormHalf ? 2 : 1);   // store warps per tile
   d.input_kind = input_kind;
   d.accumulate = 0;
   d.ready = nullptr;
@@ -325,7 +335,7 @@ int r2l_debug_set_stats(long long* stats) {
 }
 
 int r2l_set_pair_mode(int mode) {
-  g_pair = mode < 0 ? -1 : (mode ? 1 : 0);
+  g_form = (mode < 0 || mode > 2) ? -1 : mode;
   return 0;
 }
 
@@ -334,9 +344,10 @@ int r2l_debug_set_trace(long long* trace) {
   return 0;
 }
 
-int r2l_debug_mma_rate(int reps, int grid, long long* out_cycles, void* stream) {
-  if (!out_cycles || reps < 1 || grid < 1) return fail("r2l_debug_mma_rate: %s", "bad arguments");
-  return check(r2l::launch_mma_rate(reps, grid, out_cycles, (cudaStream_t)stream), "r2l_debug_mma_rate");
+int r2l_debug_mma_rate(int form, int variant, int reps, int grid, long long* out_cycles, void* stream) {
+  if (!out_cycles || reps < 1 || grid < 1 || form < 0 || form > 2 || (form > 0 && (grid & 1)))
+    return fail("r2l_debug_mma_rate: %s", "bad arguments");
+  return check(r2l::launch_mma_rate(form, variant, reps, grid, out_cycles, (cudaStream_t)stream), "r2l_debug_mma_rate");
 }
 
 int r2l_selftest_layer(const float* A, const void* packed, int layer, float* C, void* stream) {

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) r2l_dw_kernel(const __grid_cons
         // the dY operand of this unit's layer (group index = position of that layer in the backward sweep)
         const int group = is_head ? kBodyLayers : ob;
         unsigned ns = 64;
-        while (flag_acquire_load(p.ready + group) < p.num_tiles) {
+        while (flag_acquire_load(p.ready + group) < p.ready_target) {
           __nanosleep(ns);
           if (ns < 2048) ns <<= 1;
         }
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) r2l_dw_kernel(const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // the whole warp waits, one elected lane issues (keeps the descriptors in uniform registers, see chain.cu)
       constexpr uint32_t idesc = umma_idesc_bf16(128, 256, 1, 1);   // both operands MN-major
       constexpr uint32_t kLbo = 2 * kDwPiece;   // next 64-feature group of the same plane
       constexpr uint32_t kSbo = 1024;           // next 8 rays
@@ -118,22 +118,25 @@ __global__ void __launch_bounds__(kDwThreads, 1) r2l_dw_kernel(const __grid_cons
         mbar_wait(bar_full(s), ph);
         tc_fence_after_sync();
         const uint32_t dy = smem_base + s * kDwStageBytes, x = dy + kDwOperand;
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
+          for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const uint32_t d = tmem_base + 256u * half;
-            const uint32_t a_hi = dy + (4 * half) * kDwPiece + ks * 2048, a_lo = a_hi + kDwPiece;
-            const uint32_t b_hi = x + ks * 2048, b_lo = b_hi + kDwPiece;
-            const uint32_t first = (it == 0 && ks == 0) ? 0u : 1u;
-            umma_bf16(d, umma_desc_sw128(a_hi, kLbo, kSbo), umma_desc_sw128(b_hi, kLbo, kSbo), idesc, first);
-            umma_bf16(d, umma_desc_sw128(a_lo, kLbo, kSbo), umma_desc_sw128(b_hi, kLbo, kSbo), idesc, 1u);
-            umma_bf16(d, umma_desc_sw128(a_hi, kLbo, kSbo), umma_desc_sw128(b_lo, kLbo, kSbo), idesc, 1u);
+            for (int half = 0; half < 2; ++half) {
+              const uint32_t d = tmem_base + 256u * half;
+              const uint32_t a_hi = dy + (4 * half) * kDwPiece + ks * 2048, a_lo = a_hi + kDwPiece;
+              const uint32_t b_hi = x + ks * 2048, b_lo = b_hi + kDwPiece;
+              const uint32_t first = (it == 0 && ks == 0) ? 0u : 1u;
+              umma_bf16(d, umma_desc_sw128(a_hi, kLbo, kSbo), umma_desc_sw128(b_hi, kLbo, kSbo), idesc, first);
+              umma_bf16(d, umma_desc_sw128(a_lo, kLbo, kSbo), umma_desc_sw128(b_hi, kLbo, kSbo), idesc, 1u);
+              umma_bf16(d, umma_desc_sw128(a_hi, kLbo, kSbo), umma_desc_sw128(b_lo, kLbo, kSbo), idesc, 1u);
+            }
           }
+          umma_commit(bar_empty(s));
         }
-        umma_commit(bar_empty(s));
+        __syncwarp();
       }
-      umma_commit(bar_done);
+      if (elect_one_sync()) umma_commit(bar_done);
     }
   } else if (warp >= 4) {
     const uint32_t t = (warp - 4) * 32 + lane;   // 0..127: owns output columns 2t, 2t+1 of dY for the bias sum

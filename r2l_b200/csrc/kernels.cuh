@@ -49,7 +49,8 @@ struct DwParams {
   float* partials;        // [90][splits][256*256 + 256] scratch (split mode)
   int* tickets;           // [90] zeroed counters (split mode)
   long long* times;       // optional debug: [unit][4] globaltimer stamps (start, flag seen, MMAs done, end)
-  const int* ready;       // optional: wait until ready[group of this unit] == num_tiles before streaming (see ChainParams)
+  const int* ready;       // optional: wait until ready[group of this unit] == ready_target before streaming (see ChainParams)
+  int ready_target;       // store warps that announce each group: num_tiles (x 2 when the chain ran in its half form)
 };
 
 struct TailGradParams {
@@ -74,8 +75,8 @@ struct TeacherParams {
 cudaError_t launch_teacher_pack(const float* params, void* packed, cudaStream_t stream);
 cudaError_t launch_teacher(const TeacherParams& p, int grid, cudaStream_t stream);
 cudaError_t launch_pack(const float* params, void* packed, cudaStream_t stream);
-cudaError_t launch_chain(int mode, const ChainParams& p, int grid, cudaStream_t stream);
-cudaError_t launch_chain_pair(int mode, const ChainParams& p, int grid, cudaStream_t stream);   // grid even: CTA pairs
+enum : int { kFormSingle = 0, kFormPair = 1, kFormHalf = 2 };   // launch forms of the chain kernels, see chain.cu
+cudaError_t launch_chain(int mode, int form, const ChainParams& p, int grid, cudaStream_t stream);   // pair / half: grid even, clusters of 2
 cudaError_t launch_dw(const DwParams& p, cudaStream_t stream);
 cudaError_t launch_tail_grads(const TailGradParams& p, bool zero_first, cudaStream_t stream);
 cudaError_t launch_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, int64_t n_rays, int n_samples,
@@ -86,7 +87,7 @@ cudaError_t launch_sample_pdf_merge(const float* z_vals, const float* weights, c
 cudaError_t launch_embed(const float* x, float* out, int64_t n, int dim, int L, int style, cudaStream_t stream);
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float w1, float beta2, float w2, float eps,
                         float step_size, float inv_bc2_sqrt, cudaStream_t stream);
-cudaError_t launch_mma_rate(int reps, int grid, long long* out, cudaStream_t stream);
+cudaError_t launch_mma_rate(int form, int variant, int reps, int grid, long long* out, cudaStream_t stream);
 cudaError_t launch_umma_selftest(const float* A, const void* images, float* C, cudaStream_t stream);
 
 }  // namespace r2l

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kTThreads, 1) r2l_teacher_kernel(const __grid_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // the whole warp waits, one elected lane issues (keeps the descriptors in uniform registers, see chain.cu)
       constexpr uint32_t idesc = umma_idesc_bf16(128, 256, 0, 0);
       uint32_t it = 0, a_phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -146,14 +146,16 @@ __global__ void __launch_bounds__(kTThreads, 1) r2l_teacher_kernel(const __grid_
               mbar_wait(bar(kTBarWFull + ws), (it / kTNumWStages) & 1u);
               tc_fence_after_sync();
               const uint32_t b = smem_base + kTSmemW + ws * kWImageBytes;
+              if (elect_one_sync()) {
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                umma_bf16(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b + 32 * ks, 16, 1024), idesc,
-                          (kc == 0 && ks == 0) ? 0u : 1u);
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_bf16(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b + 32 * ks, 16, 1024), idesc,
+                            (kc == 0 && ks == 0) ? 0u : 1u);
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                umma_bf16(d, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw128(b + 32 * ks, 16, 1024), idesc, 1u);
-              umma_commit(bar(kTBarWEmpty + ws));
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_bf16(d, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw128(b + 32 * ks, 16, 1024), idesc, 1u);
+                umma_commit(bar(kTBarWEmpty + ws));
+              }
               ++it;
             }
             {
@@ -161,15 +163,17 @@ __global__ void __launch_bounds__(kTThreads, 1) r2l_teacher_kernel(const __grid_
               mbar_wait(bar(kTBarWFull + ws), (it / kTNumWStages) & 1u);
               tc_fence_after_sync();
               const uint32_t b = smem_base + kTSmemW + ws * kWImageBytes;
+              if (elect_one_sync()) {
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                umma_bf16(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b + 32 * ks, 16, 1024), idesc, 1u);
-              umma_commit(bar(kTBarWEmpty + ws));
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_bf16(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b + 32 * ks, 16, 1024), idesc, 1u);
+                umma_commit(bar(kTBarWEmpty + ws));
+                if (nkc == 5 && kc == 0) umma_commit(bar(kTBarAEmpty));   // slot 0 is recycled for the 5th chunk
+              }
               ++it;
             }
-            if (nkc == 5 && kc == 0) umma_commit(bar(kTBarAEmpty));   // slot 0 is recycled for the 5th chunk
           }
-          umma_commit(bar(kTBarAccFull));
+          if (elect_one_sync()) umma_commit(bar(kTBarAccFull));
         }
       }
     }

@@ -1,4 +1,4 @@
-"""Per-layer time line of the forward chain kernel (debug stamps): where do the ~3.4k idle cycles per layer go?"""
+"""Per-layer time line of the forward chain kernel (debug stamps).  Usage: gpu_trace.py [infer|train] [form 0|1|2]"""
 import ctypes, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -10,16 +10,17 @@ packed = ops.pack_weights(init_flat_params(0).to(dev))
 n = 4096
 o = torch.randn(n, 3, device=dev) * 0.5; d = torch.randn(n, 3, device=dev); z = orc.sampler_z_vals(2.0, 6.0).tolist()
 mode = sys.argv[1] if len(sys.argv) > 1 else "infer"
-pair = len(sys.argv) > 2 and sys.argv[2] == "pair"
-_lib.lib().r2l_set_pair_mode(1 if pair else 0)
-cta = 2 if pair else 3
+form = int(sys.argv[2]) if len(sys.argv) > 2 else 0   # launch form of chain.cu: 0 single, 1 pair, 2 half
+_lib.lib().r2l_set_pair_mode(form)
+cta = 2 if form else 3                                # a leader CTA (the MMA thread's stamps live there)
+tensor = 3078 if form == 2 else 6151
 run = (lambda: ops.forward(packed, rays_o=o, rays_d=d, z_vals=z)) if mode == "infer" else (lambda: ops.forward_train(packed, rays_o=o, rays_d=d, z_vals=z))
 for _ in range(3): run()
 trace = torch.zeros(148 * 5 * 96 + 360, dtype=torch.int64, device=dev)
 _lib.lib().r2l_debug_set_trace(ctypes.c_void_p(trace.data_ptr()))
 run(); torch.cuda.synchronize()
 _lib.lib().r2l_debug_set_trace(None)
-print("mode:", mode)
+print("mode:", mode, "form:", form)
 t = trace[:148 * 5 * 96].view(148, 5, 96).cpu().numpy().astype(np.int64)[cta]
 start, issued, accdone, pub0, epidone = t
 L = 87
@@ -30,7 +31,7 @@ for l in (1, 2, 3, 10, 11, 40, 41, 85, 86):
 body = np.arange(1, 86)
 print("mean over body layers:")
 print("  layer period (start l+1 - start l)        ", np.mean(start[body + 1] - start[body]))
-print("  MMA start -> accumulator seen complete     ", np.mean(accdone[body] - start[body]), " (tensor work of a layer = 6151)")
+print("  MMA start -> accumulator seen complete     ", np.mean(accdone[body] - start[body]), f" (tensor work of a layer = {tensor})")
 print("  MMA start -> all 48 issued                 ", np.mean(issued[body] - start[body]))
 print("  acc complete -> first k-step published     ", np.mean(pub0[body] - accdone[body]))
 print("  first publish -> next layer's first MMA    ", np.mean(start[body + 1] - pub0[body]))
