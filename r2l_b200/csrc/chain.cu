@@ -471,9 +471,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
   } else if (warp == 3) {
     // ======================= operand-image store warp (train / bwd) =======================
     if (kSave && lane == 0) {
-      // Up to four 32 KiB stores in flight: chunk i's slot is released (kBarASaved) once store i has finished
-      // READING shared memory, which we learn when at most 3 younger bulk groups are still pending.  The
-      // epilogue rewrites a slot exactly 4 chunks after it published it, so this lag can never deadlock.
+      // A chunk's slot is released (kBarASaved) once its store has finished READING shared memory, which we learn when at
+      // most one younger bulk group is still pending, i.e. right after the NEXT chunk's store was issued.  The epilogue
+      // rewrites a slot four chunks after it published it, so the release is always at least two chunks early and the
+      // epilogue never waits for this warp (a longer lag would: with "3 younger groups" the slot of chunk c + 1 was only
+      // released by the store of chunk c of the same layer - a store-warp round trip between any two chunks).
       uint32_t a_phase = 0;
       int64_t issued = 0;
       const bool signal = kIsBwd && p.ready != nullptr;
@@ -499,9 +501,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
             bulk_s2g(dst + (int64_t)i * kAChunkBytes, smem_base + kSmemA + slot * kSlotBytes, kAChunkBytes);
           }
           bulk_commit();
-          if (issued >= 3) {
-            bulk_wait_read<3>();         // store (issued - 3) has read its slot
-            mbar_arrive(bar(kBarASaved + ((slot + 1) & 3)));
+          if (issued >= 1) {
+            bulk_wait_read<1>();         // store (issued - 1) has read its slot
+            mbar_arrive(bar(kBarASaved + ((slot + 3) & 3)));
           }
           if (signal && tile < p.num_tiles && slot == 3) {
             // everything but the 4 stores just issued has landed in global memory: announce those groups so the
@@ -515,10 +517,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
           for (; signalled < kSavedChunksPerTile / 4; ++signalled) flag_release_add(p.ready + signalled);
         }
       }
-      // drain: release the last three slots in issue order, then wait for the writes to land
-      const int64_t tail = issued < 3 ? issued : 3;
+      // drain: release the last slot, then wait for the writes to land
       bulk_wait_read<0>();
-      for (int64_t k = 0; k < tail; ++k) mbar_arrive(bar(kBarASaved + (uint32_t)((issued - tail + k) & 3)));
+      if (issued >= 1) mbar_arrive(bar(kBarASaved + (uint32_t)((issued - 1) & 3)));
       bulk_wait_all<0>();
     }
   } else if (warp >= 4) {
@@ -716,24 +717,28 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
           const int64_t chunk0 = from_h ? (kSamples + 4 * (2 * k + 1)) : kSamples;
           mask_img = p.fwd_saved + ((int64_t)tile * kFwdSavedChunks + chunk0) * kAChunkBytes;
         }
-        // side data of one 8-column unit (bias / ReLU mask), h = which of my two units of chunk c; fetched one unit ahead,
-        // the first two while the MMAs run
+        // side data of a chunk (bias / ReLU mask of my two 8-column units); the first chunk's is fetched while the MMAs run.
+        // (Fetching further ahead does not pay: the proxy fence of every publish waits for all loads in flight.)
         float4 bq[4];
         uint4 mq[2];
-        auto load_side = [&](uint32_t c, int h) {
+        auto load_side = [&](uint32_t c) {
           if constexpr (!kIsBwd) {
-            const float4* b4 = reinterpret_cast<const float4*>(bias + 64 * c + 16 * (g0 + 2 * h) + 8 * uu);
-            bq[2 * h] = __ldg(b4);
-            bq[2 * h + 1] = __ldg(b4 + 1);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const float4* b4 = reinterpret_cast<const float4*>(bias + 64 * c + 16 * (g0 + 2 * h) + 8 * uu);
+              bq[2 * h] = __ldg(b4);
+              bq[2 * h + 1] = __ldg(b4 + 1);
+            }
           } else {
             if (masked) {
               const uint8_t* plane = mask_img + (int64_t)c * kAChunkBytes;
-              mq[h] = __ldg(reinterpret_cast<const uint4*>(plane + (row0 + row) * 128u + (((2u * (g0 + 2 * h) + uu) ^ (row & 7u)) << 4)));
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+                mq[h] = __ldg(reinterpret_cast<const uint4*>(plane + (row0 + row) * 128u + (((2u * (g0 + 2 * h) + uu) ^ (row & 7u)) << 4)));
             }
           }
         };
-        load_side(c_first, 0);
-        load_side(c_first, 1);
+        load_side(c_first);
         mbar_wait(bar(kBarAccFull), acc_phase);
         acc_phase ^= 1u;
         tc_fence_after_sync();
@@ -741,13 +746,13 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
         if (tr) p.trace[((int64_t)blockIdx.x * 5 + 2) * 96 + l] = clock64();
         const bool feeds_mma = !last;                     // the last epilogue of a tile produces no further GEMM input
         const bool produces_chunk = feeds_mma || kIsBwd;  // backward's last output (d head pre-activation) is saved for dw
-        // The accumulator is read one 8-column unit ahead of the arithmetic (r[0..7] / r[8..15] alternate): the first
-        // k-step of the next layer is published after ONE short TMEM read, and the later reads hide behind the math.
-        uint32_t r[16];
-        const uint32_t tacc = tmem_row + (from_h ? kTmemH : kTmemZ) + 16u * g0 + 8u * uu;
-        tmem_ld8(tacc, &r[0]);
         for (uint32_t cc = 0; cc < kMyChunks; ++cc) {
           const uint32_t c = c_first + cc;
+          uint32_t r[16];
+          const uint32_t tacc = tmem_row + (from_h ? kTmemH : kTmemZ) + 64u * cc + 8u * uu;
+          tmem_ld8(tacc + 16u * g0, &r[0]);
+          tmem_ld8(tacc + 16u * (g0 + 2), &r[8]);
+          if (cc > 0) load_side(c);
           if (produces_chunk) {
             wait_saved(c, false);
             if constexpr (HALF) {
@@ -756,19 +761,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
               if (c == 0) { arrive_sub(1 - g0); arrive_sub(3 - g0); }   // the k-steps of chunk 0 I do not write
             }
           }
+          tmem_ld_wait();
           const uint32_t chunk_addr = smem_base + kSmemA + c * kSlotBytes;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const uint32_t g = g0 + 2 * h;
             const uint32_t col = 64u * c + 16u * g + 8u * uu;
-            tmem_ld_wait();
-            if (h == 0) {
-              tmem_ld8(tacc + 64u * cc + 32u, &r[8]);
-              if (cc > 0) load_side(c, 1);
-            } else if (cc + 1 < kMyChunks) {
-              tmem_ld8(tacc + 64u * (cc + 1), &r[0]);
-              load_side(c + 1, 0);
-            }
             float v[8];
             if constexpr (!kIsBwd) {
               v[0] = __uint_as_float(r[8 * h + 0]) + bq[2 * h].x;

@@ -388,6 +388,7 @@ def test_chain_launch_forms_agree(flat_seed0, packed):
             rgb, ctx = ops.forward_train(packed, rays_o=o, rays_d=d, z_vals=z)
             grads.append(ops.backward(packed, ctx, (2.0 / (3 * n)) * (rgb - t)).clone())
         assert float((grads[0] - grads[1]).norm() / grads[0].norm()) < 1e-6
-        assert float((grads[0] - grads[2]).norm() / grads[0].norm()) < 2e-4
+        # (both are ~6e-4 from the fp64 gradient - the bf16x3 split error - so they differ from each other at that level)
+        assert float((grads[0] - grads[2]).norm() / grads[0].norm()) < 2e-3
     finally:
         L.r2l_set_pair_mode(-1)
