@@ -109,8 +109,8 @@ int r2l_debug_set_stats(long long* stats);
 /* Launch form of the chain kernels (r2l_b200/csrc/chain.cu): 0 = single CTA per 128-ray tile, 1 = CTA pair (tcgen05
  * cta_group::2, M = 256) with one tile per CTA, 2 = CTA pair sharing one tile (cta_group::2, M = 128, 64 rays per CTA:
  * half the latency per layer, the form for small batches), -1 = default = chosen per call (form 2 for the training
- * kernels and for inference batches that leave SM pairs idle, form 0 otherwise).  Forms 0 and 1 give bit-identical
- * results, form 2 differs by fp32 round-off.  Process-wide; buffers sized by the *_bytes queries fit every form. */
+ * kernels and for inference batches that leave SM pairs idle, form 0 otherwise).  All forms issue their MMAs in the same order: results are
+ * bit-identical, whichever form a call takes.  Process-wide; buffers sized by the *_bytes queries fit every form. */
 int r2l_set_pair_mode(int mode);
 
 /* Debug: device buffer [grid][5][96] of clock64 stamps for the first tile of each CTA of the next chain launches:

@@ -69,7 +69,7 @@ __host__ __device__ constexpr ChainGeom chain_geom(int form) {
   g.off_w = 4u * g.slot;
   g.off_bar = g.off_w + g.w_stages * g.w_stage_bytes;
   g.off_tail = g.off_bar + kBarBlockBytes;
-  g.used = g.off_tail + (form == kFormHalf ? 64u * 8u * 3u * 4u : 0u);   // half: 8 partial tail dots per ray
+  g.used = g.off_tail + (form == kFormHalf ? 64u * 16u * 3u * 4u : 0u);  // half: 16 partial tail dots per ray
   g.tmem_h = form == kFormHalf ? 128u : 256u;           // half: an accumulator is 128 columns wide (2x2 layout)
   return g;
 }
@@ -97,13 +97,6 @@ enum : uint32_t {
                                           //           by the 8 warps per CTA that own its feature half)
   kBarCount = kBarAMma + 16
 };
-// half form: the j-th weight image a group of four K chunks needs (the MMA issuer takes the chunks in the order 0, 2, 1, 3 -
-// chunks 0,1 and 2,3 are written by different warps at the same time - and per chunk pair first both W_hi, then both W_lo)
-__host__ __device__ constexpr int kHalfImageOrder(int j) { return ((j & 1) << 2) | ((j >> 2) << 1) | ((j >> 1) & 1); }
-static_assert(kHalfImageOrder(0) == 0 && kHalfImageOrder(1) == 4 && kHalfImageOrder(2) == 1 && kHalfImageOrder(3) == 5 &&
-              kHalfImageOrder(4) == 2 && kHalfImageOrder(5) == 6 && kHalfImageOrder(6) == 3 && kHalfImageOrder(7) == 7, "");
-static_assert(8 * kBarCount + 8 <= kBarBlockBytes, "barrier block overflow");
-
 // Quarter QT of a fused-order K chunk: 16 slots = 8 (sin, cos) pairs; the last quarter ends with x0,x1,x2,0.
 template <int QT>
 __device__ __forceinline__ void encode_quarter(const float (&x)[3], float (&out)[16]) {
@@ -223,12 +216,20 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
           mbar_wait(bar(kBarWEmpty + ws), ph ^ 1u);
           if (p.stats) t_wait += clock64() - t0;
           mbar_arrive_expect_tx(bar(kBarWFull + ws), kWStageBytes);
-          // half form: stage j of the ring holds the j-th image the MMA issuer needs of each group of four K chunks
-          const int ii = HALF ? (i & ~7) + kHalfImageOrder(i & 7) : i;
           const uint8_t* src;
-          if (kIsBwd) src = body_images + (int64_t)ii * kWImageBytes;
-          else src = ii < 32 ? head_images + (int64_t)ii * kWImageBytes : body_images + (int64_t)(ii - 32) * kWImageBytes;
-          bulk_g2s(smem_base + kSmemW + ws * kWStageBytes, src + rank * kWStageBytes, kWStageBytes, bar(kBarWFull + ws));
+          if (kIsBwd) src = body_images + (int64_t)i * kWImageBytes;
+          else src = i < 32 ? head_images + (int64_t)i * kWImageBytes : body_images + (int64_t)(i - 32) * kWImageBytes;
+          if constexpr (HALF) {
+            // my rows of the image = output features of K chunks rank and rank + 2 of the next layer: with the 2x2
+            // accumulator layout the leader's rows land in TMEM lanes 0..63 and the peer's in lanes 64..127, so either
+            // lane half ends up holding one EARLY (0 / 1) and one LATE (2 / 3) chunk of the next layer's operand, and the
+            // chunks become ready in the order the GEMM takes them - the same order as in the other forms
+            const uint32_t dst = smem_base + kSmemW + ws * kWStageBytes;
+            bulk_g2s(dst, src + rank * 8192u, 8192u, bar(kBarWFull + ws));
+            bulk_g2s(dst + 8192u, src + 16384u + rank * 8192u, 8192u, bar(kBarWFull + ws));
+          } else {
+            bulk_g2s(smem_base + kSmemW + ws * kWStageBytes, src + rank * kWStageBytes, kWStageBytes, bar(kBarWFull + ws));
+          }
         }
       }
       if (p.stats) p.stats[blockIdx.x * 8 + 3] = t_wait;
@@ -249,9 +250,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
     // ======================= MMA issuer, half form (leader CTA) =======================
     // At 64 cycles per MMA the ~100-cycle latency of a barrier probe would dominate a thread that waits for one barrier
     // after the other.  So the whole warp probes: lane i < 16 watches the operand barrier of (slot i / 4, k-step i % 4),
-    // lanes 16..23 my weight stages, lanes 24..31 the peer's; one ballot tells lane 0 everything that has become ready,
-    // and lane 0 issues in a FIXED order (deterministic accumulation order) that follows the order of production:
-    // chunks 0 and 2 (first chunk of either feature half) k-step by k-step, their W_lo products, then chunks 1 and 3.
+    // lanes 16..23 my weight stages, lanes 24..31 the peer's; one ballot tells the warp everything that has become ready.
+    // The issue ORDER is fixed and the same as in the other forms (chunk 0 k-step by k-step: A_hi W_hi, A_lo W_hi; then
+    // A_hi W_lo; chunks 1..3: 4 x A_hi W_hi, 4 x A_lo W_hi, 4 x A_hi W_lo), so all forms accumulate in the same order
+    // and give bit-identical results.
     static_assert(!HALF || kNumWStages == 8, "one group of four K chunks = one turn of the weight ring");
     constexpr uint32_t idesc = umma_idesc_bf16(128, 256, 0, 0);
     uint32_t group = 0;        // groups of four K chunks (= 8 weight images = 16 operand units) issued so far
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
         if (++spins > R2L_SPIN_LIMIT) __trap();
         if (p.stats) { (waits_a ? t_a : t_w) += clock64() - t0; ++n_probe; }
       }
-      __syncwarp();   // orders lane 0 behind the acquire of whichever lane saw the phase complete
+      __syncwarp();   // orders the issuing lane behind the acquire of whichever lane saw the phase complete
     };
     const long long t_begin = p.stats ? clock64() : 0;
     for (int pt = pair_id; pt < num_ptiles; pt += num_pairs) {
@@ -280,49 +282,37 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
         const bool tr = p.trace != nullptr && pt == pair_id;
         for (int g = 0; g < (head ? kSamples / 4 : 1); ++g, ++group) {
           ready = 0;
-          bool first = fresh && g == 0;    // the very first MMA of the layer overwrites the accumulator
 #pragma unroll
-          for (int pr = 0; pr < 2; ++pr) {           // chunk pairs (0, 2) and (1, 3); stage of W_hi(c) / W_lo(c) below
+          for (uint32_t c = 0; c < 4; ++c) {   // slot; stage 2c holds W_hi, stage 2c + 1 W_lo of this K chunk
+            const uint32_t a_hi = smem_base + kSmemA + c * kSlotBytes, a_lo = a_hi + kPlane;
+            const uint32_t b_hi = smem_base + kSmemW + (2 * c) * kWStageBytes, b_lo = b_hi + kWStageBytes;
+            const uint32_t w_hi = (1u << (16 + 2 * c)) | (1u << (24 + 2 * c)), w_lo = w_hi << 1;
 #pragma unroll
-            for (int hk = 0; hk < 2; ++hk) {         // k-steps 0,1 then 2,3
-#pragma unroll
-              for (int s2 = 0; s2 < 2; ++s2) {
-                const uint32_t c = pr + 2 * s2;      // slot
-                const uint32_t st_hi = 4 * pr + s2;
-                const uint32_t a_hi = smem_base + kSmemA + c * kSlotBytes, a_lo = a_hi + kPlane;
-                const uint32_t b_hi = smem_base + kSmemW + st_hi * kWStageBytes;
-#pragma unroll
-                for (int k2 = 0; k2 < 2; ++k2) {
-                  const uint32_t ks = 2 * hk + k2;
-                  need((1u << (4 * c + ks)) | (1u << (16 + st_hi)) | (1u << (24 + st_hi)));
-                  // TMEM hazards (the epilogue's tcgen05.ld / st of earlier layers vs this layer's accumulator writes) are
-                  // all behind the first operand barrier of a layer: ONE tcgen05 fence per layer - a fence in front of
-                  // every MMA group drains the tensor pipe each time (measured: 2x the tensor time of a layer)
-                  if (pr == 0 && hk == 0 && s2 == 0 && k2 == 0) tc_fence_after_sync();
-                  if (elect_one_sync()) {
-                    if (tr && pr == 0 && hk == 0 && s2 == 0 && k2 == 0) p.trace[((int64_t)blockIdx.x * 5 + 0) * 96 + l] = clock64();
-                    umma_bf16_pair(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b_hi + 32 * ks, 16, 1024), idesc, first ? 0u : 1u);
-                    umma_bf16_pair(d, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw128(b_hi + 32 * ks, 16, 1024), idesc, 1u);
-                  }
-                  first = false;
-                }
-                if (hk == 1 && elect_one_sync()) umma_commit_pair(bar(kBarWEmpty + st_hi));   // W_hi(c) has been read
+            for (uint32_t ks = 0; ks < 4; ++ks) {
+              need((1u << (4 * c + ks)) | w_hi);
+              // TMEM hazards (the epilogue's tcgen05.ld / st of earlier layers vs this layer's accumulator writes) are
+              // all behind the first operand barrier of a layer: one tcgen05 fence per group is enough
+              if (c == 0 && ks == 0) tc_fence_after_sync();
+              if (elect_one_sync()) {
+                if (tr && g == 0 && c == 0 && ks == 0) p.trace[((int64_t)blockIdx.x * 5 + 0) * 96 + l] = clock64();
+                umma_bf16_pair(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b_hi + 32 * ks, 16, 1024), idesc,
+                               (fresh && g == 0 && c == 0 && ks == 0) ? 0u : 1u);
+                if (c == 0) umma_bf16_pair(d, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw128(b_hi + 32 * ks, 16, 1024), idesc, 1u);
               }
             }
+            need(w_lo);   // (probed early: its latency hides behind the MMAs just queued)
+            if (elect_one_sync()) {
+              if (c != 0) {
 #pragma unroll
-            for (int s2 = 0; s2 < 2; ++s2) {
-              const uint32_t c = pr + 2 * s2;
-              const uint32_t st_lo = 4 * pr + 2 + s2;
-              const uint32_t a_hi = smem_base + kSmemA + c * kSlotBytes;
-              const uint32_t b_lo = smem_base + kSmemW + st_lo * kWStageBytes;
-              need((1u << (16 + st_lo)) | (1u << (24 + st_lo)));
-              if (elect_one_sync()) {
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                  umma_bf16_pair(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b_lo + 32 * ks, 16, 1024), idesc, 1u);
-                umma_commit_pair(bar(kBarWEmpty + st_lo));
-                if (head) umma_commit_pair(bar(kBarAEmpty + c));   // the head's A chunks recycle through the 4 slots
+                for (uint32_t ks = 0; ks < 4; ++ks)
+                  umma_bf16_pair(d, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw128(b_hi + 32 * ks, 16, 1024), idesc, 1u);
               }
+              umma_commit_pair(bar(kBarWEmpty + 2 * c));       // W_hi of this chunk has been read
+#pragma unroll
+              for (uint32_t ks = 0; ks < 4; ++ks)
+                umma_bf16_pair(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b_lo + 32 * ks, 16, 1024), idesc, 1u);
+              umma_commit_pair(bar(kBarWEmpty + 2 * c + 1));
+              if (head) umma_commit_pair(bar(kBarAEmpty + c));   // the head's A chunks recycle through the 4 slots
             }
           }
         }
@@ -527,12 +517,14 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
     const uint32_t ew = warp - 4;
     const uint32_t q = ew & 3u;       // TMEM lane quarter (== warp % 4)
     const uint32_t qt = ew >> 2;      // which quarter of a 64-column chunk this thread works on (0..3)
-    // half form (2x2 TMEM layout): lanes 0..63 hold features 0..127 of my 64 rays, lanes 64..127 features 128..255
-    const uint32_t hh = HALF ? (q >> 1) : 0u;                       // which half of the features
+    // half form (2x2 TMEM layout, weight rows split as in the producer): TMEM lanes 64 hh .. 64 hh + 63, hh = q / 2, hold my
+    // 64 rays' output features of K chunks hh (columns 0..63) and hh + 2 (columns 64..127) of the next layer
+    const uint32_t hh = HALF ? (q >> 1) : 0u;
     const uint32_t row = HALF ? (q & 1u) * 32u + lane : q * 32u + lane;   // my ray inside this CTA's rows
-    const uint32_t c_first = 2u * hh;                                // first of the K chunks this thread produces
-    constexpr uint32_t kMyChunks = HALF ? 2 : 4;                     // ... and how many (chunk c <-> TMEM columns 64 (c - c_first) ..)
-    auto mine = [&](uint32_t c) { return !HALF || (c >> 1) == hh; };
+    constexpr uint32_t kMyChunks = HALF ? 2 : 4;                     // K chunks this thread produces: c = hh + 2 cc / c = cc
+    auto my_chunk = [&](uint32_t cc) { return HALF ? hh + 2u * cc : cc; };
+    auto mine = [&](uint32_t c) { return !HALF || (c & 1u) == hh; };
+    auto tmem_col = [&](uint32_t c) { return HALF ? 64u * (c >> 1) : 64u * c; };   // where chunk c's 64 columns start
     const uint32_t tmem_row = tmem_base + ((q * 32u) << 16);
     const float* cumbias = reinterpret_cast<const float*>(p.packed + kPackOffCumBias);
     const float* headb = reinterpret_cast<const float*>(p.packed + kPackOffHeadB);
@@ -540,10 +532,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
     const float* tailw = reinterpret_cast<const float*>(p.packed + kPackOffTailW);
     const float* tailb = reinterpret_cast<const float*>(p.packed + kPackOffTailB);
     float* hrow = p.scratch + ((int64_t)blockIdx.x * kTileM + row) * kWidth;
-    float* tail_part = tail_smem + (row * 8u + hh * 4u + qt) * 3u;   // half form
     uint32_t acc_phase = 0;
     uint32_t saved_phase = 0;   // per-slot parity of kBarASaved
-    (void)cumbias; (void)headb; (void)b1; (void)tailb; (void)tail_smem; (void)tail_part; (void)c_first;
+    (void)cumbias; (void)headb; (void)b1; (void)tailb; (void)tail_smem;
     // Epilogue column ownership inside a 64-column chunk: k-steps g0 = qt>>1 and g0+2, and inside each k-step the
     // 8-column unit u = qt&1, i.e. the 16-byte operand units 2g+u.  K-steps 0/2 belong to the warps with qt in {0,1},
     // k-steps 1/3 to qt in {2,3}: the first 16 columns of a layer's output are ready after 8 warps did 8 columns each.
@@ -619,7 +610,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
         }
         for (int c = 0; c < kSamples; ++c) {
           const uint32_t slot = c & 3;
-          // half form: the eight threads of a ray split the samples by slot (slots 0,1 <-> feature half 0, as in the body)
+          // half form: the eight threads of a ray split the samples by slot parity (as the chunks of the body layers)
           const bool writer = mine(slot);
           float f[16];
           if (!writer) {
@@ -683,8 +674,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(v[i]);
-          tmem_st8(tmem_row + kTmemZ + col - 64u * c_first, &r[0]);
-          tmem_st8(tmem_row + kTmemZ + col - 64u * c_first + 8, &r[8]);
+          tmem_st8(tmem_row + kTmemZ + tmem_col(c) + 16u * qt, &r[0]);
+          tmem_st8(tmem_row + kTmemZ + tmem_col(c) + 16u * qt + 8, &r[8]);
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             reinterpret_cast<float4*>(hrow + col)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -738,7 +729,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
             }
           }
         };
-        load_side(c_first);
+        load_side(my_chunk(0));
         mbar_wait(bar(kBarAccFull), acc_phase);
         acc_phase ^= 1u;
         tc_fence_after_sync();
@@ -747,7 +738,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
         const bool feeds_mma = !last;                     // the last epilogue of a tile produces no further GEMM input
         const bool produces_chunk = feeds_mma || kIsBwd;  // backward's last output (d head pre-activation) is saved for dw
         for (uint32_t cc = 0; cc < kMyChunks; ++cc) {
-          const uint32_t c = c_first + cc;
+          const uint32_t c = my_chunk(cc);
           uint32_t r[16];
           const uint32_t tacc = tmem_row + (from_h ? kTmemH : kTmemZ) + 64u * cc + 8u * uu;
           tmem_ld8(tacc + 16u * g0, &r[0]);
@@ -786,7 +777,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
                 uint32_t w[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) w[i] = __float_as_uint(v[i]);
-                tmem_st8(tmem_row + kTmemZ + col - 64u * c_first, w);
+                tmem_st8(tmem_row + kTmemZ + tmem_col(c) + 16u * g + 8u * uu, w);
                 reinterpret_cast<float4*>(hrow + col)[0] = make_float4(v[0], v[1], v[2], v[3]);
                 reinterpret_cast<float4*>(hrow + col)[1] = make_float4(v[4], v[5], v[6], v[7]);
                 tmem_st_wait();
@@ -851,49 +842,58 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
           } else {
             if (produces_chunk && c > 0) publish(c);
           }
+          if constexpr (!kIsBwd) {
+            if (last) {
+              // park this chunk's partial tail dots (the same 16 columns in every form) where one thread per ray can add
+              // all sixteen in a fixed order: the accumulator region H, idle in the last layer, is shared by the four
+              // threads of a ray; the half form's eight threads per ray sit in two lane halves and use shared memory
+              if constexpr (HALF) {
+                float* tp = tail_smem + ((row * 4u + c) * 4u + qt) * 3u;
+                tp[0] = dot0; tp[1] = dot1; tp[2] = dot2;
+              } else {
+                uint32_t w4[4] = {__float_as_uint(dot0), __float_as_uint(dot1), __float_as_uint(dot2), 0u};
+                tmem_st4(tmem_row + kTmemH + 16u * c + 4u * qt, w4);
+              }
+              dot0 = dot1 = dot2 = 0.f;
+            }
+          }
         }
         if (tr) p.trace[((int64_t)blockIdx.x * 5 + 4) * 96 + l] = clock64();
       }
-      if constexpr (!kIsBwd && HALF) {
-        // combine the eight partial sums of each ray (2 feature halves x 4 column quarters) through shared memory,
-        // fixed summation order
-        tail_part[0] = dot0; tail_part[1] = dot1; tail_part[2] = dot2;
-        named_bar_sync(1, kEpiWarps * 32);
+      if constexpr (!kIsBwd) {
+        // rgb = sigmoid(sum of the 16 partial dots in the order (chunk 0: quarter 0..3), (chunk 1: ...), ... + bias)
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        if constexpr (HALF) {
+          named_bar_sync(1, kEpiWarps * 32);
+          if (hh == 0 && qt == 0) {
+            const float* tp = tail_smem + row * 48u;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { s0 += tp[3 * j]; s1 += tp[3 * j + 1]; s2 += tp[3 * j + 2]; }
+          }
+        } else {
+          tmem_st_wait();
+          tc_fence_before_sync();
+          named_bar_sync(1, kEpiWarps * 32);
+          tc_fence_after_sync();
+          if (qt == 0) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t a[16];
+              tmem_ld16(tmem_row + kTmemH + 16u * c, a);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                s0 += __uint_as_float(a[4 * j]); s1 += __uint_as_float(a[4 * j + 1]); s2 += __uint_as_float(a[4 * j + 2]);
+              }
+            }
+          }
+        }
         if (hh == 0 && qt == 0 && valid) {
-          const float* tp = tail_smem + row * 24u;
-          float s[3];
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            float a = tp[k];
-#pragma unroll
-            for (int j = 1; j < 8; ++j) a += tp[3 * j + k];
-            s[k] = a + __ldg(tailb + k);
-            p.rgb[grow * 3 + k] = 1.f / (1.f + expf(-s[k]));
-          }
+          p.rgb[grow * 3 + 0] = 1.f / (1.f + expf(-(s0 + __ldg(tailb + 0))));
+          p.rgb[grow * 3 + 1] = 1.f / (1.f + expf(-(s1 + __ldg(tailb + 1))));
+          p.rgb[grow * 3 + 2] = 1.f / (1.f + expf(-(s2 + __ldg(tailb + 2))));
         }
-        named_bar_sync(1, kEpiWarps * 32);   // the partials are read before the next tile overwrites them
-      } else if constexpr (!kIsBwd) {
-        // combine the four column-quarter partial sums of each ray through TMEM (the H region is idle here, and the
-        // four threads of a ray share its TMEM lane): fixed summation order, no shared memory needed
-        uint32_t w4[4] = {__float_as_uint(dot0), __float_as_uint(dot1), __float_as_uint(dot2), 0u};
-        tmem_st4(tmem_row + kTmemH + 4u * qt, w4);
-        tmem_st_wait();
-        tc_fence_before_sync();
-        named_bar_sync(1, kEpiWarps * 32);
-        tc_fence_after_sync();
-        if (qt == 0) {
-          uint32_t a[16];
-          tmem_ld16(tmem_row + kTmemH, a);
-          tmem_ld_wait();
-          if (valid) {
-            const float s0 = ((__uint_as_float(a[0]) + __uint_as_float(a[4])) + __uint_as_float(a[8])) + __uint_as_float(a[12]) + __ldg(tailb + 0);
-            const float s1 = ((__uint_as_float(a[1]) + __uint_as_float(a[5])) + __uint_as_float(a[9])) + __uint_as_float(a[13]) + __ldg(tailb + 1);
-            const float s2 = ((__uint_as_float(a[2]) + __uint_as_float(a[6])) + __uint_as_float(a[10])) + __uint_as_float(a[14]) + __ldg(tailb + 2);
-            p.rgb[grow * 3 + 0] = 1.f / (1.f + expf(-s0));
-            p.rgb[grow * 3 + 1] = 1.f / (1.f + expf(-s1));
-            p.rgb[grow * 3 + 2] = 1.f / (1.f + expf(-s2));
-          }
-        }
+        if constexpr (HALF) named_bar_sync(1, kEpiWarps * 32);   // the partials are read before the next tile overwrites them
         tc_fence_before_sync();
       }
     }
