@@ -45,6 +45,15 @@ int r2l_forward(int input_kind, const float* in0, const float* in1, const float*
                 const float* z_diff, const void* packed, float* rgb, void* workspace, size_t workspace_bytes,
                 int64_t n_rays, void* stream);
 
+/* Pose in -> frame out: for every pose c2w[p] (DEVICE [P,3,4] row-major camera-to-world) and pixel
+ * (row j, column i) of a height x width frame, the ray PointSampler.__init__/sample_test builds (nerf_raybased.py:80-86,
+ * :94-102: dirs = [(i - W/2)/f, -(j - H/2)/f, -1], rays_d = sum_k dirs_k c2w[:, k], rays_o = c2w[:, 3]) goes through the
+ * fused forward; nothing but the poses is read and nothing but the image is written (the reference materialises dirs,
+ * pts [H W,48] and the encoding [H W,1008] per frame, main.py:300-309).  z_vals: HOST pointer to the 16 depths.
+ *   rgb  : [P,H,W,3] fp32 or NULL;  rgb8 : [P,H,W,3] uint8 = to8b(rgb) (nerf_raybased.py:16, main.py:338) or NULL. */
+int r2l_render_poses(const float* c2w, int64_t n_poses, int height, int width, float focal, const float* z_vals,
+                     const void* packed, float* rgb, uint8_t* rgb8, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- training: fused forward that keeps what the backward needs, and the fused backward ----
  * Replaces loss.backward() through NeRF_v3_2 (main.py:1404; autograd of nerf_raybased.py:539-544).
  *   zf        : [N,256] fp32 out, z_43 + h (input of the tail Linear)

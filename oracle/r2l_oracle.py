@@ -86,6 +86,21 @@ def sample_test(dirs: np.ndarray, c2w: np.ndarray, z_vals: np.ndarray) -> np.nda
     return pts.reshape(pts.shape[0], -1)
 
 
+def to8b(x: np.ndarray) -> np.ndarray:
+    """:16 — (255 * clip(x, 0, 1)).astype(uint8): the product is rounded in x's dtype, the cast truncates."""
+    return (255 * np.clip(x, 0, 1)).astype(np.uint8)
+
+
+def render_poses(flat: np.ndarray, c2w: np.ndarray, H: int, W: int, focal: float, near: float, far: float):
+    """The per-frame body of render_path for the R2L network (main.py:300-309 sample_test -> positional_embedder ->
+    model; :322-324 view as [H,W,3]; :338 to8b) for poses c2w[P,3,4] -> (rgb[P,H,W,3], rgb8[P,H,W,3])."""
+    dt = flat.dtype.type
+    dirs, z = sampler_dirs(H, W, focal, dt), sampler_z_vals(near, far, N_SAMPLES, dt)
+    frames = [r2l_forward(flat, positional_embed(sample_test(dirs, m.astype(dt), z))).reshape(H, W, 3) for m in c2w]
+    rgb = np.stack(frames)
+    return rgb, to8b(rgb)
+
+
 def sample_train(rays_o: np.ndarray, rays_d: np.ndarray, z_vals: np.ndarray, t_rand: np.ndarray | None) -> np.ndarray:
     """:114-126 — t_rand None == perturb 0; otherwise the stratified jitter with the supplied uniforms."""
     z = np.broadcast_to(z_vals[None, :], (rays_o.shape[0], z_vals.shape[0]))

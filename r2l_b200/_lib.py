@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes
 import os
 import subprocess
-from ctypes import c_char_p, c_double, c_int, c_int64, c_size_t, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
@@ -25,6 +25,8 @@ _PROTOTYPES = {
     "r2l_pack_weights": (c_int, [c_void_p, c_void_p, c_void_p]),
     "r2l_forward": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                             c_void_p, c_size_t, c_int64, c_void_p]),
+    "r2l_render_poses": (c_int, [c_void_p, c_int64, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_size_t, c_void_p]),
     "r2l_bwd_workspace_bytes": (c_size_t, [c_int64]),
     "r2l_train_fwd_saved_bytes": (c_size_t, [c_int64]),
     "r2l_train_bwd_saved_bytes": (c_size_t, [c_int64]),

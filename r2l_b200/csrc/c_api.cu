@@ -144,6 +144,34 @@ int r2l_forward(int input_kind, const float* in0, const float* in1, const float*
   return check(launch_chain_any(r2l::kFwdInfer, p, fwd_grid(n_rays, r2l::kFwdInfer), (cudaStream_t)stream), "r2l_forward");
 }
 
+int r2l_render_poses(const float* c2w, int64_t n_poses, int height, int width, float focal, const float* z_vals,
+                     const void* packed, float* rgb, uint8_t* rgb8, void* workspace, size_t workspace_bytes, void* stream) {
+  if (n_poses == 0) return 0;
+  if (n_poses < 0 || height <= 0 || width <= 0) return fail("r2l_render_poses: %s", "bad frame geometry");
+  if (!(focal > 0.f)) return fail("r2l_render_poses: %s", "focal must be positive");
+  const int64_t n_rays = n_poses * (int64_t)height * width;
+  if (!c2w || !z_vals || !packed || !workspace || (!rgb && !rgb8)) return fail("r2l_render_poses: %s", "null pointer");
+  if (workspace_bytes < r2l_fwd_workspace_bytes(n_rays)) return fail("r2l_render_poses: %s", "workspace too small");
+  if (misaligned(packed) || misaligned(workspace)) return fail("r2l_render_poses: %s", "packed/workspace must be 16-byte aligned");
+  r2l::ChainParams p;
+  memset(&p, 0, sizeof(p));
+  p.in0 = c2w;
+  for (int i = 0; i < r2l::kSamples; ++i) p.z_lo[i] = z_vals[i];
+  p.input_kind = r2l::kInputPose;
+  p.img_h = height;
+  p.img_w = width;
+  p.focal = focal;
+  p.packed = static_cast<const uint8_t*>(packed);
+  p.rgb = rgb;
+  p.rgb8 = rgb8;
+  p.scratch = static_cast<float*>(workspace);
+  p.n_rays = n_rays;
+  p.num_tiles = num_tiles(n_rays);
+  p.stats = g_stats;
+  p.trace = g_trace;
+  return check(launch_chain_any(r2l::kFwdInfer, p, fwd_grid(n_rays, r2l::kFwdInfer), (cudaStream_t)stream), "r2l_render_poses");
+}
+
 size_t r2l_bwd_workspace_bytes(int64_t n_rays) { return r2l_fwd_workspace_bytes(n_rays) + kDwPartialBytes; }
 
 size_t r2l_train_fwd_saved_bytes(int64_t n_rays) {

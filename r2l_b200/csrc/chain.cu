@@ -607,6 +607,21 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
             o[c] = __ldg(p.in0 + grow * 3 + c);
             dd[c] = __ldg(p.in1 + grow * 3 + c);
           }
+        } else if (p.input_kind == kInputPose && valid) {
+          // PointSampler.__init__ / sample_test (nerf_raybased.py:80-86, :94-99): dirs = [(i - W/2)/f, -(j - H/2)/f, -1],
+          // rays_d[r] = sum_k dirs[k] c2w[r][k] (summed left to right), rays_o = c2w[:, 3]
+          const int64_t frame = (int64_t)p.img_h * p.img_w;
+          const int64_t pose = grow / frame;
+          const int pix = (int)(grow - pose * frame);
+          const int pj = pix / p.img_w, pi = pix - pj * p.img_w;
+          const float* m = p.in0 + pose * 12;
+          const float dx = __fdiv_rn(__fsub_rn((float)pi, (float)p.img_w * .5f), p.focal);
+          const float dy = -__fdiv_rn(__fsub_rn((float)pj, (float)p.img_h * .5f), p.focal);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            dd[c] = __fadd_rn(__fadd_rn(__fmul_rn(dx, __ldg(m + 4 * c)), __fmul_rn(dy, __ldg(m + 4 * c + 1))), -__ldg(m + 4 * c + 2));
+            o[c] = __ldg(m + 4 * c + 3);
+          }
         }
         for (int c = 0; c < kSamples; ++c) {
           const uint32_t slot = c & 3;
@@ -889,9 +904,19 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
           }
         }
         if (hh == 0 && qt == 0 && valid) {
-          p.rgb[grow * 3 + 0] = 1.f / (1.f + expf(-(s0 + __ldg(tailb + 0))));
-          p.rgb[grow * 3 + 1] = 1.f / (1.f + expf(-(s1 + __ldg(tailb + 1))));
-          p.rgb[grow * 3 + 2] = 1.f / (1.f + expf(-(s2 + __ldg(tailb + 2))));
+          const float y0 = 1.f / (1.f + expf(-(s0 + __ldg(tailb + 0))));
+          const float y1 = 1.f / (1.f + expf(-(s1 + __ldg(tailb + 1))));
+          const float y2 = 1.f / (1.f + expf(-(s2 + __ldg(tailb + 2))));
+          if (p.rgb != nullptr) {
+            p.rgb[grow * 3 + 0] = y0;
+            p.rgb[grow * 3 + 1] = y1;
+            p.rgb[grow * 3 + 2] = y2;
+          }
+          if (p.rgb8 != nullptr) {   // to8b (nerf_raybased.py:16): (255 * clip(x, 0, 1)).astype(uint8), i.e. truncation
+            p.rgb8[grow * 3 + 0] = (uint8_t)__fmul_rn(255.f, fminf(fmaxf(y0, 0.f), 1.f));
+            p.rgb8[grow * 3 + 1] = (uint8_t)__fmul_rn(255.f, fminf(fmaxf(y1, 0.f), 1.f));
+            p.rgb8[grow * 3 + 2] = (uint8_t)__fmul_rn(255.f, fminf(fmaxf(y2, 0.f), 1.f));
+          }
         }
         if constexpr (HALF) named_bar_sync(1, kEpiWarps * 32);   // the partials are read before the next tile overwrites them
         tc_fence_before_sync();

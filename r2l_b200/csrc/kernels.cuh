@@ -11,13 +11,16 @@ enum ChainMode : int { kFwdInfer = 0, kFwdTrain = 1, kBwd = 2 };
 
 struct ChainParams {
   // forward inputs
-  const float* in0;       // rays_o[N,3] | pts[N,48] | x[N,1008]
+  const float* in0;       // rays_o[N,3] | pts[N,48] | x[N,1008] | c2w[P,3,4]
   const float* in1;       // rays_d[N,3] | unused
   const float* t_rand;    // [N,16] or nullptr (kInputRays only)
   float z_lo[kSamples];   // z_vals (no jitter) or `lower` (jitter)
   float z_diff[kSamples]; // `upper - lower` (jitter)
   const uint8_t* packed;
-  float* rgb;             // forward out [N,3]
+  float* rgb;             // forward out [N,3] (may be nullptr when rgb8 is given)
+  uint8_t* rgb8;          // optional forward out [N,3] uint8 = to8b(rgb) (nerf_raybased.py:16); nullptr = off
+  int img_h, img_w;       // kInputPose: frame size; pixel (i = column, j = row) of ray r is r % (H W)
+  float focal;            // kInputPose: focal length in pixels
   float* scratch;         // [gridDim.x][128][256] fp32: head output (fwd) / dL/dz_43 (bwd) for the outer skip
   long long* stats;       // optional [gridDim.x][8] cycle counters (debug), nullptr in production
   long long* trace;       // optional [gridDim.x][5][96] clock64 stamps of the first tile's layers (debug)

@@ -330,6 +330,23 @@ class NeRF_v3_2(nn.Module):
         lower, diff = point_sampler.jitter_bounds()
         return self._run(rays_o=rays_o, rays_d=rays_d, t_rand=t_rand, z_lower=lower.tolist(), z_diff=diff.tolist())
 
+    @torch.no_grad()
+    def render_poses(self, c2w, point_sampler, focal, as_uint8=False):
+        """Fused `model(positional_embedder(point_sampler.sample_test(c2w)))` for one pose [3,4] or a batch [P,3,4]
+        (the per-frame body of render_path, main.py:300-309,:322-324): pose in, frame [P,H,W,3] out.  `focal` is the
+        value the sampler was built with (it keeps only the derived directions).  as_uint8 = to8b of the frame
+        (main.py:338), converted in the kernel's last step."""
+        if not self.flat.is_cuda:
+            raise RuntimeError("r2l_b200 NeRF_v3_2 runs on CUDA only: move the model with .to('cuda') (no CPU fallback)")
+        if point_sampler.z_vals.numel() != N_SAMPLES:
+            raise NotImplementedError("r2l_b200 NeRF_v3_2: unsupported configuration (--n_sample_per_ray 16)")
+        single = c2w.dim() == 2
+        rgb, rgb8 = ops.render_poses(self.packed_weights(), c2w.to(self.flat.device, torch.float32), point_sampler.H,
+                                     point_sampler.W, focal, point_sampler.z_vals.tolist(), want_rgb=not as_uint8,
+                                     want_rgb8=as_uint8)
+        out = rgb8 if as_uint8 else rgb
+        return out[0] if single else out
+
     def _run(self, **inputs):
         if not self.flat.is_cuda:
             raise RuntimeError("r2l_b200 NeRF_v3_2 runs on CUDA only: move the model with .to('cuda') (no CPU fallback)")

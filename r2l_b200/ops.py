@@ -104,6 +104,36 @@ def forward(packed: torch.Tensor, *, rays_o=None, rays_d=None, z_vals=None, t_ra
     return out
 
 
+def render_poses(packed: torch.Tensor, c2w: torch.Tensor, height: int, width: int, focal: float, z_vals,
+                 want_rgb: bool = True, want_rgb8: bool = False):
+    """Frames for camera poses c2w[P,3,4] (or [3,4]): rays are generated in-kernel (PointSampler.sample_test).
+    Returns (rgb[P,H,W,3] float32 or None, rgb8[P,H,W,3] uint8 = to8b(rgb) or None)."""
+    c2w = _require_cuda_f32(c2w, "c2w")
+    if c2w.dim() == 2:
+        c2w = c2w[None]
+    if c2w.dim() != 3 or c2w.shape[1] < 3 or c2w.shape[2] != 4:
+        raise ValueError(f"c2w: expected [P,3,4] (or [P,4,4]), got {tuple(c2w.shape)}")
+    c2w = c2w[:, :3, :].contiguous()
+    if not (want_rgb or want_rgb8):
+        raise ValueError("render_poses: nothing to compute (want_rgb and want_rgb8 both False)")
+    height, width = int(height), int(width)
+    if height <= 0 or width <= 0 or not float(focal) > 0:
+        raise ValueError("render_poses: height, width and focal must be positive")
+    n_poses, dev = c2w.shape[0], c2w.device
+    if packed.device != dev:
+        raise RuntimeError("packed weights live on a different device")
+    rgb = torch.empty((n_poses, height, width, 3), dtype=torch.float32, device=dev) if want_rgb else None
+    rgb8 = torch.empty((n_poses, height, width, 3), dtype=torch.uint8, device=dev) if want_rgb8 else None
+    zl = (ctypes.c_float * N_SAMPLES)(*[float(v) for v in z_vals])
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        wbytes = int(L.r2l_fwd_workspace_bytes(n_poses * height * width))
+        ws = _workspace(dev, wbytes)
+        _lib.check(L.r2l_render_poses(_ptr(c2w), n_poses, height, width, float(focal), zl, _ptr(packed), _ptr(rgb), _ptr(rgb8),
+                                      _ptr(ws), wbytes, _stream()), "r2l_render_poses")
+    return rgb, rgb8
+
+
 def selftest_layer(a: torch.Tensor, packed: torch.Tensor, layer: int) -> torch.Tensor:
     a = _require_cuda_f32(a, "a", (256,))
     c = torch.empty_like(a)

@@ -25,6 +25,11 @@ def golden_teacher():
 
 
 @pytest.fixture(scope="session")
+def golden_pose():
+    return dict(np.load(os.path.join(GOLDEN, "pose_seed0.npz"), allow_pickle=False))
+
+
+@pytest.fixture(scope="session")
 def flat_seed0():
     """Seed-0 weights; bit-identical to the reference's (asserted when the fixtures were generated and
     re-checked against the stored per-tensor checksums in test_oracle.py)."""

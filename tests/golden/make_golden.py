@@ -215,5 +215,38 @@ def main():
     print("teacher_seed0.npz written; raw range", float(raw.min()), float(raw.max()))
 
 
+def make_pose():
+    """pose_seed0.npz: the per-frame body of render_path (main.py:300-309,:322-324,:338) on two poses of a small
+    non-square frame: PointSampler.sample_test -> PositionalEmbedder -> NeRF_v3_2 (seed 0) -> to8b."""
+    ref, _ = import_reference()
+    ref.device = torch.device("cpu")
+    torch.set_num_threads(8)
+    torch.manual_seed(0)
+    emb = ref.PositionalEmbedder(L=10)
+    model = ref.NeRF_v3_2(ref_args(), 16 * 3 * emb.embed_dim, 3)
+    H, W, focal = 18, 20, 27.77777577984421   # the lego focal scaled to a 20-pixel-wide frame
+    sampler = ref.PointSampler(H, W, focal, 16, 2.0, 6.0)
+    rng = np.random.RandomState(5)
+    poses = np.stack([pose_spherical_np(rng.uniform(-180, 180), rng.uniform(-90, 0), 4.0)[:3, :4] for _ in range(2)])
+    out = dict(H=np.int64(H), W=np.int64(W), focal=np.float64(focal), c2w=poses, z_vals=sampler.z_vals.numpy(),
+               dirs=sampler.dirs.numpy())
+    frames, frames8, pts_all = [], [], []
+    for c2w in poses:
+        pts = sampler.sample_test(torch.from_numpy(c2w))
+        with torch.no_grad():
+            rgb = model(emb(pts))
+        rgb = rgb.view(H, W, 3)
+        pts_all.append(pts.numpy())
+        frames.append(rgb.numpy())
+        frames8.append(ref.to8b(rgb))
+    out.update(pts=np.stack(pts_all), rgb=np.stack(frames), rgb8=np.stack(frames8))
+    np.savez_compressed(os.path.join(HERE, "pose_seed0.npz"), **out)
+    print("pose_seed0.npz written:", out["rgb"].shape, out["rgb8"].dtype, out["rgb8"].reshape(-1, 3)[:3])
+
+
 if __name__ == "__main__":
-    main()
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "main"):
+        main()
+    if which in ("all", "pose"):
+        make_pose()

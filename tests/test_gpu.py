@@ -68,6 +68,58 @@ def test_forward_ragged_sizes_vs_oracle(n, flat_seed0, packed):
     assert np.isfinite(rgb).all() and relerr(rgb[-m:], ref) < FWD_TOL
 
 
+def test_render_poses_golden(golden_pose, packed, flat_seed0):
+    """Row N4: poses in, frames out (rays generated in-kernel) against the reference's frames and the oracle."""
+    g = golden_pose
+    H, W, focal = int(g["H"]), int(g["W"]), float(g["focal"])
+    c2w = torch.from_numpy(g["c2w"]).to(DEV)
+    rgb, rgb8 = ops.render_poses(packed, c2w, H, W, focal, g["z_vals"].tolist(), want_rgb=True, want_rgb8=True)
+    assert rgb.shape == (2, H, W, 3) and rgb8.shape == (2, H, W, 3) and rgb8.dtype == torch.uint8
+    assert relerr(rgb.cpu().numpy(), g["rgb"]) < FWD_TOL
+    orgb, _ = orc.render_poses(flat_seed0, g["c2w"], H, W, focal, 2.0, 6.0)
+    assert relerr(rgb.cpu().numpy(), orgb) < FWD_TOL
+    # the uint8 frame is to8b of the float frame of the same launch, bit for bit; against the reference's uint8 frame a
+    # value within the 1e-3 tolerance of an integer boundary may differ by one level
+    assert np.array_equal(rgb8.cpu().numpy(), orc.to8b(rgb.cpu().numpy()))
+    assert np.abs(rgb8.cpu().numpy().astype(int) - g["rgb8"].astype(int)).max() <= 1
+    # identical to the unfused route through the host sampler (same rays, same arithmetic): pts -> forward
+    nb.device = torch.device(DEV)
+    ps = nb.PointSampler(H, W, focal, 16, 2.0, 6.0)
+    for k in range(2):
+        via_pts = ops.forward(packed, pts=ps.sample_test(c2w[k]).contiguous())
+        assert relerr(rgb[k].reshape(-1, 3).cpu().numpy(), via_pts.cpu().numpy()) < 2e-5
+    # only one output requested; a single [3,4] pose; a [4,4] pose
+    only8 = ops.render_poses(packed, c2w[0], H, W, focal, g["z_vals"].tolist(), want_rgb=False, want_rgb8=True)
+    assert only8[0] is None and torch.equal(only8[1][0], rgb8[0])
+    c44 = torch.cat([c2w[1], torch.tensor([[0., 0., 0., 1.]], device=DEV)], 0)
+    assert torch.equal(ops.render_poses(packed, c44[None], H, W, focal, g["z_vals"].tolist())[0][0], rgb[1])
+
+
+def test_render_poses_module_surface_and_full_frame(packed, flat_seed0):
+    """NeRF_v3_2.render_poses on the BASELINE config-2 frame size (400x400 = 160,000 rays per pose, 2 poses): every
+    pixel equals the three-step reference idiom (sample_test -> positional_embedder -> model) run through the same
+    library, and a pose's frame does not depend on which other poses share the launch."""
+    nb.device = torch.device(DEV)
+    model = nb.NeRF_v3_2(nb.readme_args(), 1008, 3).to(DEV)
+    with torch.no_grad():
+        model.flat.copy_(torch.from_numpy(flat_seed0).to(DEV))
+    focal = 555.5555155968841
+    ps = nb.PointSampler(400, 400, focal, 16, 2.0, 6.0)
+    emb = nb.PositionalEmbedder(10)
+    poses = torch.tensor([[[-0.9, 0.2, -0.3, -1.3], [-0.4, -0.5, 0.7, 3.0], [0.0, 0.8, 0.5, 2.2]],
+                          [[0.6, -0.3, 0.7, 2.9], [0.8, 0.2, -0.5, -2.2], [0.0, 0.9, 0.4, 1.6]]], device=DEV)
+    frames = model.render_poses(poses, ps, focal)
+    assert frames.shape == (2, 400, 400, 3) and bool(torch.isfinite(frames).all())
+    with torch.no_grad():
+        for k in range(2):
+            ref = model(emb(ps.sample_test(poses[k]))).view(400, 400, 3)
+            assert float(((frames[k] - ref).abs() / ref).max()) < 2e-5
+    one = model.render_poses(poses[1], ps, focal)
+    assert torch.equal(one, frames[1])
+    u8 = model.render_poses(poses, ps, focal, as_uint8=True)
+    assert u8.dtype == torch.uint8 and np.array_equal(u8.cpu().numpy(), orc.to8b(frames.cpu().numpy()))
+
+
 def test_forward_empty_batch(packed):
     out = ops.forward(packed, rays_o=torch.zeros(0, 3, device=DEV), rays_d=torch.zeros(0, 3, device=DEV), z_vals=[0.] * 16)
     assert out.shape == (0, 3)

@@ -91,4 +91,5 @@ def test_point_sampler_and_embedder_match_golden(golden_r2l):
     assert np.array_equal((ro[:, None, :] + rd[:, None, :] * z[:, :, None]).reshape(200, -1).numpy(), g["pts_jit"])
     emb = nb.PositionalEmbedder(L=10)
     assert emb.embed_dim == 21
-    assert np.array_equal(emb(torch.from_numpy(g["pts"])).numpy(), g["x_embed"])
+    # sin/cos: ATen's vectorised and scalar paths differ in the last bit depending on how the array is split over threads
+    np.testing.assert_allclose(emb(torch.from_numpy(g["pts"])).numpy(), g["x_embed"], rtol=0, atol=5e-7)

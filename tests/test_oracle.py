@@ -31,6 +31,25 @@ def test_point_sampler(golden_r2l):
     np.testing.assert_allclose(pts_test[g["pix"]], g["pts_test_pix"], rtol=0, atol=2e-6)
 
 
+def test_render_poses_against_reference_frames(golden_pose, flat_seed0):
+    """sample_test -> embed -> network -> to8b on two poses of an 18x20 frame (reference outputs: pose_seed0.npz)."""
+    g = golden_pose
+    H, W, focal = int(g["H"]), int(g["W"]), float(g["focal"])
+    dirs = orc.sampler_dirs(H, W, focal)
+    assert np.array_equal(dirs, g["dirs"])
+    assert np.array_equal(orc.sampler_z_vals(2.0, 6.0), g["z_vals"])
+    for k in range(2):
+        np.testing.assert_allclose(orc.sample_test(dirs, g["c2w"][k], g["z_vals"]), g["pts"][k], rtol=0, atol=2e-6)
+    rgb, rgb8 = orc.render_poses(flat_seed0, g["c2w"], H, W, focal, 2.0, 6.0)
+    assert rgb.shape == (2, H, W, 3) and rgb8.dtype == np.uint8
+    assert rel(rgb, g["rgb"]) < 2e-5
+    # to8b truncates: a 1e-5 difference can flip a value sitting on an integer boundary by one level, never more
+    assert np.abs(rgb8.astype(int) - g["rgb8"].astype(int)).max() <= 1
+    assert (rgb8 != g["rgb8"]).mean() < 0.01
+    assert np.array_equal(orc.to8b(g["rgb"]), g["rgb8"])
+    assert np.array_equal(orc.to8b(np.array([-0.5, 0.0, 0.5, 0.999, 1.0, 7.0], np.float32)), np.array([0, 0, 127, 254, 255, 255], np.uint8))
+
+
 def test_positional_embed(golden_r2l):
     x = orc.positional_embed(golden_r2l["pts"])
     assert x.shape == (200, 1008)
