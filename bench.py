@@ -67,33 +67,70 @@ def synthetic_rays(n, seed):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md "clocks" line), read through NVML every
+    2 ms (a 20-step timed region is only ~20 ms long: one nvidia-smi process per sample would see it once at best);
+    falls back to polling nvidia-smi when NVML cannot be opened.  Samples taken while `active` is set are the ones
+    summarised as "under load"."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.stop_flag, self.active = index, [], False, False
+        self.max_mhz, self.source = None, "nvml"
+
+    def _open_nvml(self):
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        return pynvml, h
 
     def run(self):
+        try:
+            nv, h = self._open_nvml()
+        except Exception:
+            return self._run_smi()
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.samples.append((self.active, float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(reasons_fn(h))))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _run_smi(self):
+        self.source = "nvidia-smi"
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        bits = [0x8, 0x40, 0x20, 0x4]
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([s.strip() for s in out.split(",")])
+                f = [x.strip() for x in out.split(",")]
+                if len(f) >= 6:
+                    self.max_mhz = float(f[1])
+                    mask = sum(b for b, v in zip(bits, f[2:6]) if v.lower().startswith("active"))
+                    self.samples.append((self.active, float(f[0]), mask))
             except Exception:
                 pass
             time.sleep(0.05)
 
     def summary(self):
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         import statistics
-        mhz = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": statistics.median(mhz) if mhz else None, "sm_max_mhz": float(self.samples[0][1]),
-                "reasons": reasons, "samples": len(self.samples)}
+        load = [s for s in self.samples if s[0]] or self.samples
+        if not load:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"], "source": self.source}
+        mask = 0
+        for s in load:
+            mask |= s[2]
+        return {"sm_mhz": statistics.median(s[1] for s in load), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(n for b, n in self.REASONS.items() if mask & b), "samples": len(load), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -227,15 +264,15 @@ def run_ours(args):
     barrier()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    sampler.active = True
     for a, b in evs:
         flush.fill_(1)          # evict L2 between timed iterations (not timed)
         a.record()
         step_device()
         b.record()
     barrier()
+    sampler.active = False
     total_ms = sum(a.elapsed_time(b) for a, b in evs)
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
     t = torch.tensor([total_ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -259,10 +296,10 @@ def run_ours(args):
         del ctx
     k_ms /= reps
     achieved_tflops = BATCH * FWD_FLOP_PER_RAY / (k_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "r2l_chain_kernel<kFwdTrain, PAIR> (4096 rays, 16 CTA pairs, cta_group::2)", "achieved": achieved_tflops,
+    roofline = {"bound": "tensor", "kernel": "r2l_chain_kernel<kFwdTrain, half form> (4096 rays = 32 tiles, one CTA pair per tile: 64 CTAs, tcgen05 cta_group::2 M=128)", "achieved": achieved_tflops,
                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved_tflops / peaks["bf16_tflops"],
                 "traffic": 358.7e6, "traffic_source": "profiles/r1_summary.md: dram read+write of the forward train kernel at 4096 rays (ncu --set full)", "peak_source": peaks["source"], "kernel_ms": k_ms,
-                "note": "algorithmic fp32 FLOPs; the kernel issues 3x that as bf16 MMAs (hi*hi+lo*hi+hi*lo) to meet the 1e-3 fp32 parity bar, and a 4096-ray batch fills 32 of 148 SMs"}
+                "note": "algorithmic fp32 FLOPs; the kernel issues 3x that as bf16 MMAs (hi*hi+lo*hi+hi*lo) to meet the 1e-3 fp32 parity bar, and a 4096-ray batch (32 tiles of 128 rays, two SMs per tile) occupies 64 of 148 SMs"}
 
     # ---- the same kernel with every SM busy (148 tiles = 18,944 rays), inference form: kernel quality, not the metric ----
     n_full = 148 * 128
@@ -319,6 +356,8 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = n_global * args.steps / float(t.item())
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
 
     line = None
     if rank == 0:

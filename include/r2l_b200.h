@@ -117,10 +117,17 @@ int r2l_debug_set_stats(long long* stats);
 
 /* Launch form of the chain kernels (r2l_b200/csrc/chain.cu): 0 = single CTA per 128-ray tile, 1 = CTA pair (tcgen05
  * cta_group::2, M = 256) with one tile per CTA, 2 = CTA pair sharing one tile (cta_group::2, M = 128, 64 rays per CTA:
- * half the latency per layer, the form for small batches), -1 = default = chosen per call (form 2 for the training
- * kernels and for inference batches that leave SM pairs idle, form 0 otherwise).  All forms issue their MMAs in the same order: results are
- * bit-identical, whichever form a call takes.  Process-wide; buffers sized by the *_bytes queries fit every form. */
+ * 0.69 of the latency per tile, the form for small batches), -1 = default = chosen per call (form 2 while the batch
+ * leaves SM pairs idle, i.e. tiles <= SMs / 2, form 1 otherwise).  All forms issue their MMAs in the same order: results
+ * are bit-identical, whichever form a call takes.  Process-wide; buffers sized by the *_bytes queries fit every form. */
 int r2l_set_pair_mode(int mode);
+
+/* Debug / tuning: schedule of the weight-gradient kernel inside r2l_backward (dw.cu).  Units = the 86 body Linears in
+ * the order the backward chain releases them, then 4 head column groups.  When the kernel overlaps the chain, units
+ * < t1 run whole, < t2 in 2 ray-tile pieces, < t3 in 4, the rest in 8; when it runs after the chain every unit is cut
+ * into serial_pieces.  Negative values (0 for serial_pieces) = built-in defaults.  Results are independent of the schedule
+ * up to fp32 summation order of the pieces. */
+int r2l_debug_set_dw_schedule(int t1, int t2, int t3, int serial_pieces);
 
 /* Debug: device buffer [grid][5][96] of clock64 stamps for the first tile of each CTA of the next chain launches:
  * row 0 MMA thread starts layer l, 1 MMA thread has issued layer l, 2 epilogue sees accumulator l complete,

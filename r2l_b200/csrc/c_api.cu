@@ -48,18 +48,43 @@ SideStream* side_stream() {
   return &s;
 }
 constexpr size_t kReadyBytes = 1024;  // 87 readiness counters + 90 reduction tickets (ints), padded
-constexpr int kDwSplits = 8;          // ray-tile ranges per weight-gradient unit in the concurrent mode
-constexpr size_t kDwPartialBytes = (size_t)90 * kDwSplits * (256 * 256 + 256) * sizeof(float);
+constexpr int kDwUnits = r2l::kBodyLayers + 4;
+constexpr int kDwMaxCtas = 720;       // scratch slots for partial weight gradients (one per CTA of a split unit)
+constexpr size_t kDwPartialBytes = (size_t)kDwMaxCtas * (256 * 256 + 256) * sizeof(float);
+// Schedule of the weight-gradient kernel (dw.cu; see DwParams).  Units are numbered in the order the backward chain
+// releases them.  g_dw_sched: {t1, t2, t3, s_after} for the concurrent mode (units < t1 whole, < t2 in 2 pieces, < t3 in
+// 4, the rest in 8) and the piece count of every unit in the serial mode; negative = built-in default.
+int g_dw_sched[4] = {-1, -1, -1, -1};
+void dw_schedule(r2l::DwParams& d, bool concurrent) {
+  // Concurrent mode.  The chain releases a layer every T/90 of its run time T and a whole unit takes about 0.37 T on one
+  // SM (measured at 4096 rays: T = 0.36 ms, unit = 0.13 ms), so a unit released before ~0.6 T finishes in time without
+  // being cut; later ones are cut so that a piece takes no longer than what is left of the chain, the last ones in 8.
+  const int t1 = g_dw_sched[0] >= 0 ? g_dw_sched[0] : 56, t2 = g_dw_sched[1] >= 0 ? g_dw_sched[1] : 72,
+            t3 = g_dw_sched[2] >= 0 ? g_dw_sched[2] : 80;
+  // Serial mode (large batches, every SM free): 3 pieces per unit = 270 CTAs keep all SMs streaming
+  const int serial = g_dw_sched[3] > 0 ? g_dw_sched[3] : (d.num_tiles >= 96 ? 3 : 1);
+  int first = 0;
+  for (int u = 0; u < kDwUnits; ++u) {
+    int s = concurrent ? (u < t1 ? 1 : u < t2 ? 2 : u < t3 ? 4 : 8) : serial;
+    if (s > 8) s = 8;                              // 90 x 8 = kDwMaxCtas scratch slots
+    while (s > 1 && 2 * s > d.num_tiles) --s;      // at least two ray tiles per piece
+    d.unit_splits[u] = (uint8_t)s;
+    d.unit_first[u] = (uint16_t)first;
+    first += s;
+  }
+  d.num_ctas = first;
+}
 
 int num_tiles(int64_t n_rays) { return (int)((n_rays + r2l::kTileM - 1) / r2l::kTileM); }
-// Which launch form a chain kernel takes.  Two SMs that share a tile (half form) finish it in about half the time, so it
-// wins whenever there are SM pairs to spare, and it keeps the per-layer latency low for the training step; with more
-// tiles than SM pairs every SM has work either way and the forms run at the same rate, so inference on whole images
-// keeps the cluster-free single form.
+// Which launch form a chain kernel takes.  Two SMs that share a tile (half form) finish it in 0.69 of the time (measured,
+// 4096 rays: 0.321 vs 0.467 ms), so it wins whenever there are SM pairs to spare (tiles <= SMs / 2).  With more tiles
+// than SM pairs every SM has work either way and a pair finishing two tiles (pair form) or an SM finishing one (single
+// form) is the better use of it: measured at 160,000 rays 5.31 (half) / 4.25 (pair) / 4.52 ms (single), training kernels
+// at 98,304 rays +15 % in the half form.  Large batches therefore run in the pair form.
 int chain_form(int mode, int64_t n_rays) {
   if (g_form >= 0) return g_form;
-  if (mode != r2l::kFwdInfer) return r2l::kFormHalf;
-  return num_tiles(n_rays) <= sm_count() / 2 ? r2l::kFormHalf : r2l::kFormSingle;
+  (void)mode;
+  return num_tiles(n_rays) <= sm_count() / 2 ? r2l::kFormHalf : r2l::kFormPair;
 }
 int fwd_grid(int64_t n_rays, int mode) {
   const int sms = sm_count();
@@ -244,17 +269,14 @@ int r2l_backward(int input_kind, const void* packed, const float* rgb, const flo
   d.input_kind = input_kind;
   d.accumulate = 0;
   d.ready = nullptr;
-  d.splits = 1;
-  d.partials = nullptr;
-  d.tickets = nullptr;
+  d.partials = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + r2l_fwd_workspace_bytes(n_rays));
+  d.tickets = ready + 128;
   d.times = g_trace ? g_trace + 148 * 5 * 96 : nullptr;   // the dW stamps follow the chain kernel's trace rows
+  dw_schedule(d, side != nullptr);
+  if (int rc = check(cudaMemsetAsync(ready, 0, kReadyBytes, st), "r2l_backward(memset)")) return rc;
   if (side) {
-    if (int rc = check(cudaMemsetAsync(ready, 0, kReadyBytes, st), "r2l_backward(memset)")) return rc;
     p.ready = ready;
     d.ready = ready;
-    d.splits = p.num_tiles >= 2 * kDwSplits ? kDwSplits : 1;
-    d.partials = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + r2l_fwd_workspace_bytes(n_rays));
-    d.tickets = ready + 128;
     if (int rc = check(cudaEventRecord(side->fork, st), "r2l_backward(fork)")) return rc;
     if (int rc = check(cudaStreamWaitEvent(side->stream, side->fork, 0), "r2l_backward(fork wait)")) return rc;
     if (int rc = check(launch_chain_any(r2l::kBwd, p, grid, st), "r2l_backward(chain)")) return rc;
@@ -359,6 +381,11 @@ int r2l_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
 
 int r2l_debug_set_stats(long long* stats) {
   g_stats = stats;
+  return 0;
+}
+
+int r2l_debug_set_dw_schedule(int t1, int t2, int t3, int serial_pieces) {
+  g_dw_sched[0] = t1; g_dw_sched[1] = t2; g_dw_sched[2] = t3; g_dw_sched[3] = serial_pieces;
   return 0;
 }
 

@@ -13,10 +13,12 @@
 //   warp 2     TMEM allocator: two fp32 accumulators [128 x 256] (output rows 0-127 and 128-255) = 512 columns
 //   warps 4-7  bias gradient: column sums of dY straight from the staged smem tiles; then the epilogue
 //              (TMEM -> registers -> global)
-// Split mode (p.splits > 1, used when the kernel overlaps the backward chain on otherwise idle SMs): each unit is cut
-// into `splits` ray-tile ranges so that the pieces finishing after the chain are short; a piece writes its partial
-// dW / db to scratch and the LAST piece of a unit to arrive (atomic ticket) sums the partials in fixed order - the
-// result does not depend on which piece was last.  CTAs are ordered by the time their layer becomes available.
+// Split units (DwParams::unit_splits[u] > 1): a unit is cut into ray-tile ranges, one CTA ("piece") each; a piece writes
+// its partial dW / db to scratch and the LAST piece of the unit to finish (atomic ticket) sums the partials in fixed
+// order - the result does not depend on which piece was last.  CTAs are ordered by the time their layer becomes
+// available.  When the kernel overlaps the backward chain on otherwise idle SMs the host (c_api.cu: dw_schedule) leaves
+// the units that are released early whole - they have the whole chain to finish in and cost no scratch traffic -
+// and cuts the later ones ever finer, so that the pieces still running when the chain ends are short.
 // Autograd equivalent in the reference: the weight/bias gradients torch.autograd produces for every
 // nn.Linear of NeRF_v3_2 (model/nerf_raybased.py:500,:453-456) under loss.backward() (main.py:1404).
 #include "kernels.cuh"
@@ -48,8 +50,9 @@ __global__ void __launch_bounds__(kDwThreads, 1) r2l_dw_kernel(const __grid_cons
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   // CTA order = order in which the backward sweep releases the layers: body layer 85 first ... layer 0, then the head
-  const int splits = p.splits > 1 ? p.splits : 1;
-  const int ob = blockIdx.x / splits, split = blockIdx.x % splits;
+  int ob = 0;
+  while (ob + 1 < kDwUnits && (int)blockIdx.x >= (int)p.unit_first[ob + 1]) ++ob;
+  const int splits = p.unit_splits[ob], split = (int)blockIdx.x - (int)p.unit_first[ob];
   const bool is_head = ob >= kBodyLayers;
   const int layer = kBodyLayers - 1 - ob;  // body layer 0..85 when !is_head
   const int hg = ob - kBodyLayers;         // head feature group 0..3 (256 encoded features each)
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) r2l_dw_kernel(const __grid_cons
     }
     // where the results go: straight into the gradient buffer, or (split mode) into this piece's scratch slot
     constexpr int kUnitFloats = kWidth * kWidth + kWidth;            // dW [256][256] + db [256]
-    float* part = splits > 1 ? p.partials + ((int64_t)ob * splits + split) * kUnitFloats : nullptr;
+    float* part = splits > 1 ? p.partials + (int64_t)blockIdx.x * kUnitFloats : nullptr;
     auto head_feature = [&](int col) {
       const int chunk = 4 * hg + (col >> 6), slot = col & 63;
       return p.input_kind == kInputX ? (64 * chunk + slot < kInDim ? 64 * chunk + slot : -1) : fused_slot_to_feature(chunk, slot);
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) r2l_dw_kernel(const __grid_cons
         const int chunk = 4 * hg + (col >> 6), slot = col & 63;
         return p.input_kind == kInputX ? (64 * chunk + slot < kInDim ? 64 * chunk + slot : -1) : fused_slot_to_feature(chunk, slot);
       };
-      const float* base = p.partials + (int64_t)ob * splits * kUnitFloats;
+      const float* base = p.partials + (int64_t)p.unit_first[ob] * kUnitFloats;
       constexpr int kVecs = kUnitFloats / 4;   // 16448
       constexpr int kU = 8;
       for (int v0 = (int)threadIdx.x; v0 < kVecs; v0 += kU * kDwThreads) {
@@ -314,7 +317,7 @@ __global__ void __launch_bounds__(256) r2l_tail_grad_kernel(const __grid_constan
 cudaError_t launch_dw(const DwParams& p, cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(r2l_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDwSmemBytes);
   if (e != cudaSuccess) return e;
-  r2l_dw_kernel<<<kDwUnits * (p.splits > 1 ? p.splits : 1), kDwThreads, kDwSmemBytes, stream>>>(p);
+  r2l_dw_kernel<<<p.num_ctas, kDwThreads, kDwSmemBytes, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -48,9 +48,14 @@ struct DwParams {
   int num_tiles;
   int input_kind;         // kInputX: head features in natural order, else fused-PE order
   int accumulate;
-  int splits;             // >1: each unit is cut into ray-tile ranges, partial results in `partials`, last piece reduces
-  float* partials;        // [90][splits][256*256 + 256] scratch (split mode)
-  int* tickets;           // [90] zeroed counters (split mode)
+  // schedule: unit u (in release order: body layer 85 .. 0, then the 4 head column groups) is cut into unit_splits[u]
+  // ray-tile ranges, one CTA each, CTAs unit_first[u] .. unit_first[u] + unit_splits[u] - 1.  A piece of a split unit
+  // writes its partial result to partials[CTA index]; the last piece of the unit to finish (ticket) sums them in order.
+  uint8_t unit_splits[kBodyLayers + 4];
+  uint16_t unit_first[kBodyLayers + 4];
+  int num_ctas;
+  float* partials;        // [num_ctas][256*256 + 256] scratch (only slots of split units are used)
+  int* tickets;           // [90] zeroed counters (only needed when some unit is split)
   long long* times;       // optional debug: [unit][4] globaltimer stamps (start, flag seen, MMAs done, end)
   const int* ready;       // optional: wait until ready[group of this unit] == ready_target before streaming (see ChainParams)
   int ready_target;       // store warps that announce each group: num_tiles (x 2 when the chain ran in its half form)

@@ -1,0 +1,37 @@
+"""Sweep of the weight-gradient schedule (r2l_debug_set_dw_schedule): backward time at 4096 rays (dW overlaps the chain)
+and at a large batch (dW after the chain), gradients compared with the first schedule.  Usage: gpu_dw_sched.py"""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from r2l_b200 import _lib, ops
+from r2l_b200.nerf_raybased import init_flat_params
+from oracle import r2l_oracle as orc
+dev = torch.device("cuda:0"); L = _lib.lib()
+packed = ops.pack_weights(init_flat_params(0).to(dev)); z = orc.sampler_z_vals(2.0, 6.0).tolist()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+def timed(n, sched, reps=10):
+    torch.manual_seed(1); o = torch.randn(n, 3, device=dev) * 0.5; d = torch.randn(n, 3, device=dev); t = torch.rand(n, 3, device=dev)
+    gr = torch.empty(ops.NUM_PARAMS, device=dev)
+    L.r2l_debug_set_dw_schedule(*sched)
+    tot_b = tot = 0.0
+    for i in range(reps + 3):
+        flush.fill_(1)
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record(); rgb, ctx = ops.forward_train(packed, rays_o=o, rays_d=d, z_vals=z)
+        g = (2.0 / (3 * n)) * (rgb - t); e1.record()
+        ops.backward(packed, ctx, g, gr); e2.record(); torch.cuda.synchronize()
+        if i >= 3: tot_b += e1.elapsed_time(e2); tot += e0.elapsed_time(e2)
+    return tot / reps, tot_b / reps, gr.clone()
+
+base = None
+for sched in [(0, 0, 0, 0), (-1, -1, -1, 0), (90, 90, 90, 0), (40, 64, 78, 0), (56, 72, 82, 0), (64, 76, 84, 0), (48, 72, 84, 0), (30, 60, 80, 0), (72, 80, 86, 0)]:
+    ms, ms_b, gr = timed(4096, sched)
+    if base is None: base = gr
+    print(f"N=4096 sched {sched}: fwd+bwd {ms:.4f} ms, backward {ms_b:.4f} ms, grads vs first rel diff {float((gr - base).norm() / base.norm()):.2e}", flush=True)
+base = None
+for sp in (1, 2, 3, 4, 8):
+    for n in (18944, 98304):
+        ms, ms_b, gr = timed(n, (-1, -1, -1, sp), reps=4)
+        print(f"N={n} serial pieces {sp}: fwd+bwd {ms:.4f} ms, backward {ms_b:.4f} ms", flush=True)
+L.r2l_debug_set_dw_schedule(-1, -1, -1, 0)
