@@ -122,6 +122,13 @@ int r2l_debug_set_stats(long long* stats);
  * are bit-identical, whichever form a call takes.  Process-wide; buffers sized by the *_bytes queries fit every form. */
 int r2l_set_pair_mode(int mode);
 
+/* Weight gradients of r2l_backward when the ray batch is cut into pieces that run on different SMs (small batches, where
+ * the weight-gradient kernel overlaps the backward chain): 0 (default) = every piece adds its result into `grads` with
+ * L2 floating-point reductions - the order in which the <= 8 pieces of a layer are summed is not fixed, so results can
+ * differ in the last bits from run to run, as torch's atomicAdd-based backward kernels do; 1 = pieces go to scratch and
+ * are summed in index order (bit-reproducible, ~0.1 ms slower per 4096-ray backward).  Process-wide. */
+int r2l_set_deterministic(int on);
+
 /* Debug / tuning: schedule of the weight-gradient kernel inside r2l_backward (dw.cu).  Units = the 86 body Linears in
  * the order the backward chain releases them, then 4 head column groups.  When the kernel overlaps the chain, units
  * < t1 run whole, < t2 in 2 ray-tile pieces, < t3 in 4, the rest in 8; when it runs after the chain every unit is cut

@@ -55,14 +55,16 @@ constexpr size_t kDwPartialBytes = (size_t)kDwMaxCtas * (256 * 256 + 256) * size
 // releases them.  g_dw_sched: {t1, t2, t3, s_after} for the concurrent mode (units < t1 whole, < t2 in 2 pieces, < t3 in
 // 4, the rest in 8) and the piece count of every unit in the serial mode; negative = built-in default.
 int g_dw_sched[4] = {-1, -1, -1, -1};
+int g_deterministic = 0;          // r2l_set_deterministic
 void dw_schedule(r2l::DwParams& d, bool concurrent) {
-  // Concurrent mode.  The chain releases a layer every T/90 of its run time T and a whole unit takes about 0.37 T on one
-  // SM (measured at 4096 rays: T = 0.36 ms, unit = 0.13 ms), so a unit released before ~0.6 T finishes in time without
-  // being cut; later ones are cut so that a piece takes no longer than what is left of the chain, the last ones in 8.
-  const int t1 = g_dw_sched[0] >= 0 ? g_dw_sched[0] : 56, t2 = g_dw_sched[1] >= 0 ? g_dw_sched[1] : 72,
-            t3 = g_dw_sched[2] >= 0 ? g_dw_sched[2] : 80;
-  // Serial mode (large batches, every SM free): 3 pieces per unit = 270 CTAs keep all SMs streaming
-  const int serial = g_dw_sched[3] > 0 ? g_dw_sched[3] : (d.num_tiles >= 96 ? 3 : 1);
+  // Concurrent mode: the kernel's persistent CTAs claim pieces in release order and follow the chain one piece behind,
+  // so the piece length sets how long dW keeps running after the chain has released its last layers: 4 pieces per unit
+  // (8 ray tiles of a 4096-ray batch, ~30 us), 8 for the layers released in the chain's last microseconds.
+  const int t1 = g_dw_sched[0] >= 0 ? g_dw_sched[0] : 0, t2 = g_dw_sched[1] >= 0 ? g_dw_sched[1] : 0,
+            t3 = g_dw_sched[2] >= 0 ? g_dw_sched[2] : 84;
+  // Serial mode (large batches, dW after the chain): whole units; the kernel is HBM-bound there (it streams 171 KiB per
+  // ray) and more pieces only add scratch traffic (measured: 1, 2, 3, 4, 8 pieces at 18,944 and 98,304 rays)
+  const int serial = g_dw_sched[3] > 0 ? g_dw_sched[3] : 1;
   int first = 0;
   for (int u = 0; u < kDwUnits; ++u) {
     int s = concurrent ? (u < t1 ? 1 : u < t2 ? 2 : u < t3 ? 4 : 8) : serial;
@@ -72,7 +74,9 @@ void dw_schedule(r2l::DwParams& d, bool concurrent) {
     d.unit_first[u] = (uint16_t)first;
     first += s;
   }
-  d.num_ctas = first;
+  d.num_items = first;
+  const int sms = sm_count();
+  d.grid = first < sms ? first : sms;
 }
 
 int num_tiles(int64_t n_rays) { return (int)((n_rays + r2l::kTileM - 1) / r2l::kTileM); }
@@ -271,20 +275,28 @@ int r2l_backward(int input_kind, const void* packed, const float* rgb, const flo
   d.ready = nullptr;
   d.partials = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + r2l_fwd_workspace_bytes(n_rays));
   d.tickets = ready + 128;
+  d.queue = ready + 250;
   d.times = g_trace ? g_trace + 148 * 5 * 96 : nullptr;   // the dW stamps follow the chain kernel's trace rows
   dw_schedule(d, side != nullptr);
+  d.deterministic = g_deterministic;
   if (int rc = check(cudaMemsetAsync(ready, 0, kReadyBytes, st), "r2l_backward(memset)")) return rc;
+  // pieces of split units add into the buffer: head + body gradients start at 0 (zeroed on the stream dW runs on)
+  const bool zero_grads = !d.deterministic && d.num_items > kDwUnits;
   if (side) {
     p.ready = ready;
     d.ready = ready;
     if (int rc = check(cudaEventRecord(side->fork, st), "r2l_backward(fork)")) return rc;
     if (int rc = check(cudaStreamWaitEvent(side->stream, side->fork, 0), "r2l_backward(fork wait)")) return rc;
     if (int rc = check(launch_chain_any(r2l::kBwd, p, grid, st), "r2l_backward(chain)")) return rc;
+    if (zero_grads)
+      if (int rc = check(cudaMemsetAsync(grads, 0, (size_t)r2l::kOffTailW * sizeof(float), side->stream), "r2l_backward(zero grads)")) return rc;
     if (int rc = check(r2l::launch_dw(d, side->stream), "r2l_backward(dw)")) return rc;
     if (int rc = check(cudaEventRecord(side->join, side->stream), "r2l_backward(join)")) return rc;
     if (int rc = check(cudaStreamWaitEvent(st, side->join, 0), "r2l_backward(join wait)")) return rc;
   } else {
     if (int rc = check(launch_chain_any(r2l::kBwd, p, grid, st), "r2l_backward(chain)")) return rc;
+    if (zero_grads)
+      if (int rc = check(cudaMemsetAsync(grads, 0, (size_t)r2l::kOffTailW * sizeof(float), st), "r2l_backward(zero grads)")) return rc;
     if (int rc = check(r2l::launch_dw(d, st), "r2l_backward(dw)")) return rc;
   }
   r2l::TailGradParams t;
@@ -381,6 +393,11 @@ int r2l_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
 
 int r2l_debug_set_stats(long long* stats) {
   g_stats = stats;
+  return 0;
+}
+
+int r2l_set_deterministic(int on) {
+  g_deterministic = on ? 1 : 0;
   return 0;
 }
 

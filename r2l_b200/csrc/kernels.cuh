@@ -49,12 +49,15 @@ struct DwParams {
   int input_kind;         // kInputX: head features in natural order, else fused-PE order
   int accumulate;
   // schedule: unit u (in release order: body layer 85 .. 0, then the 4 head column groups) is cut into unit_splits[u]
-  // ray-tile ranges, one CTA each, CTAs unit_first[u] .. unit_first[u] + unit_splits[u] - 1.  A piece of a split unit
-  // writes its partial result to partials[CTA index]; the last piece of the unit to finish (ticket) sums them in order.
+  // ray-tile ranges, one work item each, items unit_first[u] .. unit_first[u] + unit_splits[u] - 1.  A piece of a split unit
+  // writes its partial result to partials[item]; the last piece of the unit to finish (ticket) sums them in order.
   uint8_t unit_splits[kBodyLayers + 4];
   uint16_t unit_first[kBodyLayers + 4];
-  int num_ctas;
-  float* partials;        // [num_ctas][256*256 + 256] scratch (only slots of split units are used)
+  int deterministic;      // split units: 1 = partials in scratch + ordered sum by the last piece, 0 = L2 reductions into grads
+  int num_items;          // work items = pieces of all units, numbered in release order (item = "CTA" above)
+  int grid;               // persistent CTAs (<= SMs); they claim items in order from `queue`
+  int* queue;             // zeroed counter
+  float* partials;        // [num_items][256*256 + 256] scratch (only slots of split units are used)
   int* tickets;           // [90] zeroed counters (only needed when some unit is split)
   long long* times;       // optional debug: [unit][4] globaltimer stamps (start, flag seen, MMAs done, end)
   const int* ready;       // optional: wait until ready[group of this unit] == ready_target before streaming (see ChainParams)

@@ -184,6 +184,14 @@ __device__ __forceinline__ void flag_release_add(int* flag) {
   asm volatile("fence.proxy.async;" ::: "memory");          // async-proxy global writes -> generic proxy
   asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(flag) : "memory");
 }
+// fire-and-forget fp32 adds in L2 (no return value): four consecutive floats, 16-byte aligned
+__device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_f32(float* addr, float a) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
+}
+
 __device__ __forceinline__ int flag_acquire_load(const int* flag) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");

@@ -24,14 +24,17 @@ def timed(n, sched, reps=10):
         if i >= 3: tot_b += e1.elapsed_time(e2); tot += e0.elapsed_time(e2)
     return tot / reps, tot_b / reps, gr.clone()
 
+det = "det" in sys.argv[1:]
+L.r2l_set_deterministic(1 if det else 0)
+print("deterministic mode:", det, flush=True)
+quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
 base = None
-for sched in [(0, 0, 0, 0), (-1, -1, -1, 0), (90, 90, 90, 0), (40, 64, 78, 0), (56, 72, 82, 0), (64, 76, 84, 0), (48, 72, 84, 0), (30, 60, 80, 0), (72, 80, 86, 0)]:
-    ms, ms_b, gr = timed(4096, sched)
+scheds = [(-1, -1, -1, 0)] if quick else [(-1, -1, -1, 0), (0, 0, 0, 0), (0, 0, 90, 0), (0, 90, 90, 0), (90, 90, 90, 0), (0, 0, 76, 0), (0, 48, 84, 0), (30, 60, 84, 0)]
+for sched in scheds:
+    ms, ms_b, gr = timed(4096, sched, reps=3 if quick else 10)
     if base is None: base = gr
     print(f"N=4096 sched {sched}: fwd+bwd {ms:.4f} ms, backward {ms_b:.4f} ms, grads vs first rel diff {float((gr - base).norm() / base.norm()):.2e}", flush=True)
-base = None
-for sp in (1, 2, 3, 4, 8):
-    for n in (18944, 98304):
-        ms, ms_b, gr = timed(n, (-1, -1, -1, sp), reps=4)
-        print(f"N={n} serial pieces {sp}: fwd+bwd {ms:.4f} ms, backward {ms_b:.4f} ms", flush=True)
+for n in ((1000, 18944) if quick else (1000, 2048, 5376, 18944, 98304)):
+    ms, ms_b, gr = timed(n, (-1, -1, -1, 0), reps=4)
+    print(f"N={n} default schedule: fwd+bwd {ms:.4f} ms, backward {ms_b:.4f} ms ({n / ms / 1e3:.2f} M rays/s), finite={bool(torch.isfinite(gr).all())}", flush=True)
 L.r2l_debug_set_dw_schedule(-1, -1, -1, 0)
