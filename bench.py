@@ -231,26 +231,21 @@ def run_ours(args):
     d_ro, d_rd, d_tg = h_ro.to(dev), h_rd.to(dev), h_tg.to(dev)
     z_vals = PointSampler(400, 400, 555.5555155968841, 16, 2.0, 6.0).z_vals.tolist()
 
-    # ---- device-resident arm: raw ops on the flat buffers ----
-    flat = init_flat_params(0).to(dev).requires_grad_(False)
-    packed = ops.pack_weights(flat)
-    grads = torch.empty_like(flat)
-    flat_param = torch.nn.Parameter(flat)
-    flat_param.grad = grads
-    from r2l_b200.optim import FlatAdam
-    opt = FlatAdam([flat_param], lr=5e-4)
+    # ---- device-resident arm: the trainer's iteration (r2l_b200.trainer.R2LTrainer) on rays already in HBM ----
+    from r2l_b200.trainer import R2LTrainer
+    model = NeRF_v3_2(readme_args(), 1008, 3).to(dev)
+    with torch.no_grad():
+        model.flat.copy_(init_flat_params(0).to(dev))
+    ps = PointSampler(400, 400, 555.5555155968841, 16, 2.0, 6.0)
+    trainer = R2LTrainer(model, ps, lrate=5e-4, lrate_decay=500)     # CUDA graph on one GPU, eager + all-reduce on N > 1
+    packed = trainer.packed
     n_global = BATCH * world
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def step_device():
-        ops.pack_weights(flat_param.data, out=packed)
-        rgb, ctx = ops.forward_train(packed, rays_o=d_ro, rays_d=d_rd, z_vals=z_vals)
-        grad_rgb = (rgb - d_tg) * (2.0 / (3 * n_global))      # d mean((rgb - t)^2) over the GLOBAL batch
-        ops.backward(packed, ctx, grad_rgb, grads)
-        if world > 1:
-            dist.all_reduce(grads)                            # one NCCL all-reduce of the flat 23.7 MB buffer
-        opt.step()
-    LAUNCHES_PER_STEP = 7  # pack x2, chain fwd, chain bwd, dw, tail, adam
+        trainer.step(d_ro, d_rd, d_tg)
+    # forward chain, loss+grad, backward chain, weight gradients, tail gradients, Adam, pack (images + tables)
+    LAUNCHES_PER_STEP = 8
 
     def barrier():
         if world > 1:
@@ -321,28 +316,9 @@ def run_ours(args):
                              "achieved": full_tflops, "frac": full_tflops / peaks["bf16_tflops"],
                              "issued_frac": 3 * full_tflops / peaks["bf16_tflops"]}
 
-    # ---- end to end through the public module API, host buffers ----
-    model = NeRF_v3_2(readme_args(), 1008, 3).to(dev)
-    with torch.no_grad():
-        model.flat.copy_(init_flat_params(0).to(dev))
-    ps = PointSampler(400, 400, 555.5555155968841, 16, 2.0, 6.0)
-    opt2 = FlatAdam(model.parameters(), lr=5e-4)
-    h_loss = torch.empty(1).pin_memory()
-
+    # ---- end to end through the public API, host buffers: pinned rays/targets -> device, one iteration, loss -> host ----
     def step_e2e():
-        o = h_ro.to(dev, non_blocking=True)
-        d = h_rd.to(dev, non_blocking=True)
-        tgt = h_tg.to(dev, non_blocking=True)
-        opt2.zero_grad(set_to_none=True)
-        rgb = model.forward_rays(o, d, ps)
-        loss = torch.mean((rgb - tgt) ** 2) / world
-        loss.backward()
-        if world > 1:
-            dist.all_reduce(model.flat.grad)
-        opt2.step()
-        h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()   # the caller reads the loss
-        return float(h_loss[0])
+        return trainer.step_host(h_ro, h_rd, h_tg)
 
     for _ in range(3):
         step_e2e()
@@ -380,10 +356,11 @@ def run_ours(args):
                 "config": {"workload": WORKLOAD, "rays_per_gpu": BATCH, "global_batch": n_global,
                            "parallelism": f"dp{world}" if world > 1 else "single",
                            "l2": "256 MiB buffer written between timed iterations (L2 flush, untimed)",
-                           "step": "pack_weights + forward_train + backward(chain, dW, tail) + allreduce(N>1) + Adam (r2l_adam_step)"},
+                           "step": "R2LTrainer.step: forward_train + mse loss/grad + backward(chain, dW, tail) + allreduce(N>1) + Adam + pack_weights"
+                                   + (" (one CUDA graph replay)" if trainer.use_graph else " (eager launches)")},
                 "clocks": sampler.summary(), "gpu_launches": LAUNCHES_PER_STEP * args.steps,
                 "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": BATCH * 9 * 4, "d2h_bytes_per_step": 4,
-                        "api": "NeRF_v3_2.forward_rays + autograd + r2l_b200.optim.FlatAdam, pinned host rays -> device each step, loss read back"},
+                        "api": "R2LTrainer.step_host: pinned host rays/targets -> device each step, one training iteration, loss read back to the host"},
                 "roofline": roofline}
         if cpu is not None:
             line["cpu_baseline"] = cpu

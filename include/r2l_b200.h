@@ -110,6 +110,30 @@ int r2l_positional_embed(const float* x, float* out, int64_t n, int dim, int n_f
 int r2l_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
                   double beta2, double eps, int64_t step, void* stream);
 
+/* Ray-shard reader (HOST function, no CUDA call inside): dst_host[i * floats_per_shard ...] = the
+ * float32 payload of the `.npy` file paths[i] (np.save of a C-ordered [rows, 9] array: utils/create_data.py:866-869), read
+ * with pread on n_threads native threads.  dst_host is normally a pinned batch buffer, so a batch of --N_rand shards is
+ * one call and one H2D copy (replaces np.load + torch.Tensor + collate + pin per shard, dataset/load_blender.py:304-318,
+ * main.py:795-808).  A file with another dtype / order / size fails the call; r2l_last_error() names it. */
+int r2l_read_ray_shards(const char* const* paths, int n_paths, float* dst_host, int64_t floats_per_shard, int n_threads);
+
+/* The same update with the two step-dependent scalars read from DEVICE memory: hyper[0] = lr / (1 - beta1^step),
+ * hyper[1] = 1 / sqrt(1 - beta2^step) (r2l_adam_hyper computes them on the host exactly as r2l_adam_step does).  A train
+ * step captured in a CUDA graph is replayed with the learning-rate schedule of main.py:1181-1195 by refreshing 8 bytes. */
+int r2l_adam_hyper(double lr, double beta1, double beta2, int64_t step, float* hyper_host /* [2], host */);
+int r2l_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double beta1, double beta2,
+                      double eps, const float* hyper, void* stream);
+
+/* loss[0] = loss_scale * sum((rgb - target)^2), grad_rgb = grad_scale * (rgb - target), per_ray_err[r] = mean_c (rgb - target)^2.
+ * With loss_scale = lw_rgb / (3 N) and grad_scale = 2 lw_rgb / (3 N_global) this is img2mse(rgb, target) * lw_rgb
+ * (nerf_raybased.py:18, main.py:1377), the dL/drgb autograd derives from it, and the per-ray error the hard-example pool
+ * sorts by (main.py:1411-1413), in one launch with no host sync.  grad_rgb / per_ray_err may be NULL.  scratch:
+ * r2l_loss_scratch_bytes() bytes of device memory, zero before the first call (the kernel leaves it zero).  The sum is taken
+ * in a fixed order: bit-reproducible. */
+size_t r2l_loss_scratch_bytes(void);
+int r2l_mse_loss_grad(const float* rgb, const float* target, int64_t n_rays, float grad_scale, float loss_scale, float* grad_rgb,
+                      float* per_ray_err, float* loss, void* scratch, void* stream);
+
 /* Debug: device buffer [grid][8] of int64 cycle counters filled by the next r2l_forward calls (NULL = off):
  * [0] MMA wait on head A chunks, [1] on body A chunks, [2] on weight stages, [3] producer wait on free stages,
  * [4] MMA-thread total. */

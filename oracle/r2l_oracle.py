@@ -306,3 +306,54 @@ def render_rays(rays_o, rays_d, viewdirs, near, far, params_coarse, params_fine,
     rgb, disp, acc, w, depth = raw2outputs(raw, z_all, rays_d, white_bkgd)
     return {"rgb_map": rgb, "disp_map": disp, "acc_map": acc, "depth_map": depth, "rgb0": rgb0, "disp0": disp0,
             "acc0": acc0, "z_samples": z_samples, "z_vals": z_all, "weights0": weights}
+
+
+# ------------------------------------------------------------------------------------------------
+# training-loop pieces around the network (main.py:1176-1425)
+# ------------------------------------------------------------------------------------------------
+def lr_schedule(global_step: int, lrate: float, lrate_decay: int, warmup_lr: str | None = None) -> float:
+    """main.py:1181-1195 — exponential decay by 0.1 every lrate_decay*1000 steps, optional linear warm-up 'start_lr,end_iter'."""
+    decay_rate = 0.1
+    decay_steps = lrate_decay * 1000
+    if warmup_lr:
+        start_lr, end_iter = [float(x) for x in warmup_lr.split(',')]
+        if global_step < end_iter:
+            return (lrate - start_lr) / end_iter * global_step + start_lr
+        return lrate * (decay_rate ** ((global_step - end_iter) / decay_steps))
+    return lrate * (decay_rate ** (global_step / decay_steps))
+
+
+def img2mse(x: np.ndarray, y: np.ndarray):
+    """model/nerf_raybased.py:18."""
+    return np.mean((x - y) ** 2)
+
+
+def per_ray_error(rgb: np.ndarray, target: np.ndarray) -> np.ndarray:
+    """main.py:1411-1413 — torch.mean((rgb - target_s)**2, dim=1)."""
+    return np.mean((rgb - target) ** 2, axis=1)
+
+
+def hard_pool_update(hard_rays, hard_pool_full, rays_o, rays_d, target, rgb, batch_size, n_hard_in, hard_mul, rand_ix_out=None):
+    """main.py:1410-1425 — the n_hard_in rays of the fresh batch with the largest error replace the first n_hard_in drawn slots
+    (pool full) or are appended; the pool is full once it holds batch_size*hard_mul rays.  Returns (hard_rays, full)."""
+    err = per_ray_error(rgb[:batch_size], target[:batch_size])
+    indices = np.argsort(err, kind="stable")
+    hard_indices = indices[-n_hard_in:]
+    hard_rays_ = np.concatenate([rays_o[hard_indices], rays_d[hard_indices], target[hard_indices]], axis=-1)
+    if hard_pool_full:
+        hard_rays = hard_rays.copy()
+        hard_rays[rand_ix_out[:n_hard_in]] = hard_rays_
+    else:
+        hard_rays = np.concatenate([hard_rays, hard_rays_], axis=0)
+        if hard_rays.shape[0] >= batch_size * hard_mul:
+            hard_pool_full = True
+    return hard_rays, hard_pool_full
+
+
+def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+    """torch.optim.Adam (the reference's optimizer, main.py:465,:1406) for one tensor, defaults otherwise; step counts from 1."""
+    m = m + (g - m) * (1 - beta1)
+    v = v * beta2 + (1 - beta2) * g * g
+    bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+    p = p - (lr / bc1) * (m / (np.sqrt(v) / np.sqrt(bc2) + eps))
+    return p, m, v

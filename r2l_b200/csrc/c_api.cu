@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstring>
 #include <mutex>
+#include <string>
 
 #include "../../include/r2l_b200.h"
 #include "kernels.cuh"
@@ -201,7 +202,7 @@ int r2l_render_poses(const float* c2w, int64_t n_poses, int height, int width, f
   return check(launch_chain_any(r2l::kFwdInfer, p, fwd_grid(n_rays, r2l::kFwdInfer), (cudaStream_t)stream), "r2l_render_poses");
 }
 
-size_t r2l_bwd_workspace_bytes(int64_t n_rays) { return r2l_fwd_workspace_bytes(n_rays) + kDwPartialBytes; }
+size_t r2l_bwd_workspace_bytes(int64_t n_rays) { return r2l_fwd_workspace_bytes(n_rays) + kDwPartialBytes + r2l::kTailPartialBytes; }
 
 size_t r2l_train_fwd_saved_bytes(int64_t n_rays) {
   return (size_t)even_tiles(n_rays) * r2l::kFwdSavedChunks * r2l::kAChunkBytes;
@@ -304,8 +305,10 @@ int r2l_backward(int input_kind, const void* packed, const float* rgb, const flo
   t.rgb = rgb;
   t.grad_rgb = grad_rgb;
   t.grads = grads;
+  t.partials = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + r2l_fwd_workspace_bytes(n_rays) + kDwPartialBytes);
+  t.ticket = ready + 252;
   t.n_rays = n_rays;
-  return check(r2l::launch_tail_grads(t, true, st), "r2l_backward(tail)");
+  return check(r2l::launch_tail_grads(t, st), "r2l_backward(tail)");
 }
 
 int r2l_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, int64_t n_rays, int n_samples,
@@ -387,8 +390,43 @@ int r2l_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
   const double bc1 = 1.0 - std::pow(beta1, (double)step);
   const double bc2 = 1.0 - std::pow(beta2, (double)step);
   return check(r2l::launch_adam(params, grads, exp_avg, exp_avg_sq, n, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
-                                (float)eps, (float)(lr / bc1), (float)(1.0 / std::sqrt(bc2)), (cudaStream_t)stream),
+                                (float)eps, (float)(lr / bc1), (float)(1.0 / std::sqrt(bc2)), nullptr, (cudaStream_t)stream),
                "r2l_adam_step");
+}
+
+int r2l_adam_hyper(double lr, double beta1, double beta2, int64_t step, float* hyper_host) {
+  if (!hyper_host || step < 1) return fail("r2l_adam_hyper: %s", "null pointer or step < 1");
+  hyper_host[0] = (float)(lr / (1.0 - std::pow(beta1, (double)step)));
+  hyper_host[1] = (float)(1.0 / std::sqrt(1.0 - std::pow(beta2, (double)step)));
+  return 0;
+}
+
+int r2l_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double beta1, double beta2,
+                      double eps, const float* hyper, void* stream) {
+  if (n == 0) return 0;
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !hyper) return fail("r2l_adam_step_dev: %s", "null pointer");
+  if (n < 0) return fail("r2l_adam_step_dev: %s", "bad n");
+  if (misaligned(params) || misaligned(grads) || misaligned(exp_avg) || misaligned(exp_avg_sq))
+    return fail("r2l_adam_step_dev: %s", "buffers must be 16-byte aligned");
+  return check(r2l::launch_adam(params, grads, exp_avg, exp_avg_sq, n, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
+                                (float)eps, 0.f, 0.f, hyper, (cudaStream_t)stream), "r2l_adam_step_dev");
+}
+
+int r2l_read_ray_shards(const char* const* paths, int n_paths, float* dst_host, int64_t floats_per_shard, int n_threads) {
+  if (n_paths == 0) return 0;
+  if (!paths || !dst_host || n_paths < 0 || floats_per_shard <= 0) return fail("r2l_read_ray_shards: %s", "bad arguments");
+  const std::string e = r2l::read_ray_shards(paths, n_paths, dst_host, floats_per_shard, n_threads);
+  return e.empty() ? 0 : fail("r2l_read_ray_shards: %s", e.c_str());
+}
+
+size_t r2l_loss_scratch_bytes(void) { return 1024; }
+
+int r2l_mse_loss_grad(const float* rgb, const float* target, int64_t n_rays, float grad_scale, float loss_scale, float* grad_rgb,
+                      float* per_ray_err, float* loss, void* scratch, void* stream) {
+  if (n_rays < 0) return fail("r2l_mse_loss_grad: %s", "negative n_rays");
+  if (!loss || !scratch || (n_rays > 0 && (!rgb || !target))) return fail("r2l_mse_loss_grad: %s", "null pointer");
+  return check(r2l::launch_mse_loss_grad(rgb, target, n_rays, grad_scale, loss_scale, grad_rgb, per_ray_err, loss,
+                                         static_cast<float*>(scratch), (cudaStream_t)stream), "r2l_mse_loss_grad");
 }
 
 int r2l_debug_set_stats(long long* stats) {

@@ -372,37 +372,56 @@ __global__ void __launch_bounds__(kDwThreads, 1) r2l_dw_kernel(const __grid_cons
 }
 
 // tail.0.weight / tail.0.bias gradients: dW_t[c,j] = sum_n dlogit[n,c] (z_43 + h)[n,j]; 768+3 outputs, CUDA cores.
+// A fixed number of blocks each sum their 128-ray tiles in order into registers and write one partial row; the last
+// block to finish (ticket) adds the rows in block order and overwrites the gradient entries: no atomics on the data, the
+// result is bit-reproducible.
+constexpr int kTailBlocks = 64;
+constexpr int kTailOutputs = kOutDim * kWidth + kOutDim;   // 771
 __global__ void __launch_bounds__(256) r2l_tail_grad_kernel(const __grid_constant__ TailGradParams p) {
   __shared__ float dl[128][3];
-  const int64_t n0 = (int64_t)blockIdx.x * 128;
-  if (threadIdx.x < 128) {
-    const int64_t n = n0 + threadIdx.x;
-    float v[3] = {0.f, 0.f, 0.f};
-    if (n < p.n_rays) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float y = p.rgb[n * 3 + c];
-        v[c] = p.grad_rgb[n * 3 + c] * y * (1.f - y);
-      }
-    }
-    dl[threadIdx.x][0] = v[0]; dl[threadIdx.x][1] = v[1]; dl[threadIdx.x][2] = v[2];
-  }
-  __syncthreads();
+  __shared__ int is_last;
   const int j = threadIdx.x;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-  const int rows = (int)((p.n_rays - n0) < 128 ? (p.n_rays - n0) : 128);
-  for (int r = 0; r < rows; ++r) {
-    const float z = p.zf[(n0 + r) * kWidth + j];
-    a0 = fmaf(dl[r][0], z, a0); a1 = fmaf(dl[r][1], z, a1); a2 = fmaf(dl[r][2], z, a2);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, bsum = 0.f;
+  const int num_tiles = (int)((p.n_rays + 127) / 128);
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int64_t n0 = (int64_t)tile * 128;
+    __syncthreads();   // the previous tile's dl is no longer read
+    if (threadIdx.x < 128) {
+      const int64_t n = n0 + threadIdx.x;
+      float v[3] = {0.f, 0.f, 0.f};
+      if (n < p.n_rays) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float y = p.rgb[n * 3 + c];
+          v[c] = p.grad_rgb[n * 3 + c] * y * (1.f - y);
+        }
+      }
+      dl[threadIdx.x][0] = v[0]; dl[threadIdx.x][1] = v[1]; dl[threadIdx.x][2] = v[2];
+    }
+    __syncthreads();
+    const int rows = (int)((p.n_rays - n0) < 128 ? (p.n_rays - n0) : 128);
+    for (int r = 0; r < rows; ++r) {
+      const float z = p.zf[(n0 + r) * kWidth + j];
+      a0 = fmaf(dl[r][0], z, a0); a1 = fmaf(dl[r][1], z, a1); a2 = fmaf(dl[r][2], z, a2);
+    }
+    if (j < 3)
+      for (int r = 0; r < rows; ++r) bsum += dl[r][j];
   }
-  atomicAdd(p.grads + kOffTailW + j, a0);
-  atomicAdd(p.grads + kOffTailW + kWidth + j, a1);
-  atomicAdd(p.grads + kOffTailW + 2 * kWidth + j, a2);
-  if (j < 3) {
+  float* part = p.partials + (int64_t)blockIdx.x * kTailOutputs;
+  part[j] = a0; part[kWidth + j] = a1; part[2 * kWidth + j] = a2;
+  if (j < 3) part[3 * kWidth + j] = bsum;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(p.ticket, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int o = j; o < kTailOutputs; o += 256) {
     float s = 0.f;
-    for (int r = 0; r < rows; ++r) s += dl[r][j];
-    atomicAdd(p.grads + kOffTailB + j, s);
+    for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(p.partials + (int64_t)b * kTailOutputs + o);
+    p.grads[kOffTailW + o] = s;   // tail.0.weight [3,256] and tail.0.bias [3] are contiguous in the flat buffer
   }
+  if (threadIdx.x == 0) *p.ticket = 0;
 }
 
 cudaError_t launch_dw(const DwParams& p, cudaStream_t stream) {
@@ -412,13 +431,9 @@ cudaError_t launch_dw(const DwParams& p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_tail_grads(const TailGradParams& p, bool zero_first, cudaStream_t stream) {
-  if (zero_first) {
-    cudaError_t e = cudaMemsetAsync(p.grads + kOffTailW, 0, (kOutDim * kWidth + kOutDim) * sizeof(float), stream);
-    if (e != cudaSuccess) return e;
-  }
-  const int blocks = (int)((p.n_rays + 127) / 128);
-  r2l_tail_grad_kernel<<<blocks, 256, 0, stream>>>(p);
+cudaError_t launch_tail_grads(const TailGradParams& p, cudaStream_t stream) {
+  const int tiles = (int)((p.n_rays + 127) / 128);
+  r2l_tail_grad_kernel<<<tiles < kTailBlocks ? tiles : kTailBlocks, 256, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -68,9 +68,12 @@ struct TailGradParams {
   const float* zf;        // [N,256]
   const float* rgb;       // [N,3]
   const float* grad_rgb;  // [N,3]
-  float* grads;           // flat; tail.0.weight / tail.0.bias accumulated atomically
+  float* grads;           // flat; tail.0.weight / tail.0.bias are overwritten
+  float* partials;        // [64][771] scratch
+  int* ticket;            // zeroed counter (left zero)
   int64_t n_rays;
 };
+constexpr size_t kTailPartialBytes = (size_t)64 * 771 * sizeof(float);
 
 struct TeacherParams {
   const float* pts;          // [P,3] sample points (ray-major: point p belongs to ray p / samples_per_ray)
@@ -89,7 +92,7 @@ cudaError_t launch_pack(const float* params, void* packed, cudaStream_t stream);
 enum : int { kFormSingle = 0, kFormPair = 1, kFormHalf = 2 };   // launch forms of the chain kernels, see chain.cu
 cudaError_t launch_chain(int mode, int form, const ChainParams& p, int grid, cudaStream_t stream);   // pair / half: grid even, clusters of 2
 cudaError_t launch_dw(const DwParams& p, cudaStream_t stream);
-cudaError_t launch_tail_grads(const TailGradParams& p, bool zero_first, cudaStream_t stream);
+cudaError_t launch_tail_grads(const TailGradParams& p, cudaStream_t stream);
 cudaError_t launch_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, int64_t n_rays, int n_samples,
                                int white_bkgd, float* rgb_map, float* disp_map, float* acc_map, float* weights,
                                float* depth_map, cudaStream_t stream);
@@ -97,7 +100,13 @@ cudaError_t launch_sample_pdf_merge(const float* z_vals, const float* weights, c
                                     int S, int M, float* z_samples, float* z_merged, const float* bins_in, cudaStream_t stream);
 cudaError_t launch_embed(const float* x, float* out, int64_t n, int dim, int L, int style, cudaStream_t stream);
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float w1, float beta2, float w2, float eps,
-                        float step_size, float inv_bc2_sqrt, cudaStream_t stream);
+                        float step_size, float inv_bc2_sqrt, const float* hyper, cudaStream_t stream);
+cudaError_t launch_mse_loss_grad(const float* rgb, const float* target, int64_t n, float grad_scale, float loss_scale,
+                                 float* grad_rgb, float* per_ray, float* loss, float* scratch, cudaStream_t stream);
+}  // namespace r2l
+#include <string>
+namespace r2l {
+std::string read_ray_shards(const char* const* paths, int n_paths, float* dst, int64_t floats_per_shard, int n_threads);   // io.cu (host)
 cudaError_t launch_mma_rate(int form, int variant, int reps, int grid, long long* out, cudaStream_t stream);
 cudaError_t launch_umma_selftest(const float* A, const void* images, float* C, cudaStream_t stream);
 

@@ -8,7 +8,13 @@ namespace r2l {
 __global__ void __launch_bounds__(256) r2l_adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                        float* __restrict__ m, float* __restrict__ v, int64_t n,
                                                        float w1, float beta2, float w2, float eps, float step_size,
-                                                       float inv_bc2_sqrt) {   // w1 = 1 - beta1, w2 = 1 - beta2
+                                                       float inv_bc2_sqrt, const float* __restrict__ hyper) {   // w1 = 1 - beta1, w2 = 1 - beta2
+  // hyper (optional, device): {step_size, inv_bc2_sqrt} of this step, so that a captured CUDA graph can be replayed with
+  // the learning-rate schedule and the bias corrections of the current step (r2l_adam_step_dev)
+  if (hyper != nullptr) {
+    step_size = __ldg(hyper);
+    inv_bc2_sqrt = __ldg(hyper + 1);
+  }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n4 = n >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -39,11 +45,11 @@ __global__ void __launch_bounds__(256) r2l_adam_kernel(float* __restrict__ p, co
 }
 
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float w1, float beta2, float w2, float eps,
-                        float step_size, float inv_bc2_sqrt, cudaStream_t stream) {
+                        float step_size, float inv_bc2_sqrt, const float* hyper, cudaStream_t stream) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  r2l_adam_kernel<<<sms * 8, 256, 0, stream>>>(p, g, m, v, n, w1, beta2, w2, eps, step_size, inv_bc2_sqrt);
+  r2l_adam_kernel<<<sms * 8, 256, 0, stream>>>(p, g, m, v, n, w1, beta2, w2, eps, step_size, inv_bc2_sqrt, hyper);
   return cudaGetLastError();
 }
 

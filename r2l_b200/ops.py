@@ -191,8 +191,11 @@ def _resolve_inputs(rays_o, rays_d, z_vals, t_rand, z_lower, z_diff, pts, x):
 
 
 def forward_train(packed: torch.Tensor, *, rays_o=None, rays_d=None, z_vals=None, t_rand=None, z_lower=None,
-                  z_diff=None, pts=None, x=None, keep: bool = False):
-    """Like forward(), but also returns the TrainContext for backward()."""
+                  z_diff=None, pts=None, x=None, keep: bool = False, fwd_saved: torch.Tensor | None = None,
+                  workspace: torch.Tensor | None = None):
+    """Like forward(), but also returns the TrainContext for backward().  fwd_saved / workspace: caller-owned uint8 buffers
+    (train_buffer_bytes(n)) instead of the per-device pools - what a captured CUDA graph needs, since pooled buffers may be
+    re-allocated by a later, larger call."""
     L = _lib.lib()
     kind, in0, in1, t_rand, zl, zd = _resolve_inputs(rays_o, rays_d, z_vals, t_rand, z_lower, z_diff, pts, x)
     n, dev = in0.shape[0], in0.device
@@ -202,21 +205,40 @@ def forward_train(packed: torch.Tensor, *, rays_o=None, rays_d=None, z_vals=None
     ctx.zf = torch.empty((n, 256), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         nsaved = int(L.r2l_train_fwd_saved_bytes(n))
-        if keep:
+        if fwd_saved is not None:
+            if fwd_saved.numel() < nsaved or fwd_saved.dtype != torch.uint8 or fwd_saved.device != dev:
+                raise ValueError(f"fwd_saved: expected a uint8 buffer of >= {nsaved} bytes on {dev}")
+            ctx.fwd_saved, ctx.generation = fwd_saved, None
+        elif keep:
             ctx.fwd_saved, ctx.generation = torch.empty(nsaved, dtype=torch.uint8, device=dev), None
         else:
             ctx.fwd_saved = _pooled(dev, "fwd", nsaved)
             ctx.generation = _generation[dev.index] = _generation.get(dev.index, 0) + 1
         ctx.device_index = dev.index
         wbytes = int(L.r2l_fwd_workspace_bytes(n))
-        ws = _workspace(dev, wbytes)
+        ws = _checked_workspace(workspace, dev, wbytes)
         _lib.check(L.r2l_forward_train(kind, _ptr(in0), _ptr(in1), _ptr(t_rand), zl, zd, _ptr(packed), _ptr(ctx.rgb),
                                        _ptr(ctx.zf), _ptr(ctx.fwd_saved), _ptr(ws), wbytes, n, _stream()),
                    "r2l_forward_train")
     return ctx.rgb, ctx
 
 
-def backward(packed: torch.Tensor, ctx: TrainContext, grad_rgb: torch.Tensor, grads: torch.Tensor | None = None) -> torch.Tensor:
+def train_buffer_bytes(n_rays: int):
+    """(fwd_saved, bwd_saved, workspace) sizes in bytes for caller-owned buffers of forward_train / backward."""
+    L = _lib.lib()
+    return int(L.r2l_train_fwd_saved_bytes(n_rays)), int(L.r2l_train_bwd_saved_bytes(n_rays)), int(L.r2l_bwd_workspace_bytes(n_rays))
+
+
+def _checked_workspace(workspace, dev, nbytes):
+    if workspace is None:
+        return _workspace(dev, nbytes)
+    if workspace.numel() < nbytes or workspace.dtype != torch.uint8 or workspace.device != dev:
+        raise ValueError(f"workspace: expected a uint8 buffer of >= {nbytes} bytes on {dev}")
+    return workspace
+
+
+def backward(packed: torch.Tensor, ctx: TrainContext, grad_rgb: torch.Tensor, grads: torch.Tensor | None = None,
+             bwd_saved: torch.Tensor | None = None, workspace: torch.Tensor | None = None) -> torch.Tensor:
     """dL/dparams (flat, state_dict order) for dL/drgb = grad_rgb.  `grads` is overwritten if given."""
     L = _lib.lib()
     grad_rgb = _require_cuda_f32(grad_rgb, "grad_rgb", (3,))
@@ -231,9 +253,13 @@ def backward(packed: torch.Tensor, ctx: TrainContext, grad_rgb: torch.Tensor, gr
     elif grads.numel() != NUM_PARAMS or grads.dtype != torch.float32 or not grads.is_contiguous() or grads.device != dev:
         raise ValueError("grads: expected a contiguous float32 CUDA tensor of NUM_PARAMS elements")
     with torch.cuda.device(dev):
-        bwd_saved = _pooled(dev, "bwd", int(L.r2l_train_bwd_saved_bytes(ctx.n)))
+        nsaved = int(L.r2l_train_bwd_saved_bytes(ctx.n))
+        if bwd_saved is None:
+            bwd_saved = _pooled(dev, "bwd", nsaved)
+        elif bwd_saved.numel() < nsaved or bwd_saved.dtype != torch.uint8 or bwd_saved.device != dev:
+            raise ValueError(f"bwd_saved: expected a uint8 buffer of >= {nsaved} bytes on {dev}")
         wbytes = int(L.r2l_bwd_workspace_bytes(ctx.n))
-        ws = _workspace(dev, wbytes)
+        ws = _checked_workspace(workspace, dev, wbytes)
         _lib.check(L.r2l_backward(ctx.kind, _ptr(packed), _ptr(ctx.rgb), _ptr(grad_rgb), _ptr(ctx.zf),
                                   _ptr(ctx.fwd_saved), _ptr(bwd_saved), _ptr(grads), _ptr(ws), wbytes, ctx.n,
                                   _stream()), "r2l_backward")
@@ -358,3 +384,51 @@ def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, n_importance: int, u: 
         _lib.check(_lib.lib().r2l_sample_pdf(_ptr(bins), _ptr(weights), _ptr(u), stride, n, b, n_importance, _ptr(out), _stream()),
                    "r2l_sample_pdf")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# loss + gradient in one launch, Adam with device-side step scalars (CUDA-graph friendly train step)
+# ------------------------------------------------------------------------------------------------
+_loss_scratch: dict = {}
+
+
+def mse_loss_grad(rgb: torch.Tensor, target: torch.Tensor, grad_scale: float, loss_scale: float, *, grad_rgb=None,
+                  per_ray_err=None, loss=None, want_per_ray: bool = False):
+    """(loss[1], grad_rgb[N,3], per_ray_err[N] or None): loss = loss_scale * sum((rgb - target)^2), grad_rgb = grad_scale *
+    (rgb - target), per_ray_err = mean over the 3 channels of (rgb - target)^2.  img2mse * lw_rgb (main.py:1377) is
+    loss_scale = lw_rgb / (3 N), grad_scale = 2 lw_rgb / (3 N_global)."""
+    rgb = _require_cuda_f32(rgb, "rgb", (3,))
+    target = _require_cuda_f32(target, "target", (3,))
+    if rgb.shape != target.shape:
+        raise ValueError("rgb / target shape mismatch")
+    n, dev = rgb.shape[0], rgb.device
+    if grad_rgb is None:
+        grad_rgb = torch.empty_like(rgb)
+    if per_ray_err is None and want_per_ray:
+        per_ray_err = torch.empty(n, dtype=torch.float32, device=dev)
+    if loss is None:
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+    scratch = _loss_scratch.get(dev.index)
+    if scratch is None:
+        scratch = _loss_scratch[dev.index] = torch.zeros(int(_lib.lib().r2l_loss_scratch_bytes()), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().r2l_mse_loss_grad(_ptr(rgb), _ptr(target), n, float(grad_scale), float(loss_scale), _ptr(grad_rgb),
+                                                _ptr(per_ray_err), _ptr(loss), _ptr(scratch), _stream()), "r2l_mse_loss_grad")
+    return loss, grad_rgb, per_ray_err
+
+
+def adam_hyper(lr: float, beta1: float, beta2: float, step: int, out: torch.Tensor) -> torch.Tensor:
+    """The two step-dependent Adam scalars into a HOST float32 tensor of 2 elements (pinned for the graph's H2D copy)."""
+    if out.is_cuda or out.dtype != torch.float32 or out.numel() < 2:
+        raise ValueError("adam_hyper: `out` must be a host float32 tensor with 2 elements")
+    _lib.check(_lib.lib().r2l_adam_hyper(float(lr), float(beta1), float(beta2), int(step), ctypes.c_void_p(out.data_ptr())), "r2l_adam_hyper")
+    return out
+
+
+def adam_step_dev(params, grads, exp_avg, exp_avg_sq, beta1, beta2, eps, hyper_dev):
+    for name, t in (("params", params), ("grads", grads), ("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq), ("hyper", hyper_dev)):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise RuntimeError(f"adam_step_dev: {name} must be a contiguous float32 CUDA tensor (no CPU fallback)")
+    with torch.cuda.device(params.device):
+        _lib.check(_lib.lib().r2l_adam_step_dev(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), params.numel(), float(beta1),
+                                                float(beta2), float(eps), _ptr(hyper_dev), _stream()), "r2l_adam_step_dev")

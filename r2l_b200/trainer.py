@@ -1,0 +1,236 @@
+"""The body of the reference's training loop for the R2L network (main.py:1176-1425) as one object, device-resident and
+(on one GPU) replayed as a CUDA graph.
+
+    reference, per iteration                                           here
+    ---------------------------------------------------------------   ------------------------------------------------
+    LR schedule, param_group['lr'] = ...            (:1181-1195)       lr_at(step): 8 bytes refreshed per step
+    hard-ray pool: np.random.permutation + cat      (:1325-1347)       HardRayPool.draw (torch ops on the device)
+    sample_train -> positional_embedder -> model    (:1369-1374)       r2l_forward_train (one kernel)
+    img2mse * lw_rgb, psnr.item()                   (:1377-1379)       r2l_mse_loss_grad (one kernel, no host sync)
+    optimizer.zero_grad(); loss.backward()          (:1403-1404)       r2l_backward (chain + weight gradients)
+    [DataParallel reduce to GPU 0]                  (:472-479)         ONE all-reduce of the flat gradient (N > 1)
+    optimizer.step()  (Adam over 176 tensors)       (:1406)            r2l_adam_step_dev + r2l_pack_weights
+    torch.sort of per-ray errors, pool update       (:1410-1425)       HardRayPool.update (device, no sync)
+
+No arithmetic of the network happens in torch; torch provides buffers, streams, the CUDA-graph capture and NCCL.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .nerf_raybased import N_SAMPLES, NUM_PARAMS
+
+
+def lr_at(global_step: int, lrate: float, lrate_decay: int, warmup_lr: str | None = None) -> float:
+    """Learning rate of iteration `global_step` (main.py:1181-1195; args.lrate, args.lrate_decay in 1000 steps,
+    args.warmup_lr = 'start_lr,end_iter')."""
+    decay_rate, decay_steps = 0.1, lrate_decay * 1000
+    if warmup_lr:
+        start_lr, end_iter = [float(x) for x in warmup_lr.split(',')]
+        if global_step < end_iter:
+            return (lrate - start_lr) / end_iter * global_step + start_lr
+        return lrate * (decay_rate ** ((global_step - end_iter) / decay_steps))
+    return lrate * (decay_rate ** (global_step / decay_steps))
+
+
+class HardRayPool:
+    """Hard-example pool of main.py:1325-1347 (draw) and :1410-1425 (update), kept on the device.
+
+    The reference sorts the per-ray errors, reads indices back implicitly and draws replacement slots with
+    np.random.permutation on the host every step; here both the top-n selection and the slot permutation are device ops,
+    so a step never waits for the host.  Semantics kept: the n_hard_in rays with the largest mean squared error of the
+    FRESH part of the batch enter; until the pool holds batch_size * hard_mul rays they are appended, afterwards they
+    overwrite the first n_hard_in of the n_hard_out slots drawn this step.  (The slot permutation comes from torch's device
+    generator instead of numpy's host generator: same distribution, different stream of numbers.)"""
+
+    def __init__(self, batch_size: int, hard_ratio, hard_mul: float, device):
+        if isinstance(hard_ratio, (list, tuple)):
+            n_in, n_out = int(hard_ratio[0] * batch_size), int(hard_ratio[1] * batch_size)
+        else:
+            n_in = n_out = int(hard_ratio * batch_size)
+        self.n_hard_in, self.n_hard_out = min(n_in, n_out), n_out
+        self.capacity = int(batch_size * hard_mul)
+        self.batch_size = batch_size
+        # appended in steps of n_hard_in until >= capacity (main.py:1423-1425)
+        slots = 0
+        while slots < self.capacity:
+            slots += max(self.n_hard_in, 1)
+        self.rays = torch.empty((slots, 9), dtype=torch.float32, device=device)
+        self.size = 0
+        self.full = False
+        self._slots_out = None
+
+    def draw(self):
+        """Rays [n_hard_out, 9] (o | d | target) to append to the batch, or None while the pool is filling."""
+        if not self.full:
+            self._slots_out = None
+            return None
+        self._slots_out = torch.randperm(self.size, device=self.rays.device)[:self.n_hard_out]
+        return self.rays[self._slots_out]
+
+    def update(self, rays_o, rays_d, target, per_ray_err):
+        """per_ray_err: mean squared error per ray of the whole batch; only the fresh rays [:batch_size] compete."""
+        if self.n_hard_in <= 0:
+            return
+        order = torch.sort(per_ray_err[:self.batch_size]).indices[-self.n_hard_in:]
+        hard = torch.cat([rays_o[order], rays_d[order], target[order]], dim=-1)
+        if self.full:
+            self.rays[self._slots_out[:self.n_hard_in]] = hard
+        else:
+            self.rays[self.size:self.size + hard.shape[0]] = hard
+            self.size += hard.shape[0]
+            if self.size >= self.capacity:
+                self.full = True
+
+
+class R2LTrainer:
+    """One training iteration of R2L per call to step(); state (parameters, Adam moments, hard pool, iteration counter)
+    lives on the device.  `model` is a r2l_b200 NeRF_v3_2 on CUDA, `point_sampler` its PointSampler."""
+
+    def __init__(self, model, point_sampler, lrate=5e-4, lrate_decay=500, warmup_lr=None, lw_rgb=1.0, perturb=0.0,
+                 hard_ratio=0, hard_mul=1, betas=(0.9, 0.999), eps=1e-8, use_graph=True, group=None, start_step=0):
+        if not model.flat.is_cuda:
+            raise RuntimeError("R2LTrainer: the model must live on a CUDA device (no CPU fallback)")
+        self.model, self.sampler = model, point_sampler
+        self.lrate, self.lrate_decay, self.warmup_lr, self.lw_rgb = lrate, lrate_decay, warmup_lr, float(lw_rgb)
+        self.perturb, self.betas, self.eps = float(perturb), betas, eps
+        self.hard_ratio, self.hard_mul = hard_ratio, hard_mul
+        self.group = group
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.use_graph = bool(use_graph) and self.world == 1
+        self.global_step = start_step          # iterations done; the next one is global_step + 1 (main.py:1175 `start + 1`)
+        dev = self.dev = model.flat.device
+        self.z_vals = point_sampler.z_vals.tolist()
+        lower, diff = point_sampler.jitter_bounds()
+        self.z_lower, self.z_diff = lower.tolist(), diff.tolist()
+        self.exp_avg = torch.zeros(NUM_PARAMS, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(NUM_PARAMS, dtype=torch.float32, device=dev)
+        self.adam_steps = 0
+        self.grads = torch.empty(NUM_PARAMS, dtype=torch.float32, device=dev)
+        self.packed = ops.pack_weights(model.flat.detach())
+        self.h_hyper = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self.d_hyper = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.h_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self.pool = None
+        self._static = {}     # n_rays -> dict(buffers, graph)
+        self._host = {}       # n_rays -> pinned staging of step_host
+        self.last_lr = None
+
+    # ---- the device work of one iteration on static buffers (captured once per batch size) ----
+    def _body(self, st):
+        n = st["o"].shape[0]
+        self.d_hyper.copy_(self.h_hyper, non_blocking=True)
+        kw = dict(rays_o=st["o"], rays_d=st["d"])
+        if st["t_rand"] is not None:
+            kw.update(t_rand=st["t_rand"], z_lower=self.z_lower, z_diff=self.z_diff)
+        else:
+            kw.update(z_vals=self.z_vals)
+        rgb, ctx = ops.forward_train(self.packed, fwd_saved=st["fwd_saved"], workspace=st["workspace"], **kw)
+        n_global = n * self.world
+        ops.mse_loss_grad(rgb, st["t"], 2.0 * self.lw_rgb / (3 * n_global), self.lw_rgb / (3 * n), grad_rgb=st["grad_rgb"],
+                          per_ray_err=st["err"], loss=self.loss)
+        ops.backward(self.packed, ctx, st["grad_rgb"], self.grads, bwd_saved=st["bwd_saved"], workspace=st["workspace"])
+        if self.world > 1:
+            dist.all_reduce(self.grads, group=self.group)       # ONE all-reduce of the flat 23.7 MB buffer
+        flat = self.model.flat.data
+        ops.adam_step_dev(flat, self.grads, self.exp_avg, self.exp_avg_sq, self.betas[0], self.betas[1], self.eps, self.d_hyper)
+        ops.pack_weights(flat, out=self.packed)                 # operands of the next forward (training or rendering)
+
+    def _static_for(self, n):
+        st = self._static.get(n)
+        if st is None:
+            dev = self.dev
+            nf, nb, nw = ops.train_buffer_bytes(n)
+            st = dict(o=torch.zeros((n, 3), device=dev), d=torch.zeros((n, 3), device=dev), t=torch.zeros((n, 3), device=dev),
+                      fwd_saved=torch.empty(nf, dtype=torch.uint8, device=dev), bwd_saved=torch.empty(nb, dtype=torch.uint8, device=dev),
+                      workspace=torch.empty(nw, dtype=torch.uint8, device=dev),
+                      t_rand=torch.zeros((n, N_SAMPLES), device=dev) if self.perturb > 0 else None,
+                      grad_rgb=torch.empty((n, 3), device=dev), err=torch.empty(n, device=dev), graph=None, warm=0)
+            self._static[n] = st
+        return st
+
+    def _run(self, st):
+        """Run the iteration body on the static buffers: eagerly twice (allocations, lazy CUDA init), then as a graph."""
+        if not self.use_graph:
+            return self._body(st)
+        if st["graph"] is None:
+            if st["warm"] < 2:
+                st["warm"] += 1
+                return self._body(st)
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(self.dev)
+            with torch.cuda.graph(g):
+                self._body(st)
+            st["graph"] = g
+        st["graph"].replay()
+
+    def _begin(self):
+        step = self.global_step + 1
+        self.last_lr = lr_at(step, self.lrate, self.lrate_decay, self.warmup_lr)
+        self.adam_steps += 1
+        ops.adam_hyper(self.last_lr, self.betas[0], self.betas[1], self.adam_steps, self.h_hyper)
+
+    def _end(self):
+        self.global_step += 1
+        # the kernels wrote the parameters and their packed image through raw pointers: tell autograd / the model's cache
+        flat = self.model.flat
+        torch.autograd.graph.increment_version(flat)
+        self.model._packed = self.packed
+        self.model._packed_version = (flat.data_ptr(), flat._version, str(flat.device))
+
+    @torch.no_grad()
+    def step(self, rays_o, rays_d, target, t_rand=None):
+        """One iteration on device tensors rays_o, rays_d, target [N,3].  Returns the loss as a 1-element device tensor
+        (no host sync; `float(loss)` when the caller wants the number).  perturb > 0 draws t_rand on the device unless given."""
+        self._begin()
+        batch = rays_o.shape[0]
+        if self.hard_ratio and self.pool is None:
+            self.pool = HardRayPool(batch, self.hard_ratio, self.hard_mul, self.dev)
+        extra = self.pool.draw() if self.pool is not None else None
+        n = batch + (extra.shape[0] if extra is not None else 0)
+        st = self._static_for(n)
+        st["o"][:batch].copy_(rays_o, non_blocking=True)      # device tensors, or pinned host tensors (step_host)
+        st["d"][:batch].copy_(rays_d, non_blocking=True)
+        st["t"][:batch].copy_(target, non_blocking=True)
+        if extra is not None:
+            st["o"][batch:].copy_(extra[:, :3]); st["d"][batch:].copy_(extra[:, 3:6]); st["t"][batch:].copy_(extra[:, 6:9])
+        if st["t_rand"] is not None:
+            if t_rand is not None:
+                st["t_rand"].copy_(t_rand)
+            else:
+                st["t_rand"].uniform_()       # sample_train's torch.rand (nerf_raybased.py:122), drawn on the device
+        self._run(st)
+        if self.pool is not None:
+            self.pool.update(st["o"], st["d"], st["t"], st["err"])
+        self._end()
+        return self.loss
+
+    @torch.no_grad()
+    def step_host(self, rays_o, rays_d, target):
+        """One iteration from HOST tensors [N,3] (a ray shard as the loader yields it): pinned staging, H2D copies, the
+        iteration, and the loss read back to the host.  Returns the loss as a float."""
+        n = rays_o.shape[0]
+        h = self._host.get(n)
+        if h is None:
+            h = self._host[n] = tuple(torch.empty((n, 3), dtype=torch.float32).pin_memory() for _ in range(3))
+        for dst, src in zip(h, (rays_o, rays_d, target)):
+            dst.copy_(src)
+        loss = self.step(*h)
+        self.h_loss.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        return float(self.h_loss[0])
+
+    def state_dict(self):
+        """Optimizer-side state in torch.optim.Adam's layout for the single flat parameter (ckpt['optimizer_state_dict'])."""
+        return {"state": {0: {"step": self.adam_steps, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}},
+                "param_groups": [{"lr": self.last_lr if self.last_lr is not None else self.lrate, "betas": self.betas,
+                                  "eps": self.eps, "params": [0]}], "global_step": self.global_step}
+
+    def load_state_dict(self, sd):
+        s = sd["state"][0]
+        self.adam_steps = int(s["step"])
+        self.exp_avg.copy_(s["exp_avg"]); self.exp_avg_sq.copy_(s["exp_avg_sq"])
+        self.global_step = int(sd.get("global_step", self.global_step))

@@ -1,0 +1,127 @@
+"""CPU tests of the host-side training pieces: ray-shard pipeline (row N2), LR schedule and hard-ray pool (row N3)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import r2l_oracle as orc
+from r2l_b200 import data as rd
+from r2l_b200.trainer import HardRayPool, lr_at
+
+
+@pytest.fixture()
+def shard_dir(tmp_path):
+    rays = np.random.RandomState(0).rand(64 * 10 + 17, 9).astype(np.float32)
+    paths = rd.write_ray_shards(rays, str(tmp_path), split_size=64, rng=np.random.RandomState(1))
+    return rays, paths, str(tmp_path)
+
+
+def test_write_ray_shards_format(shard_dir):
+    rays, paths, d = shard_dir
+    assert len(paths) == 10 and os.path.basename(paths[0]) == "data_1.npy"      # remainder of 17 rays dropped (create_data.py:864)
+    got = np.concatenate([np.load(p) for p in paths])
+    assert got.dtype == np.float32 and got.shape == (640, 9)
+    # a permutation of (a subset of) the input rows
+    key = lambda a: {r.tobytes() for r in a}
+    assert key(got) <= key(rays) and len(key(got)) == 640
+
+
+def test_native_reader_matches_np_load(shard_dir):
+    _, paths, d = shard_dir
+    out = torch.empty(64 * 4, 9)
+    rd.read_shards_into(paths[2:6], out, threads=3)
+    for k, p in enumerate(paths[2:6]):
+        assert np.array_equal(out[64 * k:64 * (k + 1)].numpy(), np.load(p))
+    # version-2 header, wrong dtype, wrong size, missing file: loud errors naming the file
+    np.save(os.path.join(d, "f64.npy"), np.zeros((64, 9)))
+    with pytest.raises(RuntimeError, match="f64.npy"):
+        rd.read_shards_into([os.path.join(d, "f64.npy")], torch.empty(64, 9))
+    with pytest.raises(RuntimeError, match="expected"):
+        rd.read_shards_into([paths[0]], torch.empty(32, 9))
+    with pytest.raises(RuntimeError, match="cannot open"):
+        rd.read_shards_into([os.path.join(d, "nope.npy")], torch.empty(64, 9))
+    with open(os.path.join(d, "v2.npy"), "wb") as f:
+        np.lib.format.write_array(f, np.load(paths[0]), version=(2, 0))
+    rd.read_shards_into([os.path.join(d, "v2.npy")], out[:64])
+    assert np.array_equal(out[:64].numpy(), np.load(paths[0]))
+    rd.read_shards_into([], torch.empty(0, 9))
+
+
+def test_loader_epochs_cover_every_shard_and_match_reference_reader(shard_dir):
+    _, paths, d = shard_dir
+    ds = rd.BlenderDataset_v2(d, pseudo_ratio=-1)
+    assert len(ds) == 10
+    by_bytes = {np.load(p).tobytes(): p for p in paths}
+    ld = rd.RayShardLoader(paths, shards_per_batch=2, rows=64, seed=5, pin=False, workers=2)
+    try:
+        seen = []
+        for _ in range(10):          # two epochs of 5 batches
+            o, dd, t = ld.next()
+            assert o.shape == (128, 3) and dd.shape == (128, 3) and t.shape == (128, 3)
+            full = torch.cat([o, dd, t], -1).numpy()
+            for k in range(2):
+                seen.append(by_bytes[full[64 * k:64 * (k + 1)].tobytes()])
+        assert sorted(seen[:10]) == sorted(paths) and sorted(seen[10:]) == sorted(paths)
+        assert seen[:10] != seen[10:]                     # a fresh permutation per epoch
+    finally:
+        ld.close()
+    # the item format of the reference's dataset class
+    o, dd, t = ds[3]
+    ref = np.load(ds.all_splits[3])
+    assert np.array_equal(o.numpy(), ref[:, :3]) and np.array_equal(dd.numpy(), ref[:, 3:6]) and np.array_equal(t.numpy(), ref[:, 6:9])
+
+
+def test_loader_rank_partition_is_disjoint(shard_dir):
+    _, paths, _ = shard_dir
+    parts = []
+    for r in range(2):
+        ld = rd.RayShardLoader(paths, 1, rows=64, seed=0, rank=r, world=2, pin=False)
+        parts.append(set(ld.paths))
+        ld.close()
+    assert parts[0].isdisjoint(parts[1]) and parts[0] | parts[1] == set(paths)
+
+
+def test_list_shards_pseudo_ratio(tmp_path):
+    for k in range(8):
+        np.save(tmp_path / f"data_{k}.npy", np.zeros((4, 9), np.float32))
+    for k in range(2):
+        np.save(tmp_path / f"train_{k}.npy", np.zeros((4, 9), np.float32))
+    allp, n_orig, n_pseudo = rd.list_shards(str(tmp_path), pseudo_ratio=-1)
+    assert (len(allp), n_orig, n_pseudo) == (10, 2, 8)
+    # pseudo_ratio 0.5: as many pseudo shards as original ones (load_blender.py:285-288)
+    allp, _, _ = rd.list_shards(str(tmp_path), pseudo_ratio=0.5, rng=np.random.RandomState(0))
+    assert len(allp) == 4 and sum(os.path.basename(p).startswith("train_") for p in allp) == 2
+
+
+def test_lr_schedule_matches_reference_formula():
+    for step in (1, 10, 1999, 2000, 2001, 250000, 1000000):
+        assert lr_at(step, 5e-4, 500) == orc.lr_schedule(step, 5e-4, 500)
+        assert lr_at(step, 5e-4, 500, "0.0001,2000") == orc.lr_schedule(step, 5e-4, 500, "0.0001,2000")
+    assert lr_at(500000, 5e-4, 500) == pytest.approx(5e-5)           # one decade per lrate_decay*1000 steps
+    assert lr_at(1000, 5e-4, 500, "0.0001,2000") == pytest.approx(3e-4)
+
+
+def test_hard_ray_pool_follows_the_reference_update():
+    """HardRayPool against the numpy restatement of main.py:1410-1425 with the same drawn slots."""
+    rng = np.random.RandomState(0)
+    batch, hard_ratio, hard_mul = 40, 0.2, 1
+    pool = HardRayPool(batch, hard_ratio, hard_mul, torch.device("cpu"))
+    n_in = int(hard_ratio * batch)
+    ref_rays, ref_full = np.zeros((0, 9), np.float32), False
+    torch.manual_seed(0)
+    for it in range(12):
+        o, d, t = (rng.rand(batch, 3).astype(np.float32) for _ in range(3))
+        extra = pool.draw()
+        assert (extra is not None) == ref_full
+        slots = None
+        if extra is not None:
+            slots = pool._slots_out.numpy()
+            assert np.array_equal(extra.numpy(), ref_rays[slots])
+            o, d, t = (np.concatenate([a, extra.numpy()[:, 3 * k:3 * k + 3]]) for k, a in enumerate((o, d, t)))
+        rgb = rng.rand(o.shape[0], 3).astype(np.float32)
+        pool.update(torch.from_numpy(o), torch.from_numpy(d), torch.from_numpy(t), torch.from_numpy(orc.per_ray_error(rgb, t)))
+        ref_rays, ref_full = orc.hard_pool_update(ref_rays, ref_full, o, d, t, rgb, batch, n_in, hard_mul, slots)
+        assert pool.full == ref_full and pool.size == ref_rays.shape[0]
+        assert np.array_equal(pool.rays[:pool.size].numpy(), ref_rays)
+    assert pool.full
