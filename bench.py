@@ -244,8 +244,8 @@ def run_ours(args):
 
     def step_device():
         trainer.step(d_ro, d_rd, d_tg)
-    # forward chain, loss+grad, backward chain, weight gradients, tail gradients, Adam, pack (images + tables)
-    LAUNCHES_PER_STEP = 8
+    # forward chain, loss+grad, backward chain, tail gradients, weight gradients, Adam, pack
+    LAUNCHES_PER_STEP = 7
 
     def barrier():
         if world > 1:

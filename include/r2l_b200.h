@@ -155,10 +155,10 @@ int r2l_set_deterministic(int on);
 
 /* Debug / tuning: schedule of the weight-gradient kernel inside r2l_backward (dw.cu).  Units = the 86 body Linears in
  * the order the backward chain releases them, then 4 head column groups.  When the kernel overlaps the chain, units
- * < t1 run whole, < t2 in 2 ray-tile pieces, < t3 in 4, the rest in 8; when it runs after the chain every unit is cut
- * into serial_pieces.  Negative values (0 for serial_pieces) = built-in defaults.  Results are independent of the schedule
- * up to fp32 summation order of the pieces. */
-int r2l_debug_set_dw_schedule(int t1, int t2, int t3, int serial_pieces);
+ * < t1 run whole, < t2 in 2 ray-tile pieces, < t3 in 4, < t4 in 8, the rest in 16; when it runs after the chain every
+ * unit is cut into serial_pieces.  Negative values (0 for serial_pieces) = built-in defaults.  Results are independent of
+ * the schedule up to fp32 summation order of the pieces. */
+int r2l_debug_set_dw_schedule(int t1, int t2, int t3, int serial_pieces, int t4);
 
 /* Debug: device buffer [grid][5][96] of clock64 stamps for the first tile of each CTA of the next chain launches:
  * row 0 MMA thread starts layer l, 1 MMA thread has issued layer l, 2 epilogue sees accumulator l complete,

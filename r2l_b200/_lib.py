@@ -52,7 +52,7 @@ _PROTOTYPES = {
     "r2l_debug_set_stats": (c_int, [c_void_p]),
     "r2l_set_pair_mode": (c_int, [c_int]),
     "r2l_set_deterministic": (c_int, [c_int]),
-    "r2l_debug_set_dw_schedule": (c_int, [c_int, c_int, c_int, c_int]),
+    "r2l_debug_set_dw_schedule": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "r2l_debug_set_trace": (c_int, [c_void_p]),
     "r2l_debug_mma_rate": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "r2l_selftest_layer": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),

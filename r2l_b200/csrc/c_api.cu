@@ -54,22 +54,24 @@ constexpr int kDwMaxCtas = 720;       // scratch slots for partial weight gradie
 constexpr size_t kDwPartialBytes = (size_t)kDwMaxCtas * (256 * 256 + 256) * sizeof(float);
 // Schedule of the weight-gradient kernel (dw.cu; see DwParams).  Units are numbered in the order the backward chain
 // releases them.  g_dw_sched: {t1, t2, t3, s_after} for the concurrent mode (units < t1 whole, < t2 in 2 pieces, < t3 in
-// 4, the rest in 8) and the piece count of every unit in the serial mode; negative = built-in default.
-int g_dw_sched[4] = {-1, -1, -1, -1};
+// 4, < t4 in 8, the rest in 16) and the piece count of every unit in the serial mode; negative = built-in default.
+int g_dw_sched[5] = {-1, -1, -1, -1, -1};
 int g_deterministic = 0;          // r2l_set_deterministic
 void dw_schedule(r2l::DwParams& d, bool concurrent) {
   // Concurrent mode: the kernel's persistent CTAs claim pieces in release order and follow the chain one piece behind,
   // so the piece length sets how long dW keeps running after the chain has released its last layers: 4 pieces per unit
-  // (8 ray tiles of a 4096-ray batch, ~30 us), 8 for the layers released in the chain's last microseconds.
+  // (8 ray tiles of a 4096-ray batch, ~30 us), 8 for the last two body layers and 16 for the head's column groups, which
+  // are released in the chain's last microseconds.
   const int t1 = g_dw_sched[0] >= 0 ? g_dw_sched[0] : 0, t2 = g_dw_sched[1] >= 0 ? g_dw_sched[1] : 0,
-            t3 = g_dw_sched[2] >= 0 ? g_dw_sched[2] : 84;
+            t3 = g_dw_sched[2] >= 0 ? g_dw_sched[2] : 84, t4 = g_dw_sched[4] >= 0 ? g_dw_sched[4] : 86;
   // Serial mode (large batches, dW after the chain): whole units; the kernel is HBM-bound there (it streams 171 KiB per
   // ray) and more pieces only add scratch traffic (measured: 1, 2, 3, 4, 8 pieces at 18,944 and 98,304 rays)
   const int serial = g_dw_sched[3] > 0 ? g_dw_sched[3] : 1;
   int first = 0;
   for (int u = 0; u < kDwUnits; ++u) {
-    int s = concurrent ? (u < t1 ? 1 : u < t2 ? 2 : u < t3 ? 4 : 8) : serial;
-    if (s > 8) s = 8;                              // 90 x 8 = kDwMaxCtas scratch slots
+    int s = concurrent ? (u < t1 ? 1 : u < t2 ? 2 : u < t3 ? 4 : u < t4 ? 8 : 16) : serial;
+    if (s > 16) s = 16;
+    if (first + s + (kDwUnits - 1 - u) > kDwMaxCtas) s = 1;   // never more items than scratch slots (deterministic mode)
     while (s > 1 && 2 * s > d.num_tiles) --s;      // at least two ray tiles per piece
     d.unit_splits[u] = (uint8_t)s;
     d.unit_first[u] = (uint16_t)first;
@@ -278,6 +280,14 @@ int r2l_backward(int input_kind, const void* packed, const float* rgb, const flo
   d.tickets = ready + 128;
   d.queue = ready + 250;
   d.times = g_trace ? g_trace + 148 * 5 * 96 : nullptr;   // the dW stamps follow the chain kernel's trace rows
+  r2l::TailGradParams t;
+  t.zf = zf;
+  t.rgb = rgb;
+  t.grad_rgb = grad_rgb;
+  t.grads = grads;
+  t.partials = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + r2l_fwd_workspace_bytes(n_rays) + kDwPartialBytes);
+  t.ticket = ready + 252;
+  t.n_rays = n_rays;
   dw_schedule(d, side != nullptr);
   d.deterministic = g_deterministic;
   if (int rc = check(cudaMemsetAsync(ready, 0, kReadyBytes, st), "r2l_backward(memset)")) return rc;
@@ -289,6 +299,8 @@ int r2l_backward(int input_kind, const void* packed, const float* rgb, const flo
     if (int rc = check(cudaEventRecord(side->fork, st), "r2l_backward(fork)")) return rc;
     if (int rc = check(cudaStreamWaitEvent(side->stream, side->fork, 0), "r2l_backward(fork wait)")) return rc;
     if (int rc = check(launch_chain_any(r2l::kBwd, p, grid, st), "r2l_backward(chain)")) return rc;
+    // the tail gradients need only forward results: first on the side stream, on SMs the chain leaves idle
+    if (int rc = check(r2l::launch_tail_grads(t, side->stream), "r2l_backward(tail)")) return rc;
     if (zero_grads)
       if (int rc = check(cudaMemsetAsync(grads, 0, (size_t)r2l::kOffTailW * sizeof(float), side->stream), "r2l_backward(zero grads)")) return rc;
     if (int rc = check(r2l::launch_dw(d, side->stream), "r2l_backward(dw)")) return rc;
@@ -300,15 +312,7 @@ int r2l_backward(int input_kind, const void* packed, const float* rgb, const flo
       if (int rc = check(cudaMemsetAsync(grads, 0, (size_t)r2l::kOffTailW * sizeof(float), st), "r2l_backward(zero grads)")) return rc;
     if (int rc = check(r2l::launch_dw(d, st), "r2l_backward(dw)")) return rc;
   }
-  r2l::TailGradParams t;
-  t.zf = zf;
-  t.rgb = rgb;
-  t.grad_rgb = grad_rgb;
-  t.grads = grads;
-  t.partials = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + r2l_fwd_workspace_bytes(n_rays) + kDwPartialBytes);
-  t.ticket = ready + 252;
-  t.n_rays = n_rays;
-  return check(r2l::launch_tail_grads(t, st), "r2l_backward(tail)");
+  return side ? 0 : check(r2l::launch_tail_grads(t, st), "r2l_backward(tail)");
 }
 
 int r2l_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, int64_t n_rays, int n_samples,
@@ -439,8 +443,8 @@ int r2l_set_deterministic(int on) {
   return 0;
 }
 
-int r2l_debug_set_dw_schedule(int t1, int t2, int t3, int serial_pieces) {
-  g_dw_sched[0] = t1; g_dw_sched[1] = t2; g_dw_sched[2] = t3; g_dw_sched[3] = serial_pieces;
+int r2l_debug_set_dw_schedule(int t1, int t2, int t3, int serial_pieces, int t4) {
+  g_dw_sched[0] = t1; g_dw_sched[1] = t2; g_dw_sched[2] = t3; g_dw_sched[3] = serial_pieces; g_dw_sched[4] = t4;
   return 0;
 }
 

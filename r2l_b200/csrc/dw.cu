@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) r2l_dw_kernel(const __grid_cons
 // A fixed number of blocks each sum their 128-ray tiles in order into registers and write one partial row; the last
 // block to finish (ticket) adds the rows in block order and overwrites the gradient entries: no atomics on the data, the
 // result is bit-reproducible.
-constexpr int kTailBlocks = 64;
+constexpr int kTailBlocks = 256;
 constexpr int kTailOutputs = kOutDim * kWidth + kOutDim;   // 771
 __global__ void __launch_bounds__(256) r2l_tail_grad_kernel(const __grid_constant__ TailGradParams p) {
   __shared__ float dl[128][3];
@@ -418,6 +418,7 @@ __global__ void __launch_bounds__(256) r2l_tail_grad_kernel(const __grid_constan
   __threadfence();
   for (int o = j; o < kTailOutputs; o += 256) {
     float s = 0.f;
+#pragma unroll 8
     for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(p.partials + (int64_t)b * kTailOutputs + o);
     p.grads[kOffTailW + o] = s;   // tail.0.weight [3,256] and tail.0.bias [3] are contiguous in the flat buffer
   }

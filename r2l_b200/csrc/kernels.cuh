@@ -69,11 +69,11 @@ struct TailGradParams {
   const float* rgb;       // [N,3]
   const float* grad_rgb;  // [N,3]
   float* grads;           // flat; tail.0.weight / tail.0.bias are overwritten
-  float* partials;        // [64][771] scratch
+  float* partials;        // [256][771] scratch
   int* ticket;            // zeroed counter (left zero)
   int64_t n_rays;
 };
-constexpr size_t kTailPartialBytes = (size_t)64 * 771 * sizeof(float);
+constexpr size_t kTailPartialBytes = (size_t)256 * 771 * sizeof(float);
 
 struct TeacherParams {
   const float* pts;          // [P,3] sample points (ray-major: point p belongs to ray p / samples_per_ray)

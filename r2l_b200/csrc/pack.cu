@@ -5,10 +5,35 @@
 
 namespace r2l {
 
+// fp32 side tables (biases, running sums of the second-layer biases, tail); one block, the first row of the
+// pack_images grid so that its serial 43-step sum hides behind the image blocks
+__device__ __forceinline__ void pack_tables(const float* __restrict__ params, uint8_t* __restrict__ packed) {
+  const int col = threadIdx.x;
+  float* cum = reinterpret_cast<float*>(packed + kPackOffCumBias);
+  float* headb = reinterpret_cast<float*>(packed + kPackOffHeadB);
+  float* b1 = reinterpret_cast<float*>(packed + kPackOffB1);
+  float* tailw = reinterpret_cast<float*>(packed + kPackOffTailW);
+  float* tailb = reinterpret_cast<float*>(packed + kPackOffTailB);
+  float acc = 0.f;
+  cum[col] = 0.f;
+  for (int k = 0; k < kBlocks; ++k) {
+    acc = __fadd_rn(acc, params[off_body_b(2 * k + 1) + col]);
+    cum[(k + 1) * kWidth + col] = acc;
+    b1[k * kWidth + col] = params[off_body_b(2 * k) + col];
+  }
+  headb[col] = params[kOffHeadB + col];
+  for (int c = 0; c < kOutDim; ++c) tailw[c * kWidth + col] = params[kOffTailW + c * kWidth + col];
+  if (col < 4) tailb[col] = col < kOutDim ? params[kOffTailB + col] : 0.f;
+}
+
 // One thread = one 16-byte swizzle unit (8 consecutive k) of one (n-row) of one image PAIR (hi+lo).
 __global__ void __launch_bounds__(256) pack_images_kernel(const float* __restrict__ params,
                                                           uint8_t* __restrict__ packed) {
-  const int ip = blockIdx.y;                                 // image pair
+  if (blockIdx.y == 0) {                                     // first grid row (dispatched first): the tables
+    if (blockIdx.x == 0) pack_tables(params, packed);
+    return;
+  }
+  const int ip = blockIdx.y - 1;                             // image pair
   const int unit = blockIdx.x * blockDim.x + threadIdx.x;    // 0 .. 2047
   const int n = unit >> 3, j = unit & 7;
   float v[8];
@@ -45,30 +70,9 @@ __global__ void __launch_bounds__(256) pack_images_kernel(const float* __restric
   *reinterpret_cast<uint4*>(img + kWImageBytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
-__global__ void __launch_bounds__(256) pack_tables_kernel(const float* __restrict__ params,
-                                                          uint8_t* __restrict__ packed) {
-  const int col = threadIdx.x;
-  float* cum = reinterpret_cast<float*>(packed + kPackOffCumBias);
-  float* headb = reinterpret_cast<float*>(packed + kPackOffHeadB);
-  float* b1 = reinterpret_cast<float*>(packed + kPackOffB1);
-  float* tailw = reinterpret_cast<float*>(packed + kPackOffTailW);
-  float* tailb = reinterpret_cast<float*>(packed + kPackOffTailB);
-  float acc = 0.f;
-  cum[col] = 0.f;
-  for (int k = 0; k < kBlocks; ++k) {
-    acc = __fadd_rn(acc, params[off_body_b(2 * k + 1) + col]);
-    cum[(k + 1) * kWidth + col] = acc;
-    b1[k * kWidth + col] = params[off_body_b(2 * k) + col];
-  }
-  headb[col] = params[kOffHeadB + col];
-  for (int c = 0; c < kOutDim; ++c) tailw[c * kWidth + col] = params[kOffTailW + c * kWidth + col];
-  if (col < 4) tailb[col] = col < kOutDim ? params[kOffTailB + col] : 0.f;
-}
-
 cudaError_t launch_pack(const float* params, void* packed, cudaStream_t stream) {
-  dim3 grid(2048 / 256, kNumImages / 2);
+  dim3 grid(2048 / 256, kNumImages / 2 + 1);
   pack_images_kernel<<<grid, 256, 0, stream>>>(params, static_cast<uint8_t*>(packed));
-  pack_tables_kernel<<<1, 256, 0, stream>>>(params, static_cast<uint8_t*>(packed));
   return cudaGetLastError();
 }
 

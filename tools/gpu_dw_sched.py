@@ -13,7 +13,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 def timed(n, sched, reps=10):
     torch.manual_seed(1); o = torch.randn(n, 3, device=dev) * 0.5; d = torch.randn(n, 3, device=dev); t = torch.rand(n, 3, device=dev)
     gr = torch.empty(ops.NUM_PARAMS, device=dev)
-    L.r2l_debug_set_dw_schedule(*sched)
+    L.r2l_debug_set_dw_schedule(*sched)   # (t1, t2, t3, serial, t4)
     tot_b = tot = 0.0
     for i in range(reps + 3):
         flush.fill_(1)
@@ -29,12 +29,12 @@ L.r2l_set_deterministic(1 if det else 0)
 print("deterministic mode:", det, flush=True)
 quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
 base = None
-scheds = [(-1, -1, -1, 0)] if quick else [(-1, -1, -1, 0), (0, 0, 0, 0), (0, 0, 90, 0), (0, 90, 90, 0), (90, 90, 90, 0), (0, 0, 76, 0), (0, 48, 84, 0), (30, 60, 84, 0)]
+scheds = [(-1, -1, -1, 0, -1)] if quick else [(-1, -1, -1, 0, -1), (0, 0, 84, 0, 90), (0, 0, 0, 0, 90), (0, 0, 80, 0, 84), (0, 0, 0, 0, 80), (0, 0, 60, 0, 86), (0, 0, 0, 0, 0), (90, 90, 90, 0, 90)]
 for sched in scheds:
     ms, ms_b, gr = timed(4096, sched, reps=3 if quick else 10)
     if base is None: base = gr
     print(f"N=4096 sched {sched}: fwd+bwd {ms:.4f} ms, backward {ms_b:.4f} ms, grads vs first rel diff {float((gr - base).norm() / base.norm()):.2e}", flush=True)
 for n in ((1000, 18944) if quick else (1000, 2048, 5376, 18944, 98304)):
-    ms, ms_b, gr = timed(n, (-1, -1, -1, 0), reps=4)
+    ms, ms_b, gr = timed(n, (-1, -1, -1, 0, -1), reps=4)
     print(f"N={n} default schedule: fwd+bwd {ms:.4f} ms, backward {ms_b:.4f} ms ({n / ms / 1e3:.2f} M rays/s), finite={bool(torch.isfinite(gr).all())}", flush=True)
-L.r2l_debug_set_dw_schedule(-1, -1, -1, 0)
+L.r2l_debug_set_dw_schedule(-1, -1, -1, 0, -1)
