@@ -293,7 +293,7 @@ def run_ours(args):
     achieved_tflops = BATCH * FWD_FLOP_PER_RAY / (k_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": "r2l_chain_kernel<kFwdTrain, half form> (4096 rays = 32 tiles, one CTA pair per tile: 64 CTAs, tcgen05 cta_group::2 M=128)", "achieved": achieved_tflops,
                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved_tflops / peaks["bf16_tflops"],
-                "traffic": 358.7e6, "traffic_source": "profiles/r1_summary.md: dram read+write of the forward train kernel at 4096 rays (ncu --set full)", "peak_source": peaks["source"], "kernel_ms": k_ms,
+                "traffic": 359.4e6, "traffic_source": "profiles/r1_summary.md section 2c: dram__bytes_read.sum + dram__bytes_write.sum of this kernel at 4096 rays (ncu --set full, profiles/r1_full_4096_raw.csv)", "peak_source": peaks["source"], "kernel_ms": k_ms,
                 "note": "algorithmic fp32 FLOPs; the kernel issues 3x that as bf16 MMAs (hi*hi+lo*hi+hi*lo) to meet the 1e-3 fp32 parity bar, and a 4096-ray batch (32 tiles of 128 rays, two SMs per tile) occupies 64 of 148 SMs"}
 
     # ---- the same kernel with every SM busy (148 tiles = 18,944 rays), inference form: kernel quality, not the metric ----
