@@ -78,6 +78,10 @@ def test_render_poses_golden(golden_pose, packed, flat_seed0):
     assert relerr(rgb.cpu().numpy(), g["rgb"]) < FWD_TOL
     orgb, _ = orc.render_poses(flat_seed0, g["c2w"], H, W, focal, 2.0, 6.0)
     assert relerr(rgb.cpu().numpy(), orgb) < FWD_TOL
+    # PSNR of our frames against the reference's own render (main.py:20 mse2psnr): > 70 dB, i.e. a PSNR measured against
+    # any ground truth moves by far less than the 0.05 dB BASELINE.json allows (no lego data on this box: SURVEY 8c)
+    mse = float(np.mean((rgb.cpu().numpy().astype(np.float64) - g["rgb"]) ** 2))
+    assert -10.0 * np.log10(mse) > 70.0
     # the uint8 frame is to8b of the float frame of the same launch, bit for bit; against the reference's uint8 frame a
     # value within the 1e-3 tolerance of an integer boundary may differ by one level
     assert np.array_equal(rgb8.cpu().numpy(), orc.to8b(rgb.cpu().numpy()))
@@ -91,6 +95,8 @@ def test_render_poses_golden(golden_pose, packed, flat_seed0):
     # only one output requested; a single [3,4] pose; a [4,4] pose
     only8 = ops.render_poses(packed, c2w[0], H, W, focal, g["z_vals"].tolist(), want_rgb=False, want_rgb8=True)
     assert only8[0] is None and torch.equal(only8[1][0], rgb8[0])
+    none = ops.render_poses(packed, c2w[:0], H, W, focal, g["z_vals"].tolist())[0]
+    assert none.shape == (0, H, W, 3)
     c44 = torch.cat([c2w[1], torch.tensor([[0., 0., 0., 1.]], device=DEV)], 0)
     assert torch.equal(ops.render_poses(packed, c44[None], H, W, focal, g["z_vals"].tolist())[0][0], rgb[1])
 
