@@ -139,9 +139,17 @@ class R2LTrainer:
         ops.adam_step_dev(flat, self.grads, self.exp_avg, self.exp_avg_sq, self.betas[0], self.betas[1], self.eps, self.d_hyper)
         ops.pack_weights(flat, out=self.packed)                 # operands of the next forward (training or rendering)
 
+    MAX_BATCH_SIZES = 4    # static buffer sets (and graphs) kept; a 4096-ray set is ~1 GB of saved operand images
+
     def _static_for(self, n):
         st = self._static.get(n)
+        if st is not None:
+            self._static[n] = self._static.pop(n)        # most recently used last
         if st is None:
+            while len(self._static) >= self.MAX_BATCH_SIZES:   # e.g. ragged last batches: drop the least recently used set
+                old = self._static.pop(next(iter(self._static)))
+                old["graph"] = None
+                del old
             dev = self.dev
             nf, nb, nw = ops.train_buffer_bytes(n)
             st = dict(o=torch.zeros((n, 3), device=dev), d=torch.zeros((n, 3), device=dev), t=torch.zeros((n, 3), device=dev),
