@@ -7,6 +7,6 @@ Everything is implemented in r2l_b200/ (B200-native kernels behind the C ABI); t
 Pickled checkpoints that name `model.nerf_raybased.NeRF_v3_2` (main.py:1534-1536) resolve to the classes here.
 """
 from r2l_b200.nerf_raybased import *  # noqa: F401,F403
-from r2l_b200.nerf_raybased import (Embedder, EncodedPoints, NeRF, NeRF_v3_2, PointSampler, PositionalEmbedder, batchify, device,  # noqa: F401
+from r2l_b200.nerf_raybased import (Embedder, EncodedPoints, NeRF, NeRF_v3_2, PointSampler, PositionalEmbedder, ResMLP, batchify, device,  # noqa: F401
                                     get_activation, get_embedder, img2mse, mse2psnr, raw2outputs, run_network, to8b,
                                     to_array, to_list, to_tensor)

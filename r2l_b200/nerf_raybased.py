@@ -240,6 +240,31 @@ def get_activation(act):
     raise NotImplementedError
 
 
+class ResMLP(nn.Module):
+    """The reference's residual block `x = body(x) * res_scale + x` with body = Linear, act, Linear (reference :443-465),
+    kept under its name for two reasons: pickled reference checkpoints (`ckpt['network_fn']`, main.py:1534-1536) contain
+    instances of it and must unpickle, and code that builds a block on its own keeps working.  NeRF_v3_2 does not execute
+    this module: its 43 blocks are fused in the chain kernel; a reference-pickled network is converted to the flat
+    parameter when it is unpickled (NeRF_v3_2.__setstate__)."""
+
+    def __init__(self, width, inact=nn.ReLU(True), outact=None, res_scale=1, n_learnable=2):
+        super().__init__()
+        m = [nn.Linear(width, width)]
+        for _ in range(n_learnable - 1):
+            if inact is not None:
+                m += [inact]
+            m += [nn.Linear(width, width)]
+        self.body = nn.Sequential(*m)
+        self.res_scale = res_scale
+        self.outact = outact
+
+    def forward(self, x):
+        x = self.body(x).mul(self.res_scale) + x
+        if self.outact is not None:
+            x = self.outact(x)
+        return x
+
+
 def _guard(args, input_dim, output_dim):
     """Dispatch guard: the kernels are specialised for the README configuration; anything else must raise
     rather than silently differ."""
@@ -278,6 +303,34 @@ class NeRF_v3_2(nn.Module):
         self.flat = nn.Parameter(init_flat_params())
         self._packed = None
         self._packed_version = None
+
+    def __setstate__(self, state):
+        """Unpickling.  A network pickled by the REFERENCE (`ckpt['network_fn']`, main.py:1534-1536) arrives as its module
+        tree (`head`, `body` = 43 ResMLP, `tail`) without a flat parameter: its tensors are gathered in state_dict order
+        into `flat`, the tree is dropped, and the configuration goes through the same dispatch guard as the constructor."""
+        super().__setstate__(state)
+        self.__dict__.setdefault("_packed", None)
+        self.__dict__.setdefault("_packed_version", None)
+        if "flat" in self._parameters:
+            return
+        mods = self._modules
+        if not all(k in mods for k in ("head", "body", "tail")):
+            raise RuntimeError("r2l_b200 NeRF_v3_2: unrecognised pickled state (neither a flat parameter nor head/body/tail)")
+        tree = nn.Module()
+        for k in ("head", "body", "tail"):
+            tree.add_module(k, mods[k])
+        sd = tree.state_dict()
+        layout = state_dict_layout()
+        if list(sd.keys()) != [n for n, _, _ in layout] or any(tuple(sd[n].shape) != tuple(sh) for n, sh, _ in layout):
+            raise NotImplementedError("r2l_b200 NeRF_v3_2: the pickled network is not the W256/D88 ResMLP configuration "
+                                      "(--netwidth 256 --netdepth 88 --trial.body_arch resmlp) the B200 kernels implement")
+        if getattr(self, "args", None) is not None:
+            _guard(self.args, getattr(self, "input_dim", IN_DIM), 3)
+        flat = torch.cat([sd[n].detach().reshape(-1).float() for n, _, _ in layout])
+        for k in ("head", "body", "tail"):
+            del self._modules[k]
+        self.register_parameter("flat", nn.Parameter(flat))
+        self.input_dim = getattr(self, "input_dim", IN_DIM)
 
     # ---- parameter views / checkpoint format ----
     def named_views(self):
