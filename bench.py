@@ -317,8 +317,10 @@ def run_ours(args):
                              "issued_frac": 3 * full_tflops / peaks["bf16_tflops"]}
 
     # ---- end to end through the public API, host buffers: pinned rays/targets -> device, one iteration, loss -> host ----
+    h9 = torch.cat([h_ro, h_rd, h_tg], dim=1).pin_memory()      # a batch as the ray-shard loader yields it: [N, 9] rows
+
     def step_e2e():
-        return trainer.step_host(h_ro, h_rd, h_tg)
+        return trainer.step_host(h9)
 
     for _ in range(3):
         step_e2e()
@@ -360,7 +362,7 @@ def run_ours(args):
                                    + (" (one CUDA graph replay)" if trainer.use_graph else " (eager launches)")},
                 "clocks": sampler.summary(), "gpu_launches": LAUNCHES_PER_STEP * args.steps,
                 "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": BATCH * 9 * 4, "d2h_bytes_per_step": 4,
-                        "api": "R2LTrainer.step_host: pinned host rays/targets -> device each step, one training iteration, loss read back to the host"},
+                        "api": "R2LTrainer.step_host: host batch of [N,9] ray-shard rows -> pinned staging -> device every step, one training iteration, loss read back to the host"},
                 "roofline": roofline}
         if cpu is not None:
             line["cpu_baseline"] = cpu
@@ -372,7 +374,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()

@@ -23,6 +23,8 @@ extern "C" {
 #define R2L_INPUT_RAYS 0 /* in0 = rays_o[N,3], in1 = rays_d[N,3]  (PointSampler.sample_train, nerf_raybased.py:114-126) */
 #define R2L_INPUT_PTS 1  /* in0 = pts[N,48]   (output of PointSampler.sample_*, :94-126)                       */
 #define R2L_INPUT_X 2    /* in0 = x[N,1008]   (output of PositionalEmbedder.__call__, :198-208)                 */
+#define R2L_INPUT_RAYS9 4 /* in0 = rays9[N,9] = (o | d | rgb) rows as the ray shards store them (utils/create_data.py:820-872,
+                           * main.py:1305-1311): o and d are read in place at stride 9, in1 is ignored                */
 
 const char* r2l_last_error(void);
 int r2l_abi_version(void);
@@ -124,15 +126,16 @@ int r2l_adam_hyper(double lr, double beta1, double beta2, int64_t step, float* h
 int r2l_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double beta1, double beta2,
                       double eps, const float* hyper, void* stream);
 
-/* loss[0] = loss_scale * sum((rgb - target)^2), grad_rgb = grad_scale * (rgb - target), per_ray_err[r] = mean_c (rgb - target)^2.
+/* loss[0] = loss_scale * sum((rgb - target)^2), grad_rgb = grad_scale * (rgb - target), per_ray_err[r] = mean_c (rgb - target)^2;
+ * target row r starts at target[r * target_stride] (3 for a [N,3] tensor, 9 with target = rays9 + 6 for shard rows).
  * With loss_scale = lw_rgb / (3 N) and grad_scale = 2 lw_rgb / (3 N_global) this is img2mse(rgb, target) * lw_rgb
  * (nerf_raybased.py:18, main.py:1377), the dL/drgb autograd derives from it, and the per-ray error the hard-example pool
  * sorts by (main.py:1411-1413), in one launch with no host sync.  grad_rgb / per_ray_err may be NULL.  scratch:
  * r2l_loss_scratch_bytes() bytes of device memory, zero before the first call (the kernel leaves it zero).  The sum is taken
  * in a fixed order: bit-reproducible. */
 size_t r2l_loss_scratch_bytes(void);
-int r2l_mse_loss_grad(const float* rgb, const float* target, int64_t n_rays, float grad_scale, float loss_scale, float* grad_rgb,
-                      float* per_ray_err, float* loss, void* scratch, void* stream);
+int r2l_mse_loss_grad(const float* rgb, const float* target, int64_t n_rays, int target_stride, float grad_scale, float loss_scale,
+                      float* grad_rgb, float* per_ray_err, float* loss, void* scratch, void* stream);
 
 /* Debug: device buffer [grid][8] of int64 cycle counters filled by the next r2l_forward calls (NULL = off):
  * [0] MMA wait on head A chunks, [1] on body A chunks, [2] on weight stages, [3] producer wait on free stages,

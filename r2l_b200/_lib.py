@@ -48,7 +48,7 @@ _PROTOTYPES = {
     "r2l_adam_hyper": (c_int, [c_double, c_double, c_double, c_int64, c_void_p]),
     "r2l_adam_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_void_p, c_void_p]),
     "r2l_loss_scratch_bytes": (c_size_t, []),
-    "r2l_mse_loss_grad": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "r2l_mse_loss_grad": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "r2l_debug_set_stats": (c_int, [c_void_p]),
     "r2l_set_pair_mode": (c_int, [c_int]),
     "r2l_set_deterministic": (c_int, [c_int]),

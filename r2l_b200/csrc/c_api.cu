@@ -139,9 +139,11 @@ namespace {
 int fill_inputs(r2l::ChainParams& p, const char* who, int input_kind, const float* in0, const float* in1,
                 const float* t_rand, const float* z_lo, const float* z_diff) {
   if (!in0) return fail("%s: null input pointer", who);
-  if (input_kind < 0 || input_kind > 2) return fail("%s: unknown input_kind", who);
-  if (input_kind == R2L_INPUT_RAYS && (!in1 || !z_lo)) return fail("%s: rays input needs in1 and z_lo", who);
-  if (t_rand && (input_kind != R2L_INPUT_RAYS || !z_diff)) return fail("%s: t_rand needs R2L_INPUT_RAYS and z_diff", who);
+  const bool rays = input_kind == R2L_INPUT_RAYS || input_kind == R2L_INPUT_RAYS9;
+  if ((input_kind < 0 || input_kind > 2) && input_kind != R2L_INPUT_RAYS9) return fail("%s: unknown input_kind", who);
+  if (input_kind == R2L_INPUT_RAYS && !in1) return fail("%s: rays input needs in1", who);
+  if (rays && !z_lo) return fail("%s: rays input needs z_lo", who);
+  if (t_rand && (!rays || !z_diff)) return fail("%s: t_rand needs a rays input kind and z_diff", who);
   p.in0 = in0;
   p.in1 = in1;
   p.t_rand = t_rand;
@@ -244,7 +246,7 @@ int r2l_backward(int input_kind, const void* packed, const float* rgb, const flo
   if (n_rays < 0) return fail("r2l_backward: %s", "negative n_rays");
   if (!packed || !rgb || !grad_rgb || !zf || !fwd_saved || !bwd_saved || !grads || !workspace)
     return fail("r2l_backward: %s", "null pointer");
-  if (input_kind < 0 || input_kind > 2) return fail("r2l_backward: %s", "unknown input_kind");
+  if ((input_kind < 0 || input_kind > 2) && input_kind != R2L_INPUT_RAYS9) return fail("r2l_backward: %s", "unknown input_kind");
   if (workspace_bytes < r2l_bwd_workspace_bytes(n_rays)) return fail("r2l_backward: %s", "workspace too small (see r2l_bwd_workspace_bytes)");
   if (misaligned(packed) || misaligned(workspace) || misaligned(fwd_saved) || misaligned(bwd_saved) || misaligned(zf) || misaligned(grads))
     return fail("r2l_backward: %s", "buffers must be 16-byte aligned");
@@ -425,11 +427,11 @@ int r2l_read_ray_shards(const char* const* paths, int n_paths, float* dst_host, 
 
 size_t r2l_loss_scratch_bytes(void) { return 1024; }
 
-int r2l_mse_loss_grad(const float* rgb, const float* target, int64_t n_rays, float grad_scale, float loss_scale, float* grad_rgb,
-                      float* per_ray_err, float* loss, void* scratch, void* stream) {
-  if (n_rays < 0) return fail("r2l_mse_loss_grad: %s", "negative n_rays");
+int r2l_mse_loss_grad(const float* rgb, const float* target, int64_t n_rays, int target_stride, float grad_scale, float loss_scale,
+                      float* grad_rgb, float* per_ray_err, float* loss, void* scratch, void* stream) {
+  if (n_rays < 0 || target_stride < 3) return fail("r2l_mse_loss_grad: %s", "negative n_rays or target_stride < 3");
   if (!loss || !scratch || (n_rays > 0 && (!rgb || !target))) return fail("r2l_mse_loss_grad: %s", "null pointer");
-  return check(r2l::launch_mse_loss_grad(rgb, target, n_rays, grad_scale, loss_scale, grad_rgb, per_ray_err, loss,
+  return check(r2l::launch_mse_loss_grad(rgb, target, n_rays, target_stride, grad_scale, loss_scale, grad_rgb, per_ray_err, loss,
                                          static_cast<float*>(scratch), (cudaStream_t)stream), "r2l_mse_loss_grad");
 }
 

@@ -607,6 +607,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
             o[c] = __ldg(p.in0 + grow * 3 + c);
             dd[c] = __ldg(p.in1 + grow * 3 + c);
           }
+        } else if (p.input_kind == kInputRays9 && valid) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            o[c] = __ldg(p.in0 + grow * 9 + c);
+            dd[c] = __ldg(p.in0 + grow * 9 + 3 + c);
+          }
         } else if (p.input_kind == kInputPose && valid) {
           // PointSampler.__init__ / sample_test (nerf_raybased.py:80-86, :94-99): dirs = [(i - W/2)/f, -(j - H/2)/f, -1],
           // rays_d[r] = sum_k dirs[k] c2w[r][k] (summed left to right), rays_o = c2w[:, 3]

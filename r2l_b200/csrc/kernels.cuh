@@ -11,7 +11,7 @@ enum ChainMode : int { kFwdInfer = 0, kFwdTrain = 1, kBwd = 2 };
 
 struct ChainParams {
   // forward inputs
-  const float* in0;       // rays_o[N,3] | pts[N,48] | x[N,1008] | c2w[P,3,4]
+  const float* in0;       // rays_o[N,3] | pts[N,48] | x[N,1008] | c2w[P,3,4] | rays9[N,9]
   const float* in1;       // rays_d[N,3] | unused
   const float* t_rand;    // [N,16] or nullptr (kInputRays only)
   float z_lo[kSamples];   // z_vals (no jitter) or `lower` (jitter)
@@ -101,7 +101,7 @@ cudaError_t launch_sample_pdf_merge(const float* z_vals, const float* weights, c
 cudaError_t launch_embed(const float* x, float* out, int64_t n, int dim, int L, int style, cudaStream_t stream);
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float w1, float beta2, float w2, float eps,
                         float step_size, float inv_bc2_sqrt, const float* hyper, cudaStream_t stream);
-cudaError_t launch_mse_loss_grad(const float* rgb, const float* target, int64_t n, float grad_scale, float loss_scale,
+cudaError_t launch_mse_loss_grad(const float* rgb, const float* target, int64_t n, int target_stride, float grad_scale, float loss_scale,
                                  float* grad_rgb, float* per_ray, float* loss, float* scratch, cudaStream_t stream);
 }  // namespace r2l
 #include <string>

@@ -94,6 +94,7 @@ enum InputKind : int {
   kInputRays = 0,  // rays_o[N,3], rays_d[N,3] (+ optional t_rand[N,16]); points and PE built in-kernel
   kInputPts = 1,   // pts[N,48] as returned by PointSampler.sample_*; PE built in-kernel
   kInputX = 2,     // x[N,1008] materialised PositionalEmbedder output
+  kInputRays9 = 4, // rays9[N,9] = (o | d | rgb) rows of a ray shard (utils/create_data.py:820-872): o, d read in place at stride 9
   kInputPose = 3,  // c2w[P,3,4] camera poses; ray r = pixel (r % (H W)) of pose r / (H W): PointSampler.sample_test in-kernel
 };
 

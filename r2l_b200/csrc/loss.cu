@@ -13,7 +13,7 @@ constexpr int kLossMaxBlocks = 128;
 // scratch: [kLossMaxBlocks] float partial sums, then one int ticket (must be zero before the first launch; the kernel
 // leaves it zero).  The last block to finish adds the partials in block order: the loss is bit-reproducible.
 __global__ void __launch_bounds__(kLossThreads) r2l_mse_loss_grad_kernel(const float* __restrict__ rgb, const float* __restrict__ target,
-                                                                        int64_t n, float grad_scale, float loss_scale,
+                                                                        int64_t n, int target_stride, float grad_scale, float loss_scale,
                                                                         float* __restrict__ grad_rgb, float* __restrict__ per_ray,
                                                                         float* __restrict__ loss, float* scratch) {
   __shared__ float warp_sums[kLossThreads / 32];
@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(kLossThreads) r2l_mse_loss_grad_kernel(const f
     float e = 0.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const float d = rgb[3 * r + c] - target[3 * r + c];
+      const float d = rgb[3 * r + c] - target[(int64_t)target_stride * r + c];
       if (grad_rgb) grad_rgb[3 * r + c] = d * grad_scale;
       e = fmaf(d, d, e);
     }
@@ -52,12 +52,12 @@ __global__ void __launch_bounds__(kLossThreads) r2l_mse_loss_grad_kernel(const f
   }
 }
 
-cudaError_t launch_mse_loss_grad(const float* rgb, const float* target, int64_t n, float grad_scale, float loss_scale,
+cudaError_t launch_mse_loss_grad(const float* rgb, const float* target, int64_t n, int target_stride, float grad_scale, float loss_scale,
                                  float* grad_rgb, float* per_ray, float* loss, float* scratch, cudaStream_t stream) {
   int64_t blocks = (n + kLossThreads - 1) / kLossThreads;
   if (blocks > kLossMaxBlocks) blocks = kLossMaxBlocks;
   if (blocks < 1) blocks = 1;
-  r2l_mse_loss_grad_kernel<<<(int)blocks, kLossThreads, 0, stream>>>(rgb, target, n, grad_scale, loss_scale, grad_rgb, per_ray, loss, scratch);
+  r2l_mse_loss_grad_kernel<<<(int)blocks, kLossThreads, 0, stream>>>(rgb, target, n, target_stride, grad_scale, loss_scale, grad_rgb, per_ray, loss, scratch);
   return cudaGetLastError();
 }
 

@@ -168,9 +168,10 @@ class RayShardLoader:
 
     next = __next__   # the reference calls trainloader.next() (main.py:1305)
 
-    def device_batches(self, device):
-        """Generator of (rays_o, rays_d, target) DEVICE tensors [N, 3] (column views of one [N, 9] device buffer); the copy of
-        the following batch runs on a side stream while the caller consumes the current one."""
+    def device_batches(self, device, packed: bool = False):
+        """Generator of (rays_o, rays_d, target) DEVICE tensors [N, 3] (column views of one [N, 9] device buffer) - or, with
+        packed=True, of the [N, 9] buffer itself (R2LTrainer.step_rays9 / the R2L_INPUT_RAYS9 kernels read the columns in
+        place); the copy of the following batch runs on a side stream while the caller consumes the current one."""
         device = torch.device(device)
         copy_stream = torch.cuda.Stream(device)
         dev_bufs = [torch.empty_like(self.buffers[0], device=device) for _ in range(2)]
@@ -191,7 +192,7 @@ class RayShardLoader:
             launch(slot ^ 1)
             torch.cuda.current_stream(device).wait_event(events[slot])
             d = dev_bufs[slot]
-            yield d[:, :3], d[:, 3:6], d[:, 6:9]
+            yield d if packed else (d[:, :3], d[:, 3:6], d[:, 6:9])
             consumed[slot].record(torch.cuda.current_stream(device))
             slot ^= 1
 

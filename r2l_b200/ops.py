@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 
-INPUT_RAYS, INPUT_PTS, INPUT_X = 0, 1, 2
+INPUT_RAYS, INPUT_PTS, INPUT_X, INPUT_RAYS9 = 0, 1, 2, 4
 NUM_PARAMS = 5917187
 N_SAMPLES = 16
 IN_DIM = 1008
@@ -66,30 +66,12 @@ def _workspace(device, nbytes: int) -> torch.Tensor:
 
 
 def forward(packed: torch.Tensor, *, rays_o=None, rays_d=None, z_vals=None, t_rand=None, z_lower=None,
-            z_diff=None, pts=None, x=None, out=None) -> torch.Tensor:
-    """rgb[N,3] for one of three input forms:
+            z_diff=None, pts=None, x=None, rays9=None, out=None) -> torch.Tensor:
+    """rgb[N,3] for one of four input forms:
        rays_o,rays_d (+ z_vals host 16-vector; or z_lower,z_diff,t_rand for the stratified jitter),
-       pts[N,48], or x[N,1008]."""
+       rays9[N,9] = (o | d | rgb) shard rows read in place (same z arguments), pts[N,48], or x[N,1008]."""
     L = _lib.lib()
-    zl = zd = None
-    if x is not None:
-        kind, in0, in1 = INPUT_X, _require_cuda_f32(x, "x", (IN_DIM,)), None
-    elif pts is not None:
-        kind, in0, in1 = INPUT_PTS, _require_cuda_f32(pts, "pts", (3 * N_SAMPLES,)), None
-    else:
-        kind = INPUT_RAYS
-        in0 = _require_cuda_f32(rays_o, "rays_o", (3,))
-        in1 = _require_cuda_f32(rays_d, "rays_d", (3,))
-        if in0.shape != in1.shape:
-            raise ValueError("rays_o / rays_d shape mismatch")
-        if t_rand is not None:
-            t_rand = _require_cuda_f32(t_rand, "t_rand", (N_SAMPLES,))
-            if t_rand.shape[0] != in0.shape[0]:
-                raise ValueError("t_rand: wrong number of rays")
-            zl = (ctypes.c_float * N_SAMPLES)(*[float(v) for v in z_lower])
-            zd = (ctypes.c_float * N_SAMPLES)(*[float(v) for v in z_diff])
-        else:
-            zl = (ctypes.c_float * N_SAMPLES)(*[float(v) for v in z_vals])
+    kind, in0, in1, t_rand, zl, zd = _resolve_inputs(rays_o, rays_d, z_vals, t_rand, z_lower, z_diff, pts, x, rays9)
     n = in0.shape[0]
     dev = in0.device
     if packed.device != dev:
@@ -167,18 +149,21 @@ def _pooled(device, tag: str, nbytes: int) -> torch.Tensor:
     return buf
 
 
-def _resolve_inputs(rays_o, rays_d, z_vals, t_rand, z_lower, z_diff, pts, x):
+def _resolve_inputs(rays_o, rays_d, z_vals, t_rand, z_lower, z_diff, pts, x, rays9=None):
     zl = zd = None
     if x is not None:
         kind, in0, in1 = INPUT_X, _require_cuda_f32(x, "x", (IN_DIM,)), None
     elif pts is not None:
         kind, in0, in1 = INPUT_PTS, _require_cuda_f32(pts, "pts", (3 * N_SAMPLES,)), None
     else:
-        kind = INPUT_RAYS
-        in0 = _require_cuda_f32(rays_o, "rays_o", (3,))
-        in1 = _require_cuda_f32(rays_d, "rays_d", (3,))
-        if in0.shape != in1.shape:
-            raise ValueError("rays_o / rays_d shape mismatch")
+        if rays9 is not None:
+            kind, in0, in1 = INPUT_RAYS9, _require_cuda_f32(rays9, "rays9", (9,)), None
+        else:
+            kind = INPUT_RAYS
+            in0 = _require_cuda_f32(rays_o, "rays_o", (3,))
+            in1 = _require_cuda_f32(rays_d, "rays_d", (3,))
+            if in0.shape != in1.shape:
+                raise ValueError("rays_o / rays_d shape mismatch")
         if t_rand is not None:
             t_rand = _require_cuda_f32(t_rand, "t_rand", (N_SAMPLES,))
             if t_rand.shape[0] != in0.shape[0]:
@@ -191,13 +176,13 @@ def _resolve_inputs(rays_o, rays_d, z_vals, t_rand, z_lower, z_diff, pts, x):
 
 
 def forward_train(packed: torch.Tensor, *, rays_o=None, rays_d=None, z_vals=None, t_rand=None, z_lower=None,
-                  z_diff=None, pts=None, x=None, keep: bool = False, fwd_saved: torch.Tensor | None = None,
+                  z_diff=None, pts=None, x=None, rays9=None, keep: bool = False, fwd_saved: torch.Tensor | None = None,
                   workspace: torch.Tensor | None = None):
     """Like forward(), but also returns the TrainContext for backward().  fwd_saved / workspace: caller-owned uint8 buffers
     (train_buffer_bytes(n)) instead of the per-device pools - what a captured CUDA graph needs, since pooled buffers may be
     re-allocated by a later, larger call."""
     L = _lib.lib()
-    kind, in0, in1, t_rand, zl, zd = _resolve_inputs(rays_o, rays_d, z_vals, t_rand, z_lower, z_diff, pts, x)
+    kind, in0, in1, t_rand, zl, zd = _resolve_inputs(rays_o, rays_d, z_vals, t_rand, z_lower, z_diff, pts, x, rays9)
     n, dev = in0.shape[0], in0.device
     ctx = TrainContext()
     ctx.kind, ctx.n = kind, n
@@ -398,7 +383,11 @@ def mse_loss_grad(rgb: torch.Tensor, target: torch.Tensor, grad_scale: float, lo
     (rgb - target), per_ray_err = mean over the 3 channels of (rgb - target)^2.  img2mse * lw_rgb (main.py:1377) is
     loss_scale = lw_rgb / (3 N), grad_scale = 2 lw_rgb / (3 N_global)."""
     rgb = _require_cuda_f32(rgb, "rgb", (3,))
-    target = _require_cuda_f32(target, "target", (3,))
+    if (isinstance(target, torch.Tensor) and target.is_cuda and target.dtype == torch.float32 and target.dim() == 2
+            and target.shape[1] == 3 and target.stride(1) == 1 and target.stride(0) >= 3):
+        t_stride = target.stride(0)       # e.g. the rgb columns of [N,9] shard rows, read in place
+    else:
+        target, t_stride = _require_cuda_f32(target, "target", (3,)), 3
     if rgb.shape != target.shape:
         raise ValueError("rgb / target shape mismatch")
     n, dev = rgb.shape[0], rgb.device
@@ -412,7 +401,7 @@ def mse_loss_grad(rgb: torch.Tensor, target: torch.Tensor, grad_scale: float, lo
     if scratch is None:
         scratch = _loss_scratch[dev.index] = torch.zeros(int(_lib.lib().r2l_loss_scratch_bytes()), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().r2l_mse_loss_grad(_ptr(rgb), _ptr(target), n, float(grad_scale), float(loss_scale), _ptr(grad_rgb),
+        _lib.check(_lib.lib().r2l_mse_loss_grad(_ptr(rgb), _ptr(target), n, int(t_stride), float(grad_scale), float(loss_scale), _ptr(grad_rgb),
                                                 _ptr(per_ray_err), _ptr(loss), _ptr(scratch), _stream()), "r2l_mse_loss_grad")
     return loss, grad_rgb, per_ray_err
 

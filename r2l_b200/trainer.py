@@ -116,21 +116,22 @@ class R2LTrainer:
         self.h_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
         self.pool = None
         self._static = {}     # n_rays -> dict(buffers, graph)
-        self._host = {}       # n_rays -> pinned staging of step_host
         self.last_lr = None
 
-    # ---- the device work of one iteration on static buffers (captured once per batch size) ----
-    def _body(self, st):
-        n = st["o"].shape[0]
+    # ---- the device work of one iteration on static buffers (captured once per batch size and entry point) ----
+    def _body(self, st, from_host: bool):
+        n = st["in9"].shape[0]
+        if from_host:     # host-fed iteration: the batch comes from the pinned staging rows, the loss goes back to the host
+            st["in9"][:st["h9"].shape[0]].copy_(st["h9"], non_blocking=True)
         self.d_hyper.copy_(self.h_hyper, non_blocking=True)
-        kw = dict(rays_o=st["o"], rays_d=st["d"])
+        kw = dict(rays9=st["in9"])                      # (o | d | rgb) rows: the kernels read the columns in place
         if st["t_rand"] is not None:
             kw.update(t_rand=st["t_rand"], z_lower=self.z_lower, z_diff=self.z_diff)
         else:
             kw.update(z_vals=self.z_vals)
         rgb, ctx = ops.forward_train(self.packed, fwd_saved=st["fwd_saved"], workspace=st["workspace"], **kw)
         n_global = n * self.world
-        ops.mse_loss_grad(rgb, st["t"], 2.0 * self.lw_rgb / (3 * n_global), self.lw_rgb / (3 * n), grad_rgb=st["grad_rgb"],
+        ops.mse_loss_grad(rgb, st["in9"][:, 6:9], 2.0 * self.lw_rgb / (3 * n_global), self.lw_rgb / (3 * n), grad_rgb=st["grad_rgb"],
                           per_ray_err=st["err"], loss=self.loss)
         ops.backward(self.packed, ctx, st["grad_rgb"], self.grads, bwd_saved=st["bwd_saved"], workspace=st["workspace"])
         if self.world > 1:
@@ -138,6 +139,8 @@ class R2LTrainer:
         flat = self.model.flat.data
         ops.adam_step_dev(flat, self.grads, self.exp_avg, self.exp_avg_sq, self.betas[0], self.betas[1], self.eps, self.d_hyper)
         ops.pack_weights(flat, out=self.packed)                 # operands of the next forward (training or rendering)
+        if from_host:
+            self.h_loss.copy_(self.loss, non_blocking=True)
 
     MAX_BATCH_SIZES = 4    # static buffer sets (and graphs) kept; a 4096-ray set is ~1 GB of saved operand images
 
@@ -148,32 +151,33 @@ class R2LTrainer:
         if st is None:
             while len(self._static) >= self.MAX_BATCH_SIZES:   # e.g. ragged last batches: drop the least recently used set
                 old = self._static.pop(next(iter(self._static)))
-                old["graph"] = None
+                old["graph"] = old["graph_host"] = None
                 del old
             dev = self.dev
             nf, nb, nw = ops.train_buffer_bytes(n)
-            st = dict(o=torch.zeros((n, 3), device=dev), d=torch.zeros((n, 3), device=dev), t=torch.zeros((n, 3), device=dev),
+            st = dict(in9=torch.zeros((n, 9), device=dev), h9=None,
                       fwd_saved=torch.empty(nf, dtype=torch.uint8, device=dev), bwd_saved=torch.empty(nb, dtype=torch.uint8, device=dev),
                       workspace=torch.empty(nw, dtype=torch.uint8, device=dev),
                       t_rand=torch.zeros((n, N_SAMPLES), device=dev) if self.perturb > 0 else None,
-                      grad_rgb=torch.empty((n, 3), device=dev), err=torch.empty(n, device=dev), graph=None, warm=0)
+                      grad_rgb=torch.empty((n, 3), device=dev), err=torch.empty(n, device=dev), graph=None, graph_host=None, warm=0)
             self._static[n] = st
         return st
 
-    def _run(self, st):
+    def _run(self, st, from_host=False):
         """Run the iteration body on the static buffers: eagerly twice (allocations, lazy CUDA init), then as a graph."""
         if not self.use_graph:
-            return self._body(st)
-        if st["graph"] is None:
+            return self._body(st, from_host)
+        key = "graph_host" if from_host else "graph"
+        if st[key] is None:
             if st["warm"] < 2:
                 st["warm"] += 1
-                return self._body(st)
+                return self._body(st, from_host)
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize(self.dev)
             with torch.cuda.graph(g):
-                self._body(st)
-            st["graph"] = g
-        st["graph"].replay()
+                self._body(st, from_host)
+            st[key] = g
+        st[key].replay()
 
     def _begin(self):
         step = self.global_step + 1
@@ -189,45 +193,61 @@ class R2LTrainer:
         self.model._packed = self.packed
         self.model._packed_version = (flat.data_ptr(), flat._version, str(flat.device))
 
-    @torch.no_grad()
-    def step(self, rays_o, rays_d, target, t_rand=None):
-        """One iteration on device tensors rays_o, rays_d, target [N,3].  Returns the loss as a 1-element device tensor
-        (no host sync; `float(loss)` when the caller wants the number).  perturb > 0 draws t_rand on the device unless given."""
+    def _iterate(self, batch, fill, from_host=False):
+        """Common part of the entry points: pool draw, static buffers of the batch size, `fill(st, batch)` puts the fresh rays
+        into rows [:batch] of the [n, 9] input buffer (or its pinned staging), the iteration, the pool update."""
         self._begin()
-        batch = rays_o.shape[0]
         if self.hard_ratio and self.pool is None:
             self.pool = HardRayPool(batch, self.hard_ratio, self.hard_mul, self.dev)
         extra = self.pool.draw() if self.pool is not None else None
         n = batch + (extra.shape[0] if extra is not None else 0)
         st = self._static_for(n)
-        st["o"][:batch].copy_(rays_o, non_blocking=True)      # device tensors, or pinned host tensors (step_host)
-        st["d"][:batch].copy_(rays_d, non_blocking=True)
-        st["t"][:batch].copy_(target, non_blocking=True)
+        fill(st, batch)
         if extra is not None:
-            st["o"][batch:].copy_(extra[:, :3]); st["d"][batch:].copy_(extra[:, 3:6]); st["t"][batch:].copy_(extra[:, 6:9])
+            st["in9"][batch:].copy_(extra)
         if st["t_rand"] is not None:
-            if t_rand is not None:
-                st["t_rand"].copy_(t_rand)
+            if st.get("t_rand_given") is not None:
+                st["t_rand"].copy_(st.pop("t_rand_given"))
             else:
                 st["t_rand"].uniform_()       # sample_train's torch.rand (nerf_raybased.py:122), drawn on the device
-        self._run(st)
+        self._run(st, from_host)
         if self.pool is not None:
-            self.pool.update(st["o"], st["d"], st["t"], st["err"])
+            self.pool.update(st["in9"][:, 0:3], st["in9"][:, 3:6], st["in9"][:, 6:9], st["err"])
         self._end()
         return self.loss
 
     @torch.no_grad()
-    def step_host(self, rays_o, rays_d, target):
-        """One iteration from HOST tensors [N,3] (a ray shard as the loader yields it): pinned staging, H2D copies, the
-        iteration, and the loss read back to the host.  Returns the loss as a float."""
-        n = rays_o.shape[0]
-        h = self._host.get(n)
-        if h is None:
-            h = self._host[n] = tuple(torch.empty((n, 3), dtype=torch.float32).pin_memory() for _ in range(3))
-        for dst, src in zip(h, (rays_o, rays_d, target)):
-            dst.copy_(src)
-        loss = self.step(*h)
-        self.h_loss.copy_(loss, non_blocking=True)
+    def step(self, rays_o, rays_d, target, t_rand=None):
+        """One iteration on device tensors rays_o, rays_d, target [N,3].  Returns the loss as a 1-element device tensor
+        (no host sync; `float(loss)` when the caller wants the number).  perturb > 0 draws t_rand on the device unless given."""
+        def fill(st, batch):
+            st["in9"][:batch, 0:3].copy_(rays_o, non_blocking=True)
+            st["in9"][:batch, 3:6].copy_(rays_d, non_blocking=True)
+            st["in9"][:batch, 6:9].copy_(target, non_blocking=True)
+            if t_rand is not None:
+                st["t_rand_given"] = t_rand
+        return self._iterate(rays_o.shape[0], fill)
+
+    @torch.no_grad()
+    def step_rays9(self, rays9):
+        """One iteration on a DEVICE batch of shard rows [N, 9] = (o | d | rgb), e.g. RayShardLoader.device_batches(packed=True):
+        one copy into the static input buffer, the kernels read the columns in place."""
+        return self._iterate(rays9.shape[0], lambda st, batch: st["in9"][:batch].copy_(rays9, non_blocking=True))
+
+    @torch.no_grad()
+    def step_host(self, rays_o, rays_d=None, target=None):
+        """One iteration from HOST tensors: either a [N, 9] batch of shard rows (RayShardLoader.next_buffer()) or the three
+        [N, 3] tensors.  The rows are staged in pinned memory; their H2D copy, the iteration and the D2H copy of the loss are
+        ONE graph replay, then the host waits for the loss.  Returns the loss as a float."""
+        def fill(st, batch):
+            if st["h9"] is None or st["h9"].shape[0] != batch:
+                st["h9"] = torch.empty((batch, 9), dtype=torch.float32).pin_memory()
+                st["graph_host"] = None               # the graph holds the staging address
+            if rays_d is None:
+                st["h9"].copy_(rays_o)
+            else:
+                st["h9"][:, 0:3].copy_(rays_o); st["h9"][:, 3:6].copy_(rays_d); st["h9"][:, 6:9].copy_(target)
+        self._iterate(rays_o.shape[0], fill, from_host=True)
         torch.cuda.current_stream(self.dev).synchronize()
         return float(self.h_loss[0])
 

@@ -103,13 +103,13 @@ def test_trainer_matches_the_reference_loop_on_cpu(flat_seed0):
 
 
 def test_trainer_graph_eager_and_host_paths_are_identical(flat_seed0):
-    """Bit-reproducible mode: the CUDA-graph replay, the eager launches and the host-fed entry point give the same
-    parameters and losses bit for bit."""
+    """Bit-reproducible mode: the CUDA-graph replay, the eager launches, the host-fed entry points and the packed [N,9] entry
+    point give the same parameters and losses bit for bit."""
     L = _lib.lib()
     L.r2l_set_deterministic(1)
     try:
         outs = []
-        for mode in ("eager", "graph", "host"):
+        for mode in ("eager", "graph", "host", "host9", "rays9"):
             model, ps = make_model(flat_seed0)
             tr = R2LTrainer(model, ps, use_graph=(mode != "eager"))
             losses = []
@@ -117,6 +117,10 @@ def test_trainer_graph_eager_and_host_paths_are_identical(flat_seed0):
                 o, d, t = rays(384, 10 + it)
                 if mode == "host":
                     losses.append(tr.step_host(o, d, t))
+                elif mode == "host9":
+                    losses.append(tr.step_host(torch.cat([o, d, t], 1)))
+                elif mode == "rays9":
+                    losses.append(float(tr.step_rays9(torch.cat([o, d, t], 1).to(DEV))))
                 else:
                     losses.append(float(tr.step(o.to(DEV), d.to(DEV), t.to(DEV))))
             assert tr.global_step == 5 and tr.adam_steps == 5
@@ -201,3 +205,24 @@ def test_training_from_ray_shards_reduces_the_loss(tmp_path, flat_seed0):
         ld.close()
     assert np.isfinite(losses).all() and losses[-1] < 0.1 * losses[0], (losses[0], losses[-1])
     assert tr.pool.full and set(tr._static) == {512, 614}        # 512 fresh rays + int(0.2 * 512) pool rays once full
+
+
+def test_rays9_rows_are_read_in_place(flat_seed0):
+    """R2L_INPUT_RAYS9: the (o | d | rgb) rows of a ray shard feed the forward and the loss without being split: bit-identical
+    to the split tensors."""
+    packed = ops.pack_weights(torch.from_numpy(flat_seed0).to(DEV))
+    o, d, t = rays(1000, 7)
+    rows = torch.cat([o, d, t], 1).to(DEV)
+    z = orc.sampler_z_vals(2.0, 6.0).tolist()
+    a = ops.forward(packed, rays_o=o.to(DEV), rays_d=d.to(DEV), z_vals=z)
+    b = ops.forward(packed, rays9=rows, z_vals=z)
+    assert torch.equal(a, b)
+    l1, g1, e1 = ops.mse_loss_grad(a, t.to(DEV), 0.01, 0.5, want_per_ray=True)
+    l2, g2, e2 = ops.mse_loss_grad(b, rows[:, 6:9], 0.01, 0.5, want_per_ray=True)
+    assert torch.equal(l1, l2) and torch.equal(g1, g2) and torch.equal(e1, e2)
+    rgb, ctx = ops.forward_train(packed, rays9=rows, z_vals=z)
+    assert torch.equal(rgb, a)
+    grads = ops.backward(packed, ctx, g2)
+    rgb0, ctx0 = ops.forward_train(packed, rays_o=o.to(DEV), rays_d=d.to(DEV), z_vals=z, keep=True)
+    grads0 = ops.backward(packed, ctx0, g1)
+    assert float((grads - grads0).norm() / grads0.norm()) < 1e-6

@@ -48,13 +48,12 @@ def main():
     ps = nb.PointSampler(400, 400, 555.5555155968841, 16, 2.0, 6.0)
     trainer = R2LTrainer(model, ps, lrate=a.lrate, lrate_decay=a.lrate_decay, warmup_lr=a.warmup_lr or None, hard_ratio=a.hard_ratio, hard_mul=a.hard_mul)
     loader = RayShardLoader(shards, a.N_rand, rows=a.rows, rank=rank, world=world, seed=1)
-    batches = loader.device_batches(dev)
+    batches = loader.device_batches(dev, packed=True)      # [N, 9] shard rows, read in place by the kernels
     t0, first = None, None
     for it in range(a.steps):
         if it == min(20, a.steps // 2):
             torch.cuda.synchronize(); t0, it0 = time.perf_counter(), it
-        rays_o, rays_d, target = next(batches)
-        loss = trainer.step(rays_o, rays_d, target)
+        loss = trainer.step_rays9(next(batches))
         if it % 50 == 0 or it == a.steps - 1:
             v = float(loss)
             first = v if first is None else first
