@@ -14,16 +14,29 @@ __device__ __forceinline__ void pack_tables(const float* __restrict__ params, ui
   float* b1 = reinterpret_cast<float*>(packed + kPackOffB1);
   float* tailw = reinterpret_cast<float*>(packed + kPackOffTailW);
   float* tailb = reinterpret_cast<float*>(packed + kPackOffTailB);
+  // every load first (independent, read-only path): the block's run time is one memory round trip, not 43
+  float b2[kBlocks], b1v[kBlocks];
+#pragma unroll
+  for (int k = 0; k < kBlocks; ++k) {
+    b2[k] = __ldg(params + off_body_b(2 * k + 1) + col);
+    b1v[k] = __ldg(params + off_body_b(2 * k) + col);
+  }
+  const float hb = __ldg(params + kOffHeadB + col);
+  float tw[kOutDim];
+#pragma unroll
+  for (int c = 0; c < kOutDim; ++c) tw[c] = __ldg(params + kOffTailW + c * kWidth + col);
   float acc = 0.f;
   cum[col] = 0.f;
+#pragma unroll
   for (int k = 0; k < kBlocks; ++k) {
-    acc = __fadd_rn(acc, params[off_body_b(2 * k + 1) + col]);
+    acc = __fadd_rn(acc, b2[k]);
     cum[(k + 1) * kWidth + col] = acc;
-    b1[k * kWidth + col] = params[off_body_b(2 * k) + col];
+    b1[k * kWidth + col] = b1v[k];
   }
-  headb[col] = params[kOffHeadB + col];
-  for (int c = 0; c < kOutDim; ++c) tailw[c * kWidth + col] = params[kOffTailW + c * kWidth + col];
-  if (col < 4) tailb[col] = col < kOutDim ? params[kOffTailB + col] : 0.f;
+  headb[col] = hb;
+#pragma unroll
+  for (int c = 0; c < kOutDim; ++c) tailw[c * kWidth + col] = tw[c];
+  if (col < 4) tailb[col] = col < kOutDim ? __ldg(params + kOffTailB + col) : 0.f;
 }
 
 // One thread = one 16-byte swizzle unit (8 consecutive k) of one (n-row) of one image PAIR (hi+lo).
