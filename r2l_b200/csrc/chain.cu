@@ -751,13 +751,17 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
           }
         };
         load_side(my_chunk(0));
+        const bool feeds_mma = !last;                     // the last epilogue of a tile produces no further GEMM input
+        const bool produces_chunk = feeds_mma || kIsBwd;  // backward's last output (d head pre-activation) is saved for dw
+        // The slot of my first chunk (0 or 1) was released by the store of the previous epilogue's NEXT chunk (store warp):
+        // that wait is paid here, while this layer's MMAs run, not between accumulator-complete and the first publish.
+        // (My later chunks stay where they are: slot 3 is only released by the store of THIS epilogue's chunk 0.)
+        if (produces_chunk) wait_saved(my_chunk(0), false);
         mbar_wait(bar(kBarAccFull), acc_phase);
         acc_phase ^= 1u;
         tc_fence_after_sync();
         const bool tr = p.trace != nullptr && pt == pair_id && warp == 4 && lane == 0;
         if (tr) p.trace[((int64_t)blockIdx.x * 5 + 2) * 96 + l] = clock64();
-        const bool feeds_mma = !last;                     // the last epilogue of a tile produces no further GEMM input
-        const bool produces_chunk = feeds_mma || kIsBwd;  // backward's last output (d head pre-activation) is saved for dw
         for (uint32_t cc = 0; cc < kMyChunks; ++cc) {
           const uint32_t c = my_chunk(cc);
           uint32_t r[16];
@@ -766,7 +770,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
           tmem_ld8(tacc + 16u * (g0 + 2), &r[8]);
           if (cc > 0) load_side(c);
           if (produces_chunk) {
-            wait_saved(c, false);
+            if (cc > 0) wait_saved(c, false);
             if constexpr (HALF) {
               if (feeds_mma) { arrive_unit(c, 1 - g0); arrive_unit(c, 3 - g0); }   // the k-steps of this chunk I do not write
             } else {
