@@ -461,11 +461,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
   } else if (warp == 3) {
     // ======================= operand-image store warp (train / bwd) =======================
     if (kSave && lane == 0) {
-      // A chunk's slot is released (kBarASaved) once its store has finished READING shared memory, which we learn when at
-      // most one younger bulk group is still pending, i.e. right after the NEXT chunk's store was issued.  The epilogue
-      // rewrites a slot four chunks after it published it, so the release is always at least two chunks early and the
-      // epilogue never waits for this warp (a longer lag would: with "3 younger groups" the slot of chunk c + 1 was only
-      // released by the store of chunk c of the same layer - a store-warp round trip between any two chunks).
+      // A chunk's slot is released (kBarASaved) once its store has finished READING shared memory: this warp waits for
+      // exactly that (bulk wait_group.read 0, a few hundred cycles for 16-32 KiB) right after issuing the store - it has
+      // nothing else to do until the next chunk is published - so every release follows its publish promptly and depends
+      // on nothing younger.  The epilogue rewrites a slot a whole layer later and pays its (already satisfied) waits
+      // while the layer's MMAs run.
       uint32_t a_phase = 0;
       int64_t issued = 0;
       const bool signal = kIsBwd && p.ready != nullptr;
@@ -491,10 +491,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
             bulk_s2g(dst + (int64_t)i * kAChunkBytes, smem_base + kSmemA + slot * kSlotBytes, kAChunkBytes);
           }
           bulk_commit();
-          if (issued >= 1) {
-            bulk_wait_read<1>();         // store (issued - 1) has read its slot
-            mbar_arrive(bar(kBarASaved + ((slot + 3) & 3)));
-          }
+          bulk_wait_read<0>();           // this store has read its slot
+          mbar_arrive(bar(kBarASaved + slot));
           if (signal && tile < p.num_tiles && slot == 3) {
             // everything but the 4 stores just issued has landed in global memory: announce those groups so the
             // weight-gradient kernel (running concurrently on idle SMs) may start on their layers
@@ -507,9 +505,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
           for (; signalled < kSavedChunksPerTile / 4; ++signalled) flag_release_add(p.ready + signalled);
         }
       }
-      // drain: release the last slot, then wait for the writes to land
-      bulk_wait_read<0>();
-      if (issued >= 1) mbar_arrive(bar(kBarASaved + (uint32_t)((issued - 1) & 3)));
+      // drain: wait for the writes to land
       bulk_wait_all<0>();
     }
   } else if (warp >= 4) {
@@ -753,10 +749,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
         load_side(my_chunk(0));
         const bool feeds_mma = !last;                     // the last epilogue of a tile produces no further GEMM input
         const bool produces_chunk = feeds_mma || kIsBwd;  // backward's last output (d head pre-activation) is saved for dw
-        // The slot of my first chunk (0 or 1) was released by the store of the previous epilogue's NEXT chunk (store warp):
-        // that wait is paid here, while this layer's MMAs run, not between accumulator-complete and the first publish.
-        // (My later chunks stay where they are: slot 3 is only released by the store of THIS epilogue's chunk 0.)
-        if (produces_chunk) wait_saved(my_chunk(0), false);
+        // The slots I am about to rewrite were released right after the previous epilogue published them (store warp):
+        // those waits are paid here, while this layer's MMAs run, not between accumulator-complete and the publishes.
+        if (produces_chunk) {
+#pragma unroll
+          for (uint32_t cc = 0; cc < kMyChunks; ++cc) wait_saved(my_chunk(cc), false);
+        }
         mbar_wait(bar(kBarAccFull), acc_phase);
         acc_phase ^= 1u;
         tc_fence_after_sync();
@@ -770,7 +768,6 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
           tmem_ld8(tacc + 16u * (g0 + 2), &r[8]);
           if (cc > 0) load_side(c);
           if (produces_chunk) {
-            if (cc > 0) wait_saved(c, false);
             if constexpr (HALF) {
               if (feeds_mma) { arrive_unit(c, 1 - g0); arrive_unit(c, 3 - g0); }   // the k-steps of this chunk I do not write
             } else {
