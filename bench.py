@@ -242,8 +242,10 @@ def run_ours(args):
     n_global = BATCH * world
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
+    d9 = torch.cat([d_ro, d_rd, d_tg], dim=1).contiguous()      # a device batch as the ray-shard loader yields it: [N, 9] rows
+
     def step_device():
-        trainer.step(d_ro, d_rd, d_tg)
+        trainer.step_rays9(d9)
     # forward chain, loss+grad, backward chain, tail gradients, weight gradients, Adam, pack
     LAUNCHES_PER_STEP = 7
 
@@ -358,7 +360,7 @@ def run_ours(args):
                 "config": {"workload": WORKLOAD, "rays_per_gpu": BATCH, "global_batch": n_global,
                            "parallelism": f"dp{world}" if world > 1 else "single",
                            "l2": "256 MiB buffer written between timed iterations (L2 flush, untimed)",
-                           "step": "R2LTrainer.step: forward_train + mse loss/grad + backward(chain, dW, tail) + allreduce(N>1) + Adam + pack_weights"
+                           "step": "R2LTrainer.step_rays9 on a resident [N,9] batch: forward_train + mse loss/grad + backward(chain, dW, tail) + allreduce(N>1) + Adam + pack_weights"
                                    + (" (one CUDA graph replay)" if trainer.use_graph else " (eager launches)")},
                 "clocks": sampler.summary(), "gpu_launches": LAUNCHES_PER_STEP * args.steps,
                 "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": BATCH * 9 * 4, "d2h_bytes_per_step": 4,
