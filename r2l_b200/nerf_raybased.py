@@ -249,20 +249,18 @@ class ResMLP(nn.Module):
 
     def __init__(self, width, inact=nn.ReLU(True), outact=None, res_scale=1, n_learnable=2):
         super().__init__()
-        m = [nn.Linear(width, width)]
-        for _ in range(n_learnable - 1):
-            if inact is not None:
-                m += [inact]
-            m += [nn.Linear(width, width)]
-        self.body = nn.Sequential(*m)
-        self.res_scale = res_scale
-        self.outact = outact
+        # body = Linear (act Linear)*: with an activation the Linears sit at indices 0, 2, 4, ... (state_dict keys body.{0,2}.*)
+        layers = []
+        for i in range(n_learnable):
+            if i > 0 and inact is not None:
+                layers.append(inact)
+            layers.append(nn.Linear(width, width))
+        self.body = nn.Sequential(*layers)
+        self.res_scale, self.outact = res_scale, outact
 
     def forward(self, x):
-        x = self.body(x).mul(self.res_scale) + x
-        if self.outact is not None:
-            x = self.outact(x)
-        return x
+        y = self.body(x).mul(self.res_scale) + x
+        return y if self.outact is None else self.outact(y)
 
 
 def _guard(args, input_dim, output_dim):
