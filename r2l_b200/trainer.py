@@ -54,9 +54,8 @@ class HardRayPool:
         self.capacity = int(batch_size * hard_mul)
         self.batch_size = batch_size
         # appended in steps of n_hard_in until >= capacity (main.py:1423-1425)
-        slots = 0
-        while slots < self.capacity:
-            slots += max(self.n_hard_in, 1)
+        step = max(self.n_hard_in, 1)
+        slots = -(-self.capacity // step) * step
         self.rays = torch.empty((slots, 9), dtype=torch.float32, device=device)
         self.size = 0
         self.full = False
@@ -206,10 +205,10 @@ class R2LTrainer:
         if extra is not None:
             st["in9"][batch:].copy_(extra)
         if st["t_rand"] is not None:
-            if st.get("t_rand_given") is not None:
-                st["t_rand"].copy_(st.pop("t_rand_given"))
-            else:
-                st["t_rand"].uniform_()       # sample_train's torch.rand (nerf_raybased.py:122), drawn on the device
+            st["t_rand"].uniform_()           # sample_train's torch.rand (nerf_raybased.py:122), drawn on the device
+            given = st.pop("t_rand_given", None)
+            if given is not None:             # the caller's uniforms for the fresh rays (pool rays keep device draws)
+                st["t_rand"][:batch].copy_(given)
         self._run(st, from_host)
         if self.pool is not None:
             self.pool.update(st["in9"][:, 0:3], st["in9"][:, 3:6], st["in9"][:, 6:9], st["err"])
@@ -220,6 +219,9 @@ class R2LTrainer:
     def step(self, rays_o, rays_d, target, t_rand=None):
         """One iteration on device tensors rays_o, rays_d, target [N,3].  Returns the loss as a 1-element device tensor
         (no host sync; `float(loss)` when the caller wants the number).  perturb > 0 draws t_rand on the device unless given."""
+        if t_rand is not None and not self.perturb > 0:
+            raise ValueError("R2LTrainer.step: t_rand given but the trainer was built with perturb = 0")
+
         def fill(st, batch):
             st["in9"][:batch, 0:3].copy_(rays_o, non_blocking=True)
             st["in9"][:batch, 3:6].copy_(rays_d, non_blocking=True)
