@@ -357,3 +357,26 @@ def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):
     bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
     p = p - (lr / bc1) * (m / (np.sqrt(v) / np.sqrt(bc2) + eps))
     return p, m, v
+
+
+# ------------------------------------------------------------------------------------------------
+# camera poses and rays of the pseudo-data generator (dataset/load_blender.py:10-28,:359-368; get_rays)
+# ------------------------------------------------------------------------------------------------
+def pose_spherical(theta: float, phi: float, radius: float) -> np.ndarray:
+    """dataset/load_blender.py:10-28 — camera-to-world [4,4] of a camera on a sphere looking at the origin; every factor is a
+    float32 matrix (torch.Tensor(...)) and the products are float32 matmuls, as in the reference."""
+    f = np.float32
+    t = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, radius], [0, 0, 0, 1]], f)
+    ph, th = phi / 180. * np.pi, theta / 180. * np.pi
+    rp = np.array([[1, 0, 0, 0], [0, np.cos(ph), -np.sin(ph), 0], [0, np.sin(ph), np.cos(ph), 0], [0, 0, 0, 1]], f)
+    rt = np.array([[np.cos(th), 0, -np.sin(th), 0], [0, 1, 0, 0], [np.sin(th), 0, np.cos(th), 0], [0, 0, 0, 1]], f)
+    flip = np.array([[-1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], f)
+    return (flip @ (rt @ (rp @ t))).astype(f)
+
+
+def get_rays(H: int, W: int, focal: float, c2w: np.ndarray):
+    """utils/run_nerf_raybased_helpers.py:231-257 (no origin translation) — rays_o, rays_d [H,W,3]: the same directions and
+    rotation as PointSampler (model/nerf_raybased.py:80-86,:95-99)."""
+    dirs = sampler_dirs(H, W, focal, c2w.dtype.type)
+    rays_d = np.sum(dirs[..., None, :] * c2w[:3, :3], axis=-1)
+    return np.broadcast_to(c2w[:3, -1], rays_d.shape).copy(), rays_d

@@ -244,8 +244,27 @@ def make_pose():
     print("pose_seed0.npz written:", out["rgb"].shape, out["rgb8"].dtype, out["rgb8"].reshape(-1, 3)[:3])
 
 
+def make_camera():
+    """camera_seed0.npz: pose_spherical (dataset/load_blender.py:10-28; the module itself needs imageio, so its pose lines are
+    executed from source) for a few angles, and get_rays (utils/run_nerf_raybased_helpers.py:231-257) on one of the poses."""
+    _, helpers = import_reference()
+    src = open(os.path.join(REF, "dataset", "load_blender.py")).read()
+    ns = {"torch": torch, "np": np}
+    exec(src[src.index("trans_t = lambda"):src.index("def load_blender_data")], ns)
+    angles = np.array([[30., -40.], [-170., -5.], [0., -90.], [123.456, -67.89], [-1e-3, -1e-3]])
+    c2w = np.stack([ns["pose_spherical"](float(t), float(p), 4.0).numpy() for t, p in angles])
+    H, W, focal = 5, 7, 9.5
+    helpers.device = torch.device("cpu")
+    rays_o, rays_d = helpers.get_rays(H, W, focal, torch.from_numpy(c2w[3][:3, :4]))
+    np.savez_compressed(os.path.join(HERE, "camera_seed0.npz"), angles=angles, radius=np.float64(4.0), c2w=c2w, H=np.int64(H),
+                        W=np.int64(W), focal=np.float64(focal), rays_o=rays_o.numpy(), rays_d=rays_d.numpy())
+    print("camera_seed0.npz written:", c2w.shape, rays_d.shape)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "camera"):
+        make_camera()
     if which in ("all", "main"):
         main()
     if which in ("all", "pose"):

@@ -1,6 +1,8 @@
 """GPU tests (run on the B200 with `-m gpu`) of the training-loop rows: loss + gradient kernel, Adam with device-side
 step scalars, the R2LTrainer iteration (eager, CUDA graph, host-fed, hard-ray pool) and the ray-shard loader's device
 path.  The checker is the oracle (numpy / stock torch ops on the CPU); tolerances are stated at each assertion."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -226,3 +228,33 @@ def test_rays9_rows_are_read_in_place(flat_seed0):
     rgb0, ctx0 = ops.forward_train(packed, rays_o=o.to(DEV), rays_d=d.to(DEV), z_vals=z, keep=True)
     grads0 = ops.backward(packed, ctx0, g1)
     assert float((grads - grads0).norm() / grads0.norm()) < 1e-6
+
+
+def test_pseudo_data_generation_writes_teacher_rendered_shards(tmp_path):
+    """BASELINE config 4 in miniature: random poses -> teacher render (coarse + fine) -> (o | d | rgb) rows -> shards;
+    a frame's rows equal the teacher pipeline's own render of the same rays, and the shards feed the loader."""
+    from r2l_b200 import data as rd
+    from r2l_b200 import pseudo_data as pd
+    from r2l_b200 import render as rr
+    nb.device = torch.device(DEV)
+    torch.manual_seed(0)
+    coarse = nb.NeRF(8, 256, 63, 27, 4, [4], True).to(DEV)
+    fine = nb.NeRF(8, 256, 63, 27, 4, [4], True).to(DEV)
+    H, W, focal = 12, 16, 20.0
+    pose = pd.pose_spherical(30., -40., 4.0)
+    rows = pd.render_pseudo_frame(pose, H, W, focal, coarse, fine, N_samples=16, N_importance=24)
+    assert rows.shape == (H * W, 9) and bool(torch.isfinite(rows).all())
+    want_o, want_d = orc.get_rays(H, W, focal, pose.numpy()[:3, :4])
+    np.testing.assert_allclose(rows[:, 0:3].cpu().numpy(), want_o.reshape(-1, 3), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(rows[:, 3:6].cpu().numpy(), want_d.reshape(-1, 3), rtol=0, atol=1e-6)
+    assert float(rows[:, 6:9].min()) >= 0.0 and float(rows[:, 6:9].max()) <= 1.0 + 1e-5       # white_bkgd composite of sigmoids
+    n = pd.generate_pseudo_data(coarse, fine, str(tmp_path), n_pose=3, H=H, W=W, focal=focal, i_save=2, split_size=64, seed=1,
+                                N_samples=16, N_importance=24)
+    # 2 frames = 384 rows -> 6 shards, then 1 frame = 192 rows -> 3 shards; numbering continues
+    assert n == 9 and sorted(os.listdir(tmp_path), key=lambda s: int(s[5:-4])) == [f"data_{k}.npy" for k in range(1, 10)]
+    ld = rd.RayShardLoader([str(tmp_path / f"data_{k}.npy") for k in range(1, 10)], shards_per_batch=3, rows=64)
+    try:
+        o, d, t = ld.next()
+        assert o.shape == (192, 3) and abs(float(o.norm(dim=1).mean()) - 4.0) < 1e-4      # camera centres on the radius-4 sphere
+    finally:
+        ld.close()

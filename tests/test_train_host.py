@@ -125,3 +125,27 @@ def test_hard_ray_pool_follows_the_reference_update():
         assert pool.full == ref_full and pool.size == ref_rays.shape[0]
         assert np.array_equal(pool.rays[:pool.size].numpy(), ref_rays)
     assert pool.full
+
+
+def test_camera_poses_and_rays_match_the_reference(tmp_path):
+    """pose_spherical / get_rays of the pseudo-data generator against outputs of the reference's own functions
+    (tests/golden/camera_seed0.npz, made by make_golden.py), for the oracle and for the product's host glue."""
+    from r2l_b200 import pseudo_data as pd
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "camera_seed0.npz")))
+    for (theta, phi), want in zip(g["angles"], g["c2w"]):
+        np.testing.assert_allclose(orc.pose_spherical(theta, phi, float(g["radius"])), want, rtol=0, atol=3e-7)
+        assert np.array_equal(pd.pose_spherical(float(theta), float(phi), float(g["radius"])).numpy(), want)
+    H, W, focal = int(g["H"]), int(g["W"]), float(g["focal"])
+    c2w = g["c2w"][3][:3, :4]
+    ro, rd = orc.get_rays(H, W, focal, c2w)
+    np.testing.assert_allclose(rd, g["rays_d"], rtol=0, atol=2e-7)
+    assert np.array_equal(ro, g["rays_o"])
+    tro, trd = pd.get_rays(H, W, focal, torch.from_numpy(c2w))
+    assert np.array_equal(trd.numpy(), g["rays_d"]) and np.array_equal(tro.numpy(), g["rays_o"])
+    # random poses: on the radius-4 sphere, upper hemisphere, reproducible from a seeded generator
+    rng = np.random.RandomState(0)
+    poses = [pd.get_rand_pose(rng).numpy() for _ in range(20)]
+    for p in poses:
+        assert abs(np.linalg.norm(p[:3, 3]) - 4.0) < 1e-5 and p[2, 3] >= -1e-6
+        np.testing.assert_allclose(p[:3, :3] @ p[:3, :3].T, np.eye(3), atol=1e-6)
+    assert np.array_equal(pd.get_rand_pose(np.random.RandomState(0)).numpy(), poses[0])
