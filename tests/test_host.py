@@ -141,3 +141,30 @@ def test_trainer_refuses_cpu_models():
     nb.device = torch.device("cpu")
     with pytest.raises(RuntimeError, match="CUDA"):
         R2LTrainer(m, nb.PointSampler(8, 8, 10.0, 16, 2.0, 6.0))
+
+
+def test_header_is_plain_c():
+    """The drop-in boundary is a C ABI: include/r2l_b200.h must compile as C99 on its own (no C++, no torch, no CUDA types)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    res = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c",
+                          os.path.join(ROOT, "include", "r2l_b200.h")], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    # and a C translation unit can call through it (link against the built library)
+    src = os.path.join(ROOT, "tests", "_abi_probe.c")
+    with open(src, "w") as f:
+        f.write('#include "../include/r2l_b200.h"\n#include <stdio.h>\nint main(void) { printf("%d %zu\\n", r2l_abi_version(), r2l_packed_bytes());'
+                ' return r2l_forward(7, 0, 0, 0, 0, 0, 0, 0, 0, 0, 5, 0) != 0 && r2l_last_error()[0] ? 0 : 1; }\n')
+    exe = os.path.join(ROOT, "tests", "_abi_probe")
+    try:
+        res = subprocess.run([gcc, "-std=c99", src, "-o", exe, "-L" + _lib.CSRC, "-lr2l_b200", "-Wl,-rpath," + _lib.CSRC], capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
+        run = subprocess.run([exe], capture_output=True, text=True)
+        assert run.returncode == 0 and run.stdout.split()[0] == "1", (run.stdout, run.stderr)
+    finally:
+        for p in (src, exe):
+            if os.path.exists(p):
+                os.remove(p)
