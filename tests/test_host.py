@@ -190,3 +190,23 @@ def test_bench_reference_arm_prints_the_contract_line():
     other = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1"], capture_output=True, text=True,
                            env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"), timeout=600)
     assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+def test_bench_synthetic_rays_follow_the_reference_camera_model():
+    """bench.py's synthetic batch = a seeded subset of the pixels of pose_spherical(theta, phi, 4) seen through get_rays at
+    400x400, focal 555.56, checked against the oracle's restatement of those reference functions."""
+    import importlib.util
+    from oracle import r2l_oracle as orc
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    ro, rd, tg = bench.synthetic_rays(4096, seed=3)
+    assert ro.shape == rd.shape == tg.shape == (4096, 3) and ro.dtype == rd.dtype == tg.dtype == np.float32
+    rng = np.random.RandomState(3)
+    theta, phi = rng.uniform(-180, 180), rng.uniform(-90, 0)
+    c2w = orc.pose_spherical(theta, phi, 4.0)
+    pix = rng.choice(400 * 400, size=4096, replace=False)
+    want_o, want_d = orc.get_rays(400, 400, 555.5555155968841, c2w[:3, :4])
+    np.testing.assert_allclose(rd, want_d.reshape(-1, 3)[pix], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(ro, want_o.reshape(-1, 3)[pix], rtol=0, atol=2e-6)
+    assert abs(np.linalg.norm(ro[0]) - 4.0) < 1e-5 and 0.0 <= tg.min() and tg.max() < 1.0
