@@ -1,16 +1,20 @@
 """CPU emulation of the kernels' split arithmetic (TEST INFRASTRUCTURE ONLY, same rules as r2l_oracle.py).
 
-The chain kernels compute every Linear as three bf16 tensor-core products with fp32 accumulation,
-    a . w  ~=  a_hi . w_hi + a_lo . w_hi + a_hi . w_lo,      x_hi = bf16(x), x_lo = bf16(x - x_hi)
-(chain.cu; DESIGN.md section 4 "Precision").  This module restates that arithmetic in numpy so that the precision claim
-- three products meet the 1e-3 bar of BASELINE.json with a wide margin, one bf16 product does not - is checked on the CPU,
-independently of the GPU (tests/test_oracle.py).  Network structure: model/nerf_raybased.py:443-465,:539-544 as in
-r2l_oracle.r2l_forward."""
+The chain kernels compute every Linear as three fp16 tensor-core products with fp32 accumulation,
+    a . w  ~=  (a_hi . W_hi + a_lo . W_hi + a_hi . W_lo) / s,    W = s w,  x_hi = fp16(x), x_lo = fp16(x - x_hi)
+with the power-of-two weight scale s = WEIGHT_SCALE (ptx.cuh: kWeightScale; chain.cu; DESIGN.md section 4 "Precision"),
+and the backward pass runs on loss_scale * dL/d(.) (dw.cu: r2l_bwd_prep_kernel).  This module restates that arithmetic in
+numpy so that the precision claims - three products meet the 1e-3 bar of BASELINE.json with a wide margin, one product
+does not; the gradients are as accurate as plain fp32 arithmetic - are checked on the CPU, independently of the GPU
+(tests/test_oracle.py).  `fmt="bf16"` keeps round 1's format for comparison (tools/cpu_*_precision_study.py).
+Network structure: model/nerf_raybased.py:443-465,:539-544 as in r2l_oracle.r2l_forward."""
 from __future__ import annotations
 
 import numpy as np
 
 from . import r2l_oracle as orc
+
+WEIGHT_SCALE = 64.0     # ptx.cuh: kWeightScale
 
 
 def to_bf16(x: np.ndarray) -> np.ndarray:
@@ -20,33 +24,108 @@ def to_bf16(x: np.ndarray) -> np.ndarray:
     return rounded.view(np.float32)
 
 
-def split(x: np.ndarray):
-    hi = to_bf16(x)
-    return hi, to_bf16(x.astype(np.float32) - hi)
+def to_fp16(x: np.ndarray) -> np.ndarray:
+    """Round-to-nearest-even to IEEE half (gradual underflow, as cvt.rn.f16x2.f32 does), returned as float32."""
+    return np.asarray(x, np.float32).astype(np.float16).astype(np.float32)
 
 
-def split_linear(a: np.ndarray, w: np.ndarray, terms: int = 3) -> np.ndarray:
-    """a [N,K] @ w[O,K]^T with `terms` of the three split products (1: hi.hi only), fp32 accumulation."""
-    a_hi, a_lo = split(a)
-    w_hi, w_lo = split(w)
-    out = a_hi @ w_hi.T
+_ROUND = {"fp16": to_fp16, "bf16": to_bf16}
+
+
+def split(x: np.ndarray, fmt: str = "fp16"):
+    rnd = _ROUND[fmt]
+    hi = rnd(x)
+    return hi, rnd(np.asarray(x, np.float32) - hi)
+
+
+def split_matmul(a: np.ndarray, b: np.ndarray, terms: int = 3, fmt: str = "fp16", b_scale: float = 1.0) -> np.ndarray:
+    """a [M,K] @ b [K,N] with `terms` of the three split products (1: hi.hi only), fp32 accumulation; b is packed as
+    b_scale * b and the result divided by b_scale (exact for powers of two)."""
+    s = np.float32(b_scale)
+    a_hi, a_lo = split(a, fmt)
+    b_hi, b_lo = split(np.asarray(b, np.float32) * s, fmt)
+    out = a_hi @ b_hi
     if terms >= 2:
-        out = out + a_lo @ w_hi.T
+        out = out + a_lo @ b_hi
     if terms >= 3:
-        out = out + a_hi @ w_lo.T
-    return out.astype(np.float32)
+        out = out + a_hi @ b_lo
+    return (out / s).astype(np.float32)
 
 
-def r2l_forward_split(flat: np.ndarray, x: np.ndarray, terms: int = 3) -> np.ndarray:
+def split_linear(a: np.ndarray, w: np.ndarray, terms: int = 3, fmt: str = "fp16", w_scale: float | None = None) -> np.ndarray:
+    """a [N,K] @ w[O,K]^T as the chain kernels do it."""
+    if w_scale is None:
+        w_scale = WEIGHT_SCALE if fmt == "fp16" else 1.0
+    return split_matmul(a, np.asarray(w).T, terms, fmt, w_scale)
+
+
+def r2l_forward_split(flat: np.ndarray, x: np.ndarray, terms: int = 3, fmt: str = "fp16", w_scale: float | None = None) -> np.ndarray:
     """r2l_oracle.r2l_forward with every body/head product done as the kernels do it (the 3-wide tail stays fp32, as in
     the kernels' CUDA-core tail)."""
     p = orc.unflatten_params(flat.astype(np.float32))
     x = x.astype(np.float32)
-    h = np.maximum(split_linear(x, p["head_w"], terms) + p["head_b"], 0)
+    lin = lambda a, w: split_linear(a, w, terms, fmt, w_scale)
+    h = np.maximum(lin(x, p["head_w"]) + p["head_b"], 0)
     z = h
     for k in range(orc.N_BLOCKS):
         (w1, b1), (w2, b2) = p["body"][2 * k], p["body"][2 * k + 1]
-        a = np.maximum(split_linear(z, w1, terms) + b1, 0)
-        z = (split_linear(a, w2, terms) + b2) + z
+        a = np.maximum(lin(z, w1) + b1, 0)
+        z = (lin(a, w2) + b2) + z
     zf = z + h
     return orc.sigmoid(zf @ p["tail_w"].T + p["tail_b"])
+
+
+def loss_scale_for(grad_rgb: np.ndarray) -> float:
+    """dw.cu: r2l_bwd_prep_kernel - the power of two S with S * max |grad_rgb| in [2^9, 2^10)."""
+    m = float(np.max(np.abs(grad_rgb)))
+    if not (0.0 < m < 3.0e38):
+        return 1.0
+    _, e = np.frexp(np.float32(m))
+    return float(np.ldexp(1.0, int(np.clip(10 - int(e), -100, 100))))
+
+
+def r2l_grads_split(flat: np.ndarray, x: np.ndarray, target: np.ndarray, fmt: str = "fp16", w_scale: float | None = None,
+                    loss_scale: float | None = None):
+    """(rgb, flat gradient [NUM_PARAMS] float64) of img2mse through the kernels' arithmetic: forward as above; backward
+    chain and weight gradients as chain.cu (kBwd) / dw.cu build them - every product three split terms, dY carrying the
+    loss scale, tail gradients in fp32 on the unscaled d logit (r2l_tail_grad_kernel)."""
+    if w_scale is None:
+        w_scale = WEIGHT_SCALE if fmt == "fp16" else 1.0
+    p = orc.unflatten_params(flat.astype(np.float32))
+    x = x.astype(np.float32)
+    n = x.shape[0]
+    lin = lambda a, w: split_linear(a, w, 3, fmt, w_scale)              # a @ w^T, weights packed scaled
+    lin_t = lambda a, w: split_matmul(a, w, 3, fmt, w_scale)           # a @ w   (the transposed images of the backward)
+    outer = lambda dy, xx: split_matmul(dy.T, xx, 3, fmt, 1.0)         # dW = dY^T X over the ray axis (dw.cu)
+    h = np.maximum(lin(x, p["head_w"]) + p["head_b"], 0)
+    z, zs, acts = h, [], []
+    for k in range(orc.N_BLOCKS):
+        (w1, b1), (w2, b2) = p["body"][2 * k], p["body"][2 * k + 1]
+        a = np.maximum(lin(z, w1) + b1, 0)
+        zs.append(z)
+        acts.append(a)
+        z = (lin(a, w2) + b2) + z
+    zf = z + h
+    rgb = orc.sigmoid(zf @ p["tail_w"].T + p["tail_b"])
+    grad_rgb = ((2.0 / (3 * n)) * (rgb - target.astype(np.float32))).astype(np.float32)
+    s = np.float32(loss_scale_for(grad_rgb) if loss_scale is None else loss_scale)
+    g = np.zeros(orc.NUM_PARAMS, np.float64)
+    dl = (grad_rgb * rgb * (1 - rgb)).astype(np.float32)
+    g[orc.OFF_TAIL_W:orc.OFF_TAIL_B] = (dl.T @ zf).reshape(-1)
+    g[orc.OFF_TAIL_B:] = dl.sum(0)
+    gz = ((dl * s) @ p["tail_w"]).astype(np.float32)
+    g43 = gz.copy()
+    for k in range(orc.N_BLOCKS - 1, -1, -1):
+        w1, w2 = p["body"][2 * k][0], p["body"][2 * k + 1][0]
+        o1 = orc.OFF_BODY + (2 * k) * orc.LINEAR_STRIDE
+        o2 = o1 + orc.LINEAR_STRIDE
+        g[o2:o2 + 65536] = outer(gz, acts[k]).reshape(-1) / s
+        g[o2 + 65536:o2 + 65792] = gz.sum(0) / s
+        dh = lin_t(gz, w2) * (acts[k] > 0)
+        g[o1:o1 + 65536] = outer(dh, zs[k]).reshape(-1) / s
+        g[o1 + 65536:o1 + 65792] = dh.sum(0) / s
+        gz = gz + lin_t(dh, w1)
+    dhead = (gz + g43) * (h > 0)
+    g[orc.OFF_HEAD_W:orc.OFF_HEAD_B] = outer(dhead, x).reshape(-1) / s
+    g[orc.OFF_HEAD_B:orc.OFF_BODY] = dhead.sum(0) / s
+    return rgb, g

@@ -48,7 +48,7 @@ SideStream* side_stream() {
   }
   return &s;
 }
-constexpr size_t kReadyBytes = 1024;  // 87 readiness counters + 90 reduction tickets (ints), padded
+constexpr size_t kReadyBytes = 1024;  // 87 readiness counters + 90 reduction tickets (ints) + queue + loss scale {S, 1/S}, padded
 constexpr int kDwUnits = r2l::kBodyLayers + 4;
 constexpr int kDwMaxCtas = 720;       // scratch slots for partial weight gradients (one per CTA of a split unit)
 constexpr size_t kDwPartialBytes = (size_t)kDwMaxCtas * (256 * 256 + 256) * sizeof(float);
@@ -292,7 +292,12 @@ int r2l_backward(int input_kind, const void* packed, const float* rgb, const flo
   t.n_rays = n_rays;
   dw_schedule(d, side != nullptr);
   d.deterministic = g_deterministic;
-  if (int rc = check(cudaMemsetAsync(ready, 0, kReadyBytes, st), "r2l_backward(memset)")) return rc;
+  // one small kernel instead of a memset: zeroes the flag words and derives the loss scale from max |grad_rgb|
+  float* bwd_scale = reinterpret_cast<float*>(ready + 254);
+  p.bwd_scale = bwd_scale;
+  d.bwd_scale = bwd_scale;
+  if (misaligned(grad_rgb)) return fail("r2l_backward: %s", "grad_rgb must be 16-byte aligned");
+  if (int rc = check(r2l::launch_bwd_prep(grad_rgb, n_rays * 3, ready, 254, bwd_scale, st), "r2l_backward(prep)")) return rc;
   // pieces of split units add into the buffer: head + body gradients start at 0 (zeroed on the stream dW runs on)
   const bool zero_grads = !d.deterministic && d.num_items > kDwUnits;
   if (side) {

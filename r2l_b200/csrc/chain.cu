@@ -12,15 +12,15 @@
 // is what torch.autograd derives for that graph (loss.backward(), main.py:1404).
 //
 // Per CTA (640 threads):
-//   warp 0      weight producer: streams bf16 operand images (TMA bulk copy) into a 96 KiB ring
-//   warp 1      MMA issuer: tcgen05.mma N=256,K=16, bf16x3 split (hi*hi + lo*hi + hi*lo), fp32 in TMEM
+//   warp 0      weight producer: streams fp16 operand images (TMA bulk copy) into a 96 KiB ring
+//   warp 1      MMA issuer: tcgen05.mma N=256,K=16, fp16x3 split (hi*hi + lo*hi + hi*lo), fp32 in TMEM
 //   warp 2      TMEM allocator (512 columns: Z [0,256) = residual stream / running gradient,
 //               H [256,512) = block hidden / its gradient)
 //   warp 3      (train / bwd) operand-image store warp: smem A chunk -> HBM via bulk async stores
 //   warps 4-19  epilogue / encoder: FOUR threads per ray (16 warps = 4 per SM sub-partition, so that TMEM-read and
 //               fence latencies of one warp hide behind the arithmetic of the others). They build the first A
 //               operand (positional encoding, or dL/dz_43) and after every layer turn the fp32 accumulator into the
-//               next layer's bf16 hi/lo A operand in shared memory (bias/ReLU or mask, split, 128B swizzle).
+//               next layer's fp16 hi/lo A operand in shared memory (bias/ReLU or mask, split, 128B swizzle).
 //
 // Three launch forms of the same kernel (template parameter FORM):
 //   single  one CTA per 128-ray tile; 3 x 32 KiB weight ring; tcgen05.mma.cta_group::1, M = 128.
@@ -62,7 +62,7 @@ constexpr uint32_t kBarBlockBytes = 512;
 __host__ __device__ constexpr ChainGeom chain_geom(int form) {
   ChainGeom g{};
   g.rows = form == kFormHalf ? 64u : 128u;              // rays per CTA
-  g.plane = g.rows * 128u;                              // one bf16 plane of a 64-feature K chunk (SW128 K-major rows)
+  g.plane = g.rows * 128u;                              // one fp16 plane of a 64-feature K chunk (SW128 K-major rows)
   g.slot = 2u * g.plane;
   g.w_stages = form == kFormHalf ? 8u : form == kFormPair ? 6u : 3u;
   g.w_stage_bytes = form == kFormSingle ? (uint32_t)kWImageBytes : (uint32_t)kWImageBytes / 2u;
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
     // A_hi W_lo; chunks 1..3: 4 x A_hi W_hi, 4 x A_lo W_hi, 4 x A_hi W_lo), so all forms accumulate in the same order
     // and give bit-identical results.
     static_assert(!HALF || kNumWStages == 8, "one group of four K chunks = one turn of the weight ring");
-    constexpr uint32_t idesc = umma_idesc_bf16(128, 256, 0, 0);
+    constexpr uint32_t idesc = umma_idesc_f16(128, 256, 0, 0);
     uint32_t group = 0;        // groups of four K chunks (= 8 weight images = 16 operand units) issued so far
     uint32_t ready = 0;        // barriers of the current group known to have completed (bit = lane that watches it)
     const uint32_t my_bar = lane < 16 ? bar(kBarAMma + lane) : lane < 24 ? bar(kBarWFull + lane - 16) : bar(kBarWPeer + lane - 24);
@@ -295,9 +295,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
               if (c == 0 && ks == 0) tc_fence_after_sync();
               if (elect_one_sync()) {
                 if (tr && g == 0 && c == 0 && ks == 0) p.trace[((int64_t)blockIdx.x * 5 + 0) * 96 + l] = clock64();
-                umma_bf16_pair(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b_hi + 32 * ks, 16, 1024), idesc,
+                umma_f16_pair(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b_hi + 32 * ks, 16, 1024), idesc,
                                (fresh && g == 0 && c == 0 && ks == 0) ? 0u : 1u);
-                if (c == 0) umma_bf16_pair(d, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw128(b_hi + 32 * ks, 16, 1024), idesc, 1u);
+                if (c == 0) umma_f16_pair(d, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw128(b_hi + 32 * ks, 16, 1024), idesc, 1u);
               }
             }
             need(w_lo);   // (probed early: its latency hides behind the MMAs just queued)
@@ -305,12 +305,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
               if (c != 0) {
 #pragma unroll
                 for (uint32_t ks = 0; ks < 4; ++ks)
-                  umma_bf16_pair(d, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw128(b_hi + 32 * ks, 16, 1024), idesc, 1u);
+                  umma_f16_pair(d, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw128(b_hi + 32 * ks, 16, 1024), idesc, 1u);
               }
               umma_commit_pair(bar(kBarWEmpty + 2 * c));       // W_hi of this chunk has been read
 #pragma unroll
               for (uint32_t ks = 0; ks < 4; ++ks)
-                umma_bf16_pair(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b_lo + 32 * ks, 16, 1024), idesc, 1u);
+                umma_f16_pair(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b_lo + 32 * ks, 16, 1024), idesc, 1u);
               umma_commit_pair(bar(kBarWEmpty + 2 * c + 1));
               if (head) umma_commit_pair(bar(kBarAEmpty + c));   // the head's A chunks recycle through the 4 slots
             }
@@ -336,9 +336,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
     // ptxas wrap every tcgen05.mma in an "any active thread" loop with per-instruction register -> uniform-register moves,
     // about 100 cycles per MMA; under elect.sync the descriptors stay in uniform registers.)
     {
-      constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, 256, 0, 0);   // pair: M = 256 over both CTAs
+      constexpr uint32_t idesc = umma_idesc_f16(PAIR ? 256 : 128, 256, 0, 0);   // pair: M = 256 over both CTAs
       auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
-        if constexpr (PAIR) umma_bf16_pair(d, a, b, idesc, acc); else umma_bf16(d, a, b, idesc, acc);
+        if constexpr (PAIR) umma_f16_pair(d, a, b, idesc, acc); else umma_f16(d, a, b, idesc, acc);
       };
       auto commit = [&](uint32_t barrier) {   // pair: arrives on the barrier at this offset in BOTH CTAs
         if constexpr (PAIR) umma_commit_pair(barrier); else umma_commit(barrier);
@@ -666,12 +666,15 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
         }
       } else {
         // ---- backward prologue: d logit = d rgb * rgb (1 - rgb);  g = d logit . W_tail  (dL/dz_43 = dL/dh_skip) ----
+        // The whole backward runs on loss_scale * dL/d(.) (a power of two chosen per call from max |d rgb| by
+        // r2l_bwd_prep_kernel, so that the fp16 dY planes sit in the normal range); dw.cu divides it out again.
+        const float loss_scale = p.bwd_scale ? __ldg(p.bwd_scale) : 1.f;
         float dl[3] = {0.f, 0.f, 0.f};
         if (valid) {
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             const float y = __ldg(p.rgb_in + grow * 3 + c);
-            dl[c] = __ldg(p.grad_rgb + grow * 3 + c) * y * (1.f - y);
+            dl[c] = __ldg(p.grad_rgb + grow * 3 + c) * y * (1.f - y) * loss_scale;
           }
         }
         for (int c = 0; c < kAChunks; ++c) {
@@ -690,7 +693,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
             v[4 * i + 3] = fmaf(dl[2], w2.w, fmaf(dl[1], w1.w, dl[0] * w0.w));
           }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(v[i]);
+          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(v[i] * kWeightScale);   // Z is kept in accumulator units
           tmem_st8(tmem_row + kTmemZ + tmem_col(c) + 16u * qt, &r[0]);
           tmem_st8(tmem_row + kTmemZ + tmem_col(c) + 16u * qt + 8, &r[8]);
 #pragma unroll
@@ -782,14 +785,15 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
             const uint32_t col = 64u * c + 16u * g + 8u * uu;
             float v[8];
             if constexpr (!kIsBwd) {
-              v[0] = __uint_as_float(r[8 * h + 0]) + bq[2 * h].x;
-              v[1] = __uint_as_float(r[8 * h + 1]) + bq[2 * h].y;
-              v[2] = __uint_as_float(r[8 * h + 2]) + bq[2 * h].z;
-              v[3] = __uint_as_float(r[8 * h + 3]) + bq[2 * h].w;
-              v[4] = __uint_as_float(r[8 * h + 4]) + bq[2 * h + 1].x;
-              v[5] = __uint_as_float(r[8 * h + 5]) + bq[2 * h + 1].y;
-              v[6] = __uint_as_float(r[8 * h + 6]) + bq[2 * h + 1].z;
-              v[7] = __uint_as_float(r[8 * h + 7]) + bq[2 * h + 1].w;
+              // the accumulators hold kWeightScale * (a . W): the rescale is an exact power of two inside the bias add
+              v[0] = fmaf(__uint_as_float(r[8 * h + 0]), kInvWeightScale, bq[2 * h].x);
+              v[1] = fmaf(__uint_as_float(r[8 * h + 1]), kInvWeightScale, bq[2 * h].y);
+              v[2] = fmaf(__uint_as_float(r[8 * h + 2]), kInvWeightScale, bq[2 * h].z);
+              v[3] = fmaf(__uint_as_float(r[8 * h + 3]), kInvWeightScale, bq[2 * h].w);
+              v[4] = fmaf(__uint_as_float(r[8 * h + 4]), kInvWeightScale, bq[2 * h + 1].x);
+              v[5] = fmaf(__uint_as_float(r[8 * h + 5]), kInvWeightScale, bq[2 * h + 1].y);
+              v[6] = fmaf(__uint_as_float(r[8 * h + 6]), kInvWeightScale, bq[2 * h + 1].z);
+              v[7] = fmaf(__uint_as_float(r[8 * h + 7]), kInvWeightScale, bq[2 * h + 1].w);
               if (relu) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -798,7 +802,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
                 // z_0 = h: seed the TMEM residual stream and keep h for the outer skip (:543)
                 uint32_t w[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) w[i] = __float_as_uint(v[i]);
+                for (int i = 0; i < 8; ++i) w[i] = __float_as_uint(v[i] * kWeightScale);   // Z is kept in accumulator units
                 tmem_st8(tmem_row + kTmemZ + tmem_col(c) + 16u * g + 8u * uu, w);
                 reinterpret_cast<float4*>(hrow + col)[0] = make_float4(v[0], v[1], v[2], v[3]);
                 reinterpret_cast<float4*>(hrow + col)[1] = make_float4(v[4], v[5], v[6], v[7]);
@@ -806,7 +810,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
               }
             } else {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * h + i]);
+              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * h + i]) * kInvWeightScale;
               if (last) {  // + dL/dz_43 through the outer skip
                 const float4 s0 = reinterpret_cast<const float4*>(hrow + col)[0];
                 const float4 s1 = reinterpret_cast<const float4*>(hrow + col)[1];
@@ -814,7 +818,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
                 v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
               }
               if (masked) {
-                // ReLU mask from the hi plane of the saved forward operand (a > 0  <=>  bf16 hi != 0; a >= 0 always)
+                // ReLU mask from the hi plane of the saved forward operand (a > 0  <=>  fp16 hi != 0 for a >= 2^-25; a >= 0 always)
                 const uint32_t w[4] = {mq[h].x, mq[h].y, mq[h].z, mq[h].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -983,7 +987,7 @@ __global__ void __launch_bounds__(128, 1) r2l_umma_selftest_kernel(const float* 
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (threadIdx.x == 0) {
-    constexpr uint32_t idesc = umma_idesc_bf16(128, 256, 0, 0);
+    constexpr uint32_t idesc = umma_idesc_f16(128, 256, 0, 0);
     for (int kc = 0; kc < kAChunks; ++kc) {
       mbar_arrive_expect_tx(bar_w, 2 * kWImageBytes);
       bulk_g2s(wbase, images + (int64_t)(2 * kc) * kWImageBytes, kWImageBytes, bar_w);
@@ -992,13 +996,13 @@ __global__ void __launch_bounds__(128, 1) r2l_umma_selftest_kernel(const float* 
       tc_fence_after_sync();
       const uint32_t a_hi = smem_base + kc * kAChunkBytes, a_lo = a_hi + kPlaneBytes;
       for (int ks = 0; ks < 4; ++ks)
-        umma_bf16(tmem_base, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(wbase + 32 * ks, 16, 1024),
+        umma_f16(tmem_base, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(wbase + 32 * ks, 16, 1024),
                   idesc, (kc == 0 && ks == 0) ? 0u : 1u);
       for (int ks = 0; ks < 4; ++ks)
-        umma_bf16(tmem_base, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw128(wbase + 32 * ks, 16, 1024),
+        umma_f16(tmem_base, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw128(wbase + 32 * ks, 16, 1024),
                   idesc, 1u);
       for (int ks = 0; ks < 4; ++ks)
-        umma_bf16(tmem_base, umma_desc_sw128(a_hi + 32 * ks, 16, 1024),
+        umma_f16(tmem_base, umma_desc_sw128(a_hi + 32 * ks, 16, 1024),
                   umma_desc_sw128(wbase + kWImageBytes + 32 * ks, 16, 1024), idesc, 1u);
       umma_commit(bar_m);
       mbar_wait(bar_m, kc & 1);
@@ -1012,7 +1016,7 @@ __global__ void __launch_bounds__(128, 1) r2l_umma_selftest_kernel(const float* 
     tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + 32 * c8, r);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) C[row * kWidth + 32 * c8 + i] = __uint_as_float(r[i]);
+    for (int i = 0; i < 32; ++i) C[row * kWidth + 32 * c8 + i] = __uint_as_float(r[i]) * kInvWeightScale;
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -1057,14 +1061,14 @@ __global__ void __launch_bounds__(128, 1) r2l_mma_rate_kernel(int reps, int vari
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
   if (threadIdx.x == 0 && rank == 0) {
-    constexpr uint32_t idesc = umma_idesc_bf16(FORM == kFormPair ? 256 : 128, 256, 0, 0);
+    constexpr uint32_t idesc = umma_idesc_f16(FORM == kFormPair ? 256 : 128, 256, 0, 0);
     auto mma = [&](uint64_t a, uint64_t b) {
-      if constexpr (PAIR) umma_bf16_pair(tmem_base, a, b, idesc, 1u); else umma_bf16(tmem_base, a, b, idesc, 1u);
+      if constexpr (PAIR) umma_f16_pair(tmem_base, a, b, idesc, 1u); else umma_f16(tmem_base, a, b, idesc, 1u);
     };
     const long long t0 = clock64();
     if (FORM == kFormHalf && pattern != 0) {
       constexpr ChainGeom G = chain_geom(kFormHalf);
-      auto mma_d = [&](uint32_t d, uint64_t a, uint64_t b) { umma_bf16_pair(d, a, b, idesc, 1u); };
+      auto mma_d = [&](uint32_t d, uint64_t a, uint64_t b) { umma_f16_pair(d, a, b, idesc, 1u); };
       for (int r = 0; r < reps; ++r) {
         const uint32_t d = tmem_base + ((r & 1) ? G.tmem_h : 0u);
         for (int pr = 0; pr < 2; ++pr) {

@@ -1,7 +1,7 @@
 // Weight-gradient kernel: dW_l[o,i] = sum_rays dY_l[ray,o] * X_l[ray,i] and db_l[o] = sum_rays dY_l[ray,o]
 // for the head and the 86 body Linears, as tcgen05 GEMMs whose K dimension is the ray axis.
 //
-// Both operands are the bf16 hi/lo operand images the chain kernels stored (chain.cu): X_l = the A operand
+// Both operands are the fp16 hi/lo operand images the chain kernels stored (chain.cu): X_l = the A operand
 // the forward pass fed to Linear l, dY_l = the A operand the backward pass built from dL/d(output of Linear l).
 // An image chunk is [128 rays][64 features] with 128-byte swizzled rows, i.e. exactly a UMMA *MN-major*
 // SWIZZLE_128B tile when the ray axis plays K — so the same bytes serve as K-major A operand in the chain
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) r2l_dw_kernel(const __grid_cons
     }
   } else if (warp == 1) {
     // the whole warp waits, one elected lane issues (keeps the descriptors in uniform registers, see chain.cu)
-    constexpr uint32_t idesc = umma_idesc_bf16(128, 256, 1, 1);   // both operands MN-major
+    constexpr uint32_t idesc = umma_idesc_f16(128, 256, 1, 1);   // both operands MN-major
     constexpr uint32_t kLbo = 2 * kDwPiece;   // next 64-feature group of the same plane
     constexpr uint32_t kSbo = 1024;           // next 8 rays
     uint32_t git = 0;
@@ -179,9 +179,9 @@ __global__ void __launch_bounds__(kDwThreads, 1) r2l_dw_kernel(const __grid_cons
               const uint32_t a_hi = dy + (4 * half) * kDwPiece + ks * 2048, a_lo = a_hi + kDwPiece;
               const uint32_t b_hi = x + ks * 2048, b_lo = b_hi + kDwPiece;
               const uint32_t first = (it == 0 && ks == 0) ? 0u : 1u;
-              umma_bf16(d, umma_desc_sw128(a_hi, kLbo, kSbo), umma_desc_sw128(b_hi, kLbo, kSbo), idesc, first);
-              umma_bf16(d, umma_desc_sw128(a_lo, kLbo, kSbo), umma_desc_sw128(b_hi, kLbo, kSbo), idesc, 1u);
-              umma_bf16(d, umma_desc_sw128(a_hi, kLbo, kSbo), umma_desc_sw128(b_lo, kLbo, kSbo), idesc, 1u);
+              umma_f16(d, umma_desc_sw128(a_hi, kLbo, kSbo), umma_desc_sw128(b_hi, kLbo, kSbo), idesc, first);
+              umma_f16(d, umma_desc_sw128(a_lo, kLbo, kSbo), umma_desc_sw128(b_hi, kLbo, kSbo), idesc, 1u);
+              umma_f16(d, umma_desc_sw128(a_hi, kLbo, kSbo), umma_desc_sw128(b_lo, kLbo, kSbo), idesc, 1u);
             }
           }
           umma_commit(bar_empty(s));
@@ -215,8 +215,9 @@ __global__ void __launch_bounds__(kDwThreads, 1) r2l_dw_kernel(const __grid_cons
           const uint32_t off = r * 128u + ((((kc >> 3) ^ (r & 7u)) << 4) | ((kc & 7u) << 1));
           const uint32_t hi = *reinterpret_cast<const uint32_t*>(dy + (2 * c) * kDwPiece + off);
           const uint32_t lo = *reinterpret_cast<const uint32_t*>(dy + (2 * c + 1) * kDwPiece + off);
-          s0 += __uint_as_float(hi << 16) + __uint_as_float(lo << 16);
-          s1 += __uint_as_float(hi & 0xFFFF0000u) + __uint_as_float(lo & 0xFFFF0000u);
+          const float2 fh = plane_word_to_float2(hi), fl = plane_word_to_float2(lo);
+          s0 += fh.x + fl.x;
+          s1 += fh.y + fl.y;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty(s));
@@ -225,6 +226,10 @@ __global__ void __launch_bounds__(kDwThreads, 1) r2l_dw_kernel(const __grid_cons
       // A piece of a split unit either adds its result into the (zeroed) gradient buffer with L2 reductions - the
       // default: no scratch traffic, no reduction pass, summation order of the <= 8 pieces not fixed - or, in the
       // deterministic mode, writes it to scratch for the unit's last piece to sum in index order.
+      // the dY operands carry the backward's loss scale (chain.cu, backward prologue): divide it out, exactly
+      const float unscale = p.bwd_scale ? __ldg(p.bwd_scale + 1) : 1.f;
+      s0 *= unscale;
+      s1 *= unscale;
       const bool atomic = w.splits > 1 && !p.deterministic;
       float* part = (w.splits > 1 && p.deterministic) ? p.partials + (int64_t)item * kUnitFloats : nullptr;
       auto head_feature = [&](int col) {
@@ -260,7 +265,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) r2l_dw_kernel(const __grid_cons
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             *reinterpret_cast<float4*>(stage + lane * kDwStageRow + 4 * i) =
-                make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+                make_float4(__uint_as_float(r[4 * i]) * unscale, __uint_as_float(r[4 * i + 1]) * unscale,
+                            __uint_as_float(r[4 * i + 2]) * unscale, __uint_as_float(r[4 * i + 3]) * unscale);
           __syncwarp();
           const int o0 = half * 128 + (int)q * 32;   // first output feature (row of dW) of this warp's block
           if (part || !w.is_head) {
@@ -423,6 +429,47 @@ __global__ void __launch_bounds__(256) r2l_tail_grad_kernel(const __grid_constan
     p.grads[kOffTailW + o] = s;   // tail.0.weight [3,256] and tail.0.bias [3] are contiguous in the flat buffer
   }
   if (threadIdx.x == 0) *p.ticket = 0;
+}
+
+// Backward preamble (one block): zero the readiness flags / tickets / queue words of this call and choose the loss scale
+// the backward chain runs on: S = 2^k with S * max |d rgb| in [2^9, 2^10).  With |d logit| <= |d rgb| / 4 and
+// |W_tail| ~ 2^-4 the dY operands then peak near 2^4 and sit around 1: inside the range where the fp16 hi/lo planes carry
+// 22 bits, with a factor of ~2^12 of head room to fp16's maximum for gradients that grow along the chain.
+__global__ void __launch_bounds__(1024) r2l_bwd_prep_kernel(const float* __restrict__ grad_rgb, int64_t n, int* __restrict__ ready,
+                                                            int ready_ints, float* __restrict__ scale_out) {
+  __shared__ float warp_max[32];
+  for (int i = threadIdx.x; i < ready_ints; i += blockDim.x) ready[i] = 0;
+  float m = 0.f;
+  const int64_t n4 = n >> 2;
+  for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(grad_rgb) + i);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  for (int64_t i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(__ldg(grad_rgb + i)));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) warp_max[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = warp_max[threadIdx.x];
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) {
+      float s = 1.f;
+      if (m > 0.f && m < 3.0e38f) {   // NaN / inf / all-zero gradients: no scaling
+        int e;
+        frexpf(m, &e);                // m = f * 2^e, f in [0.5, 1)
+        int k = 10 - e;
+        k = k > 100 ? 100 : (k < -100 ? -100 : k);
+        s = ldexpf(1.f, k);
+      }
+      scale_out[0] = s;
+      scale_out[1] = 1.f / s;
+    }
+  }
+}
+
+cudaError_t launch_bwd_prep(const float* grad_rgb, int64_t n_values, int* ready, int ready_ints, float* scale_out, cudaStream_t stream) {
+  r2l_bwd_prep_kernel<<<1, 1024, 0, stream>>>(grad_rgb, n_values, ready, ready_ints, scale_out);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_dw(const DwParams& p, cudaStream_t stream) {

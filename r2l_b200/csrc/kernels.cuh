@@ -30,6 +30,7 @@ struct ChainParams {
   const uint8_t* fwd_saved;  // kBwd in: the forward pass's `saved`
   const float* rgb_in;    // kBwd in: forward rgb [N,3]
   const float* grad_rgb;  // kBwd in: dL/d rgb [N,3]
+  const float* bwd_scale; // kBwd in (device): [0] = loss scale the backward runs on (power of two), [1] = its inverse
   int* ready;             // kBwd out (optional): [87] counters, ready[g] += 1 when this CTA's tile has stored operand group g
                           // (g = 0: dL/dz_43, g = 1 + j: output of backward epilogue j); lets dw.cu run concurrently
   int64_t n_rays;
@@ -60,6 +61,7 @@ struct DwParams {
   float* partials;        // [num_items][256*256 + 256] scratch (only slots of split units are used)
   int* tickets;           // [90] zeroed counters (only needed when some unit is split)
   long long* times;       // optional debug: [unit][4] globaltimer stamps (start, flag seen, MMAs done, end)
+  const float* bwd_scale; // device: [1] = 1 / (loss scale of the dY operands); results are multiplied by it (exact)
   const int* ready;       // optional: wait until ready[group of this unit] == ready_target before streaming (see ChainParams)
   int ready_target;       // store warps that announce each group: num_tiles (x 2 when the chain ran in its half form)
 };
@@ -93,6 +95,8 @@ enum : int { kFormSingle = 0, kFormPair = 1, kFormHalf = 2 };   // launch forms 
 cudaError_t launch_chain(int mode, int form, const ChainParams& p, int grid, cudaStream_t stream);   // pair / half: grid even, clusters of 2
 cudaError_t launch_dw(const DwParams& p, cudaStream_t stream);
 cudaError_t launch_tail_grads(const TailGradParams& p, cudaStream_t stream);
+// zeroes the `ready_ints` flag words at `ready` and writes {S, 1/S} to scale_out: S = 2^k with S * max |grad_rgb| in [2^9, 2^10)
+cudaError_t launch_bwd_prep(const float* grad_rgb, int64_t n_values, int* ready, int ready_ints, float* scale_out, cudaStream_t stream);
 cudaError_t launch_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, int64_t n_rays, int n_samples,
                                int white_bkgd, float* rgb_map, float* disp_map, float* acc_map, float* weights,
                                float* depth_map, cudaStream_t stream);

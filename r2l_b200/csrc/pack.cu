@@ -1,4 +1,4 @@
-// Weight packing: flat fp32 state_dict buffer -> bf16 hi/lo UMMA operand images + fp32 side tables.
+// Weight packing: flat fp32 state_dict buffer -> fp16 hi/lo UMMA operand images (of kWeightScale * W) + fp32 side tables.
 // Runs once per parameter update (inference: once; training: once per optimizer step).
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) pack_images_kernel(const float* __restric
   }
   uint32_t hi[4], lo[4];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) split2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+  for (int e = 0; e < 4; ++e) split2(v[2 * e] * kWeightScale, v[2 * e + 1] * kWeightScale, hi[e], lo[e]);   // see ptx.cuh
   const uint32_t off = sw128_offset(n, 8 * j);
   uint8_t* img = packed + (int64_t)(2 * ip) * kWImageBytes;
   *reinterpret_cast<uint4*>(img + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);

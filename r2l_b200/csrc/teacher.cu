@@ -6,7 +6,7 @@
 // run_network :312-334, NeRF.__init__ :339-375, NeRF.forward :377-401 (use_viewdirs=True, D=8, W=256, skips=[4]);
 // call sites utils/create_data.py:490,521.
 //
-// Layer program (weights streamed as 32 KiB bf16 hi/lo K-major images, N padded to 256):
+// Layer program (weights streamed as 32 KiB fp16 hi/lo K-major images, N padded to 256):
 //   T0  pts63 (1 chunk)                -> 256, relu          T1..T4  256 -> 256, relu
 //   T5  [h256, pts63] (5 chunks)       -> 256, relu          T6, T7  256 -> 256, relu      (alpha = w_a . h7 + b_a on CUDA cores)
 //   T8  feature: 256 -> 256 (linear)   T9  [feature256, dirs27] (5 chunks) -> 128, relu   (rgb = W_rgb hv + b on CUDA cores)
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kTThreads, 1) r2l_teacher_kernel(const __grid_
     }
   } else if (warp == 1) {
     {   // the whole warp waits, one elected lane issues (keeps the descriptors in uniform registers, see chain.cu)
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 256, 0, 0);
+      constexpr uint32_t idesc = umma_idesc_f16(128, 256, 0, 0);
       uint32_t it = 0, a_phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         for (int l = 0; l < kTeacherLayers; ++l) {
@@ -149,11 +149,11 @@ __global__ void __launch_bounds__(kTThreads, 1) r2l_teacher_kernel(const __grid_
               if (elect_one_sync()) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
-                  umma_bf16(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b + 32 * ks, 16, 1024), idesc,
+                  umma_f16(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b + 32 * ks, 16, 1024), idesc,
                             (kc == 0 && ks == 0) ? 0u : 1u);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
-                  umma_bf16(d, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw128(b + 32 * ks, 16, 1024), idesc, 1u);
+                  umma_f16(d, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw128(b + 32 * ks, 16, 1024), idesc, 1u);
                 umma_commit(bar(kTBarWEmpty + ws));
               }
               ++it;
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kTThreads, 1) r2l_teacher_kernel(const __grid_
               if (elect_one_sync()) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
-                  umma_bf16(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b + 32 * ks, 16, 1024), idesc, 1u);
+                  umma_f16(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b + 32 * ks, 16, 1024), idesc, 1u);
                 umma_commit(bar(kTBarWEmpty + ws));
                 if (nkc == 5 && kc == 0) umma_commit(bar(kTBarAEmpty));   // slot 0 is recycled for the 5th chunk
               }
@@ -241,10 +241,10 @@ __global__ void __launch_bounds__(kTThreads, 1) r2l_teacher_kernel(const __grid_
           float v[32];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + bq[i].x;
-            v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bq[i].y;
-            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bq[i].z;
-            v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bq[i].w;
+            v[4 * i + 0] = fmaf(__uint_as_float(r[4 * i + 0]), kInvWeightScale, bq[i].x);   // exact power-of-two rescale
+            v[4 * i + 1] = fmaf(__uint_as_float(r[4 * i + 1]), kInvWeightScale, bq[i].y);
+            v[4 * i + 2] = fmaf(__uint_as_float(r[4 * i + 2]), kInvWeightScale, bq[i].z);
+            v[4 * i + 3] = fmaf(__uint_as_float(r[4 * i + 3]), kInvWeightScale, bq[i].w);
           }
           if (relu) {
 #pragma unroll
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(256) teacher_pack_images_kernel(const float* _
   }
   uint32_t hi[4], lo[4];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) split2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+  for (int e = 0; e < 4; ++e) split2(v[2 * e] * kWeightScale, v[2 * e + 1] * kWeightScale, hi[e], lo[e]);   // see ptx.cuh
   const uint32_t off = sw128_offset(n, 8 * j);
   uint8_t* img = packed + (int64_t)(2 * ip) * kWImageBytes;
   *reinterpret_cast<uint4*>(img + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);

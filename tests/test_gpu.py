@@ -126,6 +126,32 @@ def test_render_poses_module_surface_and_full_frame(packed, flat_seed0):
     assert u8.dtype == torch.uint8 and np.array_equal(u8.cpu().numpy(), orc.to8b(frames.cpu().numpy()))
 
 
+def test_forward_nchw_branch_matches_the_reference(golden_surface, flat_seed0):
+    """NeRF_v3_2.forward's channels-first branch (:540-541): x [n, 1008, h, w] is permuted to channels-last; the reference's
+    output on the fixture (seed-0 weights) is [n, h, w, 3]."""
+    g = golden_surface
+    nb.device = torch.device(DEV)
+    model = nb.NeRF_v3_2(nb.readme_args(), 1008, 3).to(DEV)
+    with torch.no_grad():
+        model.flat.copy_(torch.from_numpy(flat_seed0).to(DEV))
+        out = model(torch.from_numpy(g["nchw_x"]).to(DEV))
+    assert tuple(out.shape) == tuple(g["nchw_rgb"].shape) == (2, 4, 3, 3)
+    assert relerr(out.cpu().numpy(), g["nchw_rgb"]) < FWD_TOL
+    assert relerr(out.reshape(-1, 3).cpu().numpy(), g["nhwc_rgb"]) < FWD_TOL
+
+
+def test_teacher_loaded_from_keras_weights_matches_the_reference(golden_surface, keras_weights):
+    """a15: a teacher whose parameters came through load_weights_from_keras evaluates like the reference's (:403-440, :377-401)."""
+    g = golden_surface
+    torch.manual_seed(3)
+    teacher = nb.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=4, skips=[4], use_viewdirs=True)
+    teacher.load_weights_from_keras(keras_weights)
+    teacher = teacher.to(DEV)
+    with torch.no_grad():
+        raw = teacher(torch.from_numpy(g["teacher_x"]).to(DEV)).cpu().numpy()
+    np.testing.assert_allclose(raw, g["teacher_raw"], rtol=1e-3, atol=1e-4)
+
+
 def test_forward_empty_batch(packed):
     out = ops.forward(packed, rays_o=torch.zeros(0, 3, device=DEV), rays_d=torch.zeros(0, 3, device=DEV), z_vals=[0.] * 16)
     assert out.shape == (0, 3)
@@ -158,9 +184,9 @@ def _grad_report(ours, g64):
 
 
 def test_backward_golden_vs_fp64(golden_r2l, flat_seed0, packed):
-    """200 golden rays.  The reference's own fp32 autograd is 6.8e-4 (flat Frobenius) from the fp64 truth on this
-    batch; the bf16x3 tensor-core path must stay within 8x of that and below 5e-3 (per-ray rounding noise averages
-    out with batch size, see the 4096-ray test for the tolerance at the BASELINE batch)."""
+    """200 golden rays (lego pose).  The reference's own fp32 autograd is 6.8e-4 (flat Frobenius) from the fp64 truth on this
+    batch; the fp16x3 tensor-core path on scaled weights is held to SURVEY 8(c) as written: flat <= 1e-3 (and inside the
+    reference's own error), every checked tensor within 3x the reference's worst per-tensor error."""
     g = golden_r2l
     ro, rd = torch.from_numpy(g["rays_o"]).to(DEV), torch.from_numpy(g["rays_d"]).to(DEV)
     tgt = torch.from_numpy(g["target"]).to(DEV)
@@ -169,21 +195,25 @@ def test_backward_golden_vs_fp64(golden_r2l, flat_seed0, packed):
     grads = ops.backward(packed, ctx, (2.0 / 600) * (rgb - tgt)).cpu().numpy().astype(np.float64)
     sub = grads[g["grad_idx"]]
     err = np.linalg.norm(sub - g["grad_f64_sub"]) / np.linalg.norm(g["grad_f64_sub"])
-    assert err < 8 * float(g["grad_f32_vs_f64_rel"]) and err < 5e-3
+    print(f"golden 200 rays: flat gradient error vs fp64 {err:.3e} (reference fp32: {float(g['grad_f32_vs_f64_rel']):.3e})")
+    assert err < 1e-3 and err < 3 * float(g["grad_f32_vs_f64_rel"]), err
     layout = {n: (o, int(np.prod(s))) for n, s, o in nb.state_dict_layout()}
-    for name in ("tail.0.weight", "tail.0.bias"):
+    bound = 3 * float(np.max(g["grad_tensor_ref32_relerr"]))
+    for name in ("tail.0.weight", "tail.0.bias", "head.0.bias", "body.0.body.0.bias", "body.42.body.2.bias", "body.20.body.0.bias"):
         o, n = layout[name]
-        assert _grad_report(grads[o:o + n], g["g64_" + name]) < 1e-3
-    for name in ("head.0.bias", "body.0.body.0.bias", "body.42.body.2.bias", "body.20.body.0.bias"):
-        o, n = layout[name]
-        assert _grad_report(grads[o:o + n], g["g64_" + name]) < 2e-2
+        assert _grad_report(grads[o:o + n], g["g64_" + name]) < bound, name
 
 
-@pytest.mark.parametrize("n", [1000, 4096])
-def test_backward_vs_fp64_autograd(n, flat_seed0, packed):
-    """Gradient parity at the BASELINE batch: flat-buffer Frobenius error vs the fp64 autograd of the same network
-    <= 1e-3 at 4096 rays and every tensor within 4e-3."""
+@pytest.mark.parametrize("n", [200, 1000, 4096])
+def test_backward_vs_fp64_autograd(n, flat_seed0, packed, golden_grad_ref):
+    """Gradient parity as SURVEY.md section 8(c) defines it, on stress batches of 200 / 1000 / 4096 rays: against the fp64
+    autograd of the same network the flat-buffer Frobenius error is <= 1e-3 and every tensor is within 3x the reference
+    fp32's own error (tests/golden/grad_ref_seed0.npz, produced by the reference module on these very batches).
+    The reference's per-tensor errors are dominated by a handful of ReLU units whose sign differs between fp32 and fp64
+    (median tensor 1.6e-5 but worst tensor 2.0e-3 at 1000 rays), so WHICH tensor carries the large error is arbitrary: the
+    yardstick per tensor is the reference's worst tensor, and the median of ours is held to 3x the reference's median."""
     from oracle.torch_reference import RefR2L, embed, sample
+    ref_err = golden_grad_ref
     torch.manual_seed(n)
     o, d, t = (torch.randn(n, 3) * 0.5).to(DEV), torch.randn(n, 3).to(DEV), torch.rand(n, 3).to(DEV)
     zt = torch.from_numpy(orc.sampler_z_vals(2.0, 6.0)).to(DEV)
@@ -192,13 +222,23 @@ def test_backward_vs_fp64_autograd(n, flat_seed0, packed):
     ref = RefR2L().load_flat(torch.from_numpy(flat_seed0)).double().to(DEV)
     ((ref(embed(sample(o, d, zt)).double()) - t.double()) ** 2).mean().backward()
     g64 = ref.flat_grads()
+    # the live fp64 truth is the reference's (committed subsample, produced by the reference module itself)
+    idx = torch.from_numpy(ref_err["grad_idx"]).to(DEV)
+    stored = torch.from_numpy(ref_err[f"g64_sub_{n}"]).to(DEV)
+    assert float((g64[idx] - stored).norm() / stored.norm()) < 1e-6
     flat_err = float((grads - g64).norm() / g64.norm())
-    assert flat_err < (1e-3 if n >= 4096 else 2e-3), flat_err
-    worst = 0.0
+    errs = []
     for name, shape, off in nb.state_dict_layout():
         k = int(np.prod(shape))
-        worst = max(worst, float((grads[off:off + k] - g64[off:off + k]).norm() / g64[off:off + k].norm()))
-    assert worst < (4e-3 if n >= 4096 else 8e-3), worst
+        errs.append(float((grads[off:off + k] - g64[off:off + k]).norm() / g64[off:off + k].norm()))
+    errs = np.array(errs)
+    ref_t = ref_err[f"tensor_err_{n}"]
+    print(f"n={n}: flat {flat_err:.3e} (reference fp32 {float(ref_err[f'flat_err_{n}']):.3e}); worst tensor {errs.max():.3e} "
+          f"(reference {ref_t.max():.3e}); median tensor {np.median(errs):.3e} (reference {np.median(ref_t):.3e})")
+    assert flat_err < 1e-3, flat_err
+    assert flat_err < 3 * float(ref_err[f"flat_err_{n}"]), flat_err
+    assert errs.max() < 3 * ref_t.max(), (int(errs.argmax()), errs.max())
+    assert np.median(errs) < 3 * np.median(ref_t), np.median(errs)
 
 
 def test_backward_is_linear_in_grad_rgb_and_rows_beyond_n_are_inert(packed):

@@ -210,3 +210,59 @@ def test_bench_synthetic_rays_follow_the_reference_camera_model():
     np.testing.assert_allclose(rd, want_d.reshape(-1, 3)[pix], rtol=0, atol=2e-6)
     np.testing.assert_allclose(ro, want_o.reshape(-1, 3)[pix], rtol=0, atol=2e-6)
     assert abs(np.linalg.norm(ro[0]) - 4.0) < 1e-5 and 0.0 <= tg.min() and tg.max() < 1.0
+
+
+# ---- SURVEY 8(a) rows a4 / a15 and the CNN-style surface, against reference-generated fixtures (surface_seed0.npz) ----
+def test_plucker_and_patch_samplers_match_the_reference(golden_surface):
+    g = golden_surface
+    ps = nb.PointSampler(int(g["H"]), int(g["W"]), float(g["focal"]), 16, 2.0, 6.0)
+    ro, rd, c2w = torch.from_numpy(g["rays_o"]), torch.from_numpy(g["rays_d"]), torch.from_numpy(g["c2w"])
+    assert np.array_equal(ps.sample_train_plucker(ro, rd).numpy(), g["plucker_train"])            # a4 (:170-176)
+    assert np.array_equal(ps.sample_test_plucker(c2w).numpy(), g["plucker_test"])                  # a4 (:178-188)
+    assert np.array_equal(ps.sample_test2(c2w).numpy(), g["test2"])                                # :104-112
+    po, pd = torch.from_numpy(g["patch_o"]), torch.from_numpy(g["patch_d"])
+    assert np.array_equal(ps.sample_train2(po, pd, 0.).numpy(), g["train2_p0"])                    # :128-147
+    assert np.array_equal(ps.sample_train_cnnstyle(po, pd, 0.).numpy(), g["cnn_p0"])               # :149-168
+    torch.manual_seed(5)
+    assert np.array_equal(ps.sample_train2(po, pd, 1.).numpy(), g["train2_p1"])                    # one uniform per image (:140)
+    torch.manual_seed(5)
+    assert np.array_equal(ps.sample_train_cnnstyle(po, pd, 1.).numpy(), g["cnn_p1"])
+    pe = nb.PositionalEmbedder(10)
+    x = torch.from_numpy(g["train2_p0"])[:1, :2]
+    np.testing.assert_allclose(pe.embed(x).numpy(), g["embed"], rtol=0, atol=1e-6)                 # :210-216
+    np.testing.assert_allclose(pe.embed_cnnstyle(x).numpy(), g["embed_cnnstyle"], rtol=0, atol=1e-6)
+    assert pe.embed(x).shape == (1, 2, 2, 16, 3, 21)
+
+
+def test_load_weights_from_keras_matches_the_reference(golden_surface, keras_weights):
+    """a15 (:403-440): the loaded state_dict equals what the reference's loader produced from the same 24 arrays."""
+    g = golden_surface
+    torch.manual_seed(3)
+    teacher = nb.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=4, skips=[4], use_viewdirs=True)
+    teacher.load_weights_from_keras(keras_weights)
+    sd = teacher.state_dict()
+    assert list(sd.keys()) == list(g["teacher_sd_names"])
+    np.testing.assert_allclose([float(v.double().sum()) for v in sd.values()], g["teacher_sd_sum"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose([float((v.double() ** 2).sum()) for v in sd.values()], g["teacher_sd_sumsq"], rtol=1e-12)
+    assert np.array_equal(sd["rgb_linear.weight"].numpy(), g["teacher_sd_rgb_linear.weight"])
+
+
+def test_torch_reference_port_is_pinned_to_the_reference(golden_r2l, flat_seed0):
+    """oracle/torch_reference.py is bench.py's reference arm and the fp64 gradient truth of the GPU tests: on the golden batch
+    it must reproduce what the reference module itself produced (tests/golden/make_golden.py) - rgb, loss and the fp32
+    gradient subsample bit for bit (same ATen ops in the same order), and the fp64 gradients to rounding."""
+    from oracle.torch_reference import RefR2L, embed
+    g = golden_r2l
+    m = RefR2L().load_flat(torch.from_numpy(flat_seed0))
+    x = embed(torch.from_numpy(g["pts"]))
+    assert np.array_equal(x.numpy(), g["x_embed"])
+    rgb = m(x)
+    assert np.array_equal(rgb.detach().numpy(), g["rgb"])
+    loss = ((rgb - torch.from_numpy(g["target"])) ** 2).mean()
+    assert np.float32(loss.item()) == g["loss"]
+    loss.backward()
+    assert np.array_equal(m.flat_grads().numpy()[g["grad_idx"]], g["grad_f32_sub"])
+    m64 = RefR2L().load_flat(torch.from_numpy(flat_seed0)).double()
+    ((m64(x.double()) - torch.from_numpy(g["target"]).double()) ** 2).mean().backward()
+    sub = m64.flat_grads().numpy()[g["grad_idx"]]
+    assert np.linalg.norm(sub - g["grad_f64_sub"]) <= 1e-12 * np.linalg.norm(g["grad_f64_sub"])

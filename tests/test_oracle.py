@@ -136,15 +136,23 @@ def test_sample_pdf(golden_teacher):
 
 
 def test_split_arithmetic_meets_the_parity_bar_on_the_cpu(golden_r2l, flat_seed0):
-    """The kernels' bf16x3 split products, emulated in numpy on the golden batch: within 2e-4 of the reference's RGB (the GPU
-    measures 3.7e-5 with its own summation order), while a single bf16 product misses the 1e-3 bar of BASELINE.json."""
+    """The kernels' fp16x3 split products on scaled weights, emulated in numpy on the golden batch: within 2e-5 of the
+    reference's RGB (round 1's bf16 planes: 1.0e-5 forward but 2e-3 on the gradients), while a single product misses the
+    margin; and the GRADIENTS of the emulated arithmetic are closer to the fp64 truth than the reference's own fp32 autograd
+    (6.8e-4 on this batch), which is what lets the GPU tests assert SURVEY 8(c) as written."""
     from oracle import split_emulation as se
-    x = np.array([1.0, -1.5, 3.14159274, 1e-3, 65504.0, 1.00390625], np.float32)
+    x = np.array([1.0, -1.5, 3.14159274, 1e-3, 65000.0, 1.00048828125, 3e-6], np.float32)
     hi, lo = se.split(x)
-    assert np.all(np.abs(x - (hi + lo)) <= np.abs(x) * 2.0 ** -16)                  # hi + lo carries 16+ mantissa bits
-    assert np.array_equal(se.to_bf16(np.array([1.00390625], np.float32)), np.array([1.0], np.float32))   # ties to even
+    assert np.all(np.abs(x - (hi + lo)) <= np.maximum(np.abs(x) * 2.0 ** -21, 2.0 ** -24))   # 22 bits, subnormal floor
+    assert np.array_equal(se.to_fp16(np.array([1.00048828125], np.float32)), np.array([1.0], np.float32))   # ties to even
+    assert se.loss_scale_for(np.array([1e-4, -3e-4], np.float32)) == 2.0 ** 21 and se.loss_scale_for(np.zeros(3, np.float32)) == 1.0
     g = golden_r2l
     rgb3 = se.r2l_forward_split(flat_seed0, g["x_embed"], terms=3)
     rgb1 = se.r2l_forward_split(flat_seed0, g["x_embed"], terms=1)
-    assert rel(rgb3, g["rgb"]) < 2e-4
-    assert rel(rgb1, g["rgb"]) > 1e-3
+    assert rel(rgb3, g["rgb"]) < 2e-5
+    assert rel(rgb1, g["rgb"]) > 2e-4
+    assert rel(se.r2l_forward_split(flat_seed0, g["x_embed"], terms=3, fmt="bf16"), g["rgb"]) > rel(rgb3, g["rgb"])
+    rgb, grads = se.r2l_grads_split(flat_seed0, g["x_embed"], g["target"])
+    sub = grads[g["grad_idx"]]
+    err = np.linalg.norm(sub - g["grad_f64_sub"]) / np.linalg.norm(g["grad_f64_sub"])
+    assert err < float(g["grad_f32_vs_f64_rel"]) and err < 1e-4, err

@@ -1,17 +1,20 @@
 """CPU study of operand formats / product counts for the chain kernels (numpy emulation, oracle/split_emulation.py): max and
 p99.9 relative error of the RGB output against the fp64 evaluation, on realistic lego-pose rays and on stress inputs.
-Round-1 results (seed-0 weights, 4096 rays):
+Results (seed-0 weights, 4096 rays; rounds 1-2):
 
     format x products                         lego rays (max / p99.9)    stress rays N(0,1) (max / p99.9)
-    bf16 x3 (the kernels today)               1.2e-05 / 9.2e-06          -
+    bf16 x3 (round 1's kernels)               1.2e-05 / 9.2e-06          -
     bf16 x1                                   5.1e-03 (200-ray golden batch)
-    fp16 x3                                   2.1e-06 / 1.7e-06          5.5e-06 / 3.3e-06
+    fp16 x3, weights unscaled                 2.1e-06 / 1.7e-06          5.5e-06 / 3.3e-06
+    fp16 x3, weights x 64 (the kernels today) 8e-07 on the golden batch = plain fp32 arithmetic
     fp16 x2  a_hi w_hi + a_lo w_hi            5.2e-04 / 3.8e-04          1.1e-03 / 7.4e-04
     fp16 x2  a_hi w_hi + a_hi w_lo            5.7e-04 / 4.7e-04          1.4e-03 / 9.6e-04
     fp16 x1                                   8.8e-04 / 6.1e-04          -
 
-Reading: fp16 operands (same tensor-core rate as bf16 with kind::f16) are 6x more accurate at equal cost; two fp16 products
-(2/3 of the tensor work) stay under the 1e-3 bar on realistic rays but not on stress inputs - an opt-in fast mode at best.
+Reading: fp16 planes (same tensor-core rate as bf16 under kind::f16) are 6x more accurate at equal cost, and once the
+weights are packed pre-multiplied by a power of two (their lo planes leave fp16's subnormal range) the three products are
+as accurate as fp32 arithmetic; two fp16 products (2/3 of the tensor work) stay under the 1e-3 bar on realistic rays but
+not on stress inputs - an opt-in fast mode at best.
 Usage: python tools/cpu_precision_study.py [n_rays]"""
 import importlib.util, os, sys
 import numpy as np
@@ -23,8 +26,11 @@ from r2l_b200.nerf_raybased import init_flat_params
 spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py")); bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 flat = init_flat_params(0).numpy()
-bf16 = se.to_bf16
-fp16 = lambda x: np.asarray(x, np.float32).astype(np.float16).astype(np.float32)
+
+
+def two_terms_w(a, w, fmt):      # a_hi w_hi + a_hi w_lo
+    a_hi, _ = se.split(a, fmt); w_hi, w_lo = se.split(w, fmt)
+    return (a_hi @ w_hi.T + a_hi @ w_lo.T).astype(np.float32)
 
 
 def forward(x, lin):
@@ -36,25 +42,19 @@ def forward(x, lin):
     return orc.sigmoid((z + h) @ p["tail_w"].T + p["tail_b"])
 
 
-def scheme(rnd, terms, drop="w_lo"):
-    def lin(a, w):
-        se.to_bf16 = rnd
-        a_hi, a_lo = se.split(a); w_hi, w_lo = se.split(w)
-        out = a_hi @ w_hi.T
-        if terms == 3: out = out + a_lo @ w_hi.T + a_hi @ w_lo.T
-        elif terms == 2: out = out + (a_lo @ w_hi.T if drop == "w_lo" else a_hi @ w_lo.T)
-        return out.astype(np.float32)
-    return lin
-
-
 z = orc.sampler_z_vals(2.0, 6.0)
 rng = np.random.RandomState(1)
 inputs = {"lego": bench.synthetic_rays(n, 0)[:2], "stress": ((rng.randn(n, 3) * 0.5).astype(np.float32), rng.randn(n, 3).astype(np.float32))}
+schemes = (("bf16 x3", lambda a, w: se.split_linear(a, w, 3, "bf16")),
+           ("fp16 x3, w x 1", lambda a, w: se.split_linear(a, w, 3, "fp16", 1.0)),
+           ("fp16 x3, w x 64", lambda a, w: se.split_linear(a, w, 3, "fp16", 64.0)),
+           ("fp16 x2 (a split)", lambda a, w: se.split_linear(a, w, 2, "fp16", 64.0)),
+           ("fp16 x2 (w split)", lambda a, w: two_terms_w(a, w, "fp16")),
+           ("fp16 x1", lambda a, w: se.split_linear(a, w, 1, "fp16", 64.0)),
+           ("bf16 x1", lambda a, w: se.split_linear(a, w, 1, "bf16")))
 for kind, (ro, rd) in inputs.items():
     x = orc.positional_embed(orc.sample_train(ro, rd, z, None))
     ref = orc.r2l_forward(flat.astype(np.float64), x.astype(np.float64))
-    for name, lin in (("bf16 x3", scheme(bf16, 3)), ("fp16 x3", scheme(fp16, 3)), ("fp16 x2 (a split)", scheme(fp16, 2, "w_lo")),
-                      ("fp16 x2 (w split)", scheme(fp16, 2, "a_lo")), ("fp16 x1", scheme(fp16, 1)), ("bf16 x1", scheme(bf16, 1))):
+    for name, lin in schemes:
         r = np.abs(forward(x, lin) - ref) / np.abs(ref)
         print(f"{kind:6s} {name:18s} max {r.max():.2e}  p99.9 {np.quantile(r, 0.999):.2e}", flush=True)
-se.to_bf16 = bf16
