@@ -123,6 +123,15 @@ int r2l_read_ray_shards(const char* const* paths, int n_paths, float* dst_host, 
  * hyper[1] = 1 / sqrt(1 - beta2^step) (r2l_adam_hyper computes them on the host exactly as r2l_adam_step does).  A train
  * step captured in a CUDA graph is replayed with the learning-rate schedule of main.py:1181-1195 by refreshing 8 bytes. */
 int r2l_adam_hyper(double lr, double beta1, double beta2, int64_t step, float* hyper_host /* [2], host */);
+/* The same scalars computed on the DEVICE from device-resident counters (one tiny launch): counters[0] (the schedule's
+ * global_step, main.py:1175-1195) and counters[1] (Adam's step) are incremented, then hyper[0..1] as above and hyper[2] = lr
+ * with lr = lrate * decay_rate^((step - warmup_end_iter) / decay_steps), or the linear warm-up
+ * (lrate - warmup_start_lr) / warmup_end_iter * step + warmup_start_lr while step < warmup_end_iter (0 = no warm-up).
+ * Nothing the step depends on lives in host memory: a host that enqueues iterations ahead of the GPU, or a replayed CUDA
+ * graph, applies the scalars of the iteration being executed. */
+int r2l_adam_schedule_dev(double lrate, double warmup_start_lr, double warmup_end_iter, double decay_rate, double decay_steps,
+                          double beta1, double beta2, int64_t* counters /* [2], device */, float* hyper /* [3], device */,
+                          void* stream);
 int r2l_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double beta1, double beta2,
                       double eps, const float* hyper, void* stream);
 
@@ -145,9 +154,16 @@ int r2l_debug_set_stats(long long* stats);
 /* Launch form of the chain kernels (r2l_b200/csrc/chain.cu): 0 = single CTA per 128-ray tile, 1 = CTA pair (tcgen05
  * cta_group::2, M = 256) with one tile per CTA, 2 = CTA pair sharing one tile (cta_group::2, M = 128, 64 rays per CTA:
  * 0.69 of the latency per tile, the form for small batches), -1 = default = chosen per call (form 2 while the batch
- * leaves SM pairs idle, i.e. tiles <= SMs / 2, form 1 otherwise).  All forms issue their MMAs in the same order: results
- * are bit-identical, whichever form a call takes.  Process-wide; buffers sized by the *_bytes queries fit every form. */
+ * leaves SM pairs idle, i.e. tiles <= SMs / 2, form 1 otherwise).  Forms 0 and 1 give bit-identical results; form 2 keeps
+ * the residual stream out of the tensor core's truncating accumulator (fresh accumulator per GEMM, fp32 residual add in the
+ * epilogue) and agrees with them to ~1e-4 relative, being the more accurate one.  Process-wide; buffers sized by the
+ * *_bytes queries fit every form. */
 int r2l_set_pair_mode(int mode);
+
+/* Form 2 multiplies every accumulator it reads by (1 + eps) to undo, in expectation, the round-toward-zero of the tensor
+ * core's fp32 accumulation: eps_body for the K = 256 GEMMs, eps_head for the K = 1024 head.  The library's defaults are
+ * calibrated on B200 (tools/gpu_accum_calibrate.py); this call overrides them for such measurements.  Process-wide. */
+int r2l_debug_set_accum_debias(float eps_body, float eps_head);
 
 /* Weight gradients of r2l_backward when the ray batch is cut into pieces that run on different SMs (small batches, where
  * the weight-gradient kernel overlaps the backward chain): 0 (default) = every piece adds its result into `grads` with

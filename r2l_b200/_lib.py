@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libr2l_b200.so")
+LIB_PATH = os.environ.get("R2L_LIB_OVERRIDE") or os.path.join(CSRC, "libr2l_b200.so")   # (override: A/B timing of an older build, tools only)
 
 _lib = None
 
@@ -46,11 +46,13 @@ _PROTOTYPES = {
                               c_void_p]),
     "r2l_read_ray_shards": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int]),
     "r2l_adam_hyper": (c_int, [c_double, c_double, c_double, c_int64, c_void_p]),
+    "r2l_adam_schedule_dev": (c_int, [c_double, c_double, c_double, c_double, c_double, c_double, c_double, c_void_p, c_void_p, c_void_p]),
     "r2l_adam_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_void_p, c_void_p]),
     "r2l_loss_scratch_bytes": (c_size_t, []),
     "r2l_mse_loss_grad": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "r2l_debug_set_stats": (c_int, [c_void_p]),
     "r2l_set_pair_mode": (c_int, [c_int]),
+    "r2l_debug_set_accum_debias": (c_int, [c_float, c_float]),
     "r2l_set_deterministic": (c_int, [c_int]),
     "r2l_debug_set_dw_schedule": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "r2l_debug_set_trace": (c_int, [c_void_p]),
@@ -82,6 +84,8 @@ def lib() -> ctypes.CDLL:
                 "(r2l_b200 has no CPU or PyTorch fallback for the hot path)")
         handle = ctypes.CDLL(LIB_PATH)
         for name, (restype, argtypes) in _PROTOTYPES.items():
+            if os.environ.get("R2L_LIB_OVERRIDE") and not hasattr(handle, name):
+                continue
             fn = getattr(handle, name)  # AttributeError if the ABI and the header drift apart
             fn.restype = restype
             fn.argtypes = argtypes

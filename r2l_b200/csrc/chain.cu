@@ -78,6 +78,13 @@ static_assert(chain_smem_bytes(kFormSingle) <= 232448 && chain_smem_bytes(kFormP
               chain_smem_bytes(kFormHalf) <= 232448, "exceeds the 227 KiB dynamic shared memory limit");
 
 constexpr uint32_t kTmemZ = 0;
+// half form only (its accumulators are 128 columns wide, so TMEM has room): Y = [256, 384), the accumulator of every GEMM
+// whose result joins the residual stream (the head, the second Linear of a block, g += dh W1 in the backward).  The tensor
+// core truncates its fp32 accumulator after every MMA (round toward zero; measured: DESIGN.md section 4 "Precision"), so
+// accumulating 43 blocks x 48 MMAs straight onto the stream biases it by ~1e-4.  In the half form every GEMM therefore starts
+// from zero, its small split terms are issued first, and the epilogue adds the result to the stream in fp32 (round to
+// nearest); Z is then plain storage for the stream (tcgen05.ld / st by the epilogue threads).
+constexpr uint32_t kTmemY = 256;
 
 // barrier slots (8 bytes each) inside kSmemBar
 enum : uint32_t {
@@ -200,6 +207,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  if (warp < 4) {
   if (warp == 0) {
     // ======================= weight producer =======================
     if (lane == 0) {
@@ -251,70 +259,63 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
     // At 64 cycles per MMA the ~100-cycle latency of a barrier probe would dominate a thread that waits for one barrier
     // after the other.  So the whole warp probes: lane i < 16 watches the operand barrier of (slot i / 4, k-step i % 4),
     // lanes 16..23 my weight stages, lanes 24..31 the peer's; one ballot tells the warp everything that has become ready.
-    // The issue ORDER is fixed and the same as in the other forms (chunk 0 k-step by k-step: A_hi W_hi, A_lo W_hi; then
-    // A_hi W_lo; chunks 1..3: 4 x A_hi W_hi, 4 x A_lo W_hi, 4 x A_hi W_lo), so all forms accumulate in the same order
-    // and give bit-identical results.
+    // Unlike the other forms this one never accumulates onto the residual stream (see kTmemY): results agree with theirs to
+    // rounding, not bit for bit.
     static_assert(!HALF || kNumWStages == 8, "one group of four K chunks = one turn of the weight ring");
     constexpr uint32_t idesc = umma_idesc_f16(128, 256, 0, 0);
     uint32_t group = 0;        // groups of four K chunks (= 8 weight images = 16 operand units) issued so far
     uint32_t ready = 0;        // barriers of the current group known to have completed (bit = lane that watches it)
     const uint32_t my_bar = lane < 16 ? bar(kBarAMma + lane) : lane < 24 ? bar(kBarWFull + lane - 16) : bar(kBarWPeer + lane - 24);
-    long long t_a = 0, t_w = 0, n_probe = 0;   // debug statistics: cycles spent probing for operands / for weights only
+
     auto need = [&](uint32_t mask) {
       uint32_t spins = 0;
       while ((ready & mask) != mask) {
-        const long long t0 = p.stats ? clock64() : 0;
-        const bool waits_a = (~ready & mask & 0xffffu) != 0;
         const bool ok = ((ready >> lane) & 1u) || mbar_test_wait(my_bar, group & 1u);
         ready = __ballot_sync(0xffffffffu, ok);
         if (++spins > R2L_SPIN_LIMIT) __trap();
-        if (p.stats) { (waits_a ? t_a : t_w) += clock64() - t0; ++n_probe; }
       }
       __syncwarp();   // orders the issuing lane behind the acquire of whichever lane saw the phase complete
     };
-    const long long t_begin = p.stats ? clock64() : 0;
     for (int pt = pair_id; pt < num_ptiles; pt += num_pairs) {
       for (int l = 0; l < kLayers; ++l) {
         const bool head = !kIsBwd && l == 0;
         const bool to_h = kIsBwd ? ((l & 1) == 0) : ((l & 1) != 0);
-        const bool fresh = to_h || head;
-        const uint32_t d = tmem_base + (to_h ? kTmemH : kTmemZ);
+        // every GEMM starts from a zeroed accumulator: H (hidden layer / its gradient) or Y (joins the stream in the epilogue)
+        const uint32_t d = tmem_base + (to_h ? kTmemH : kTmemY);
         const bool tr = p.trace != nullptr && pt == pair_id;
         for (int g = 0; g < (head ? kSamples / 4 : 1); ++g, ++group) {
           ready = 0;
+          // Issue order inside a K chunk: first its SMALL split terms (A_hi W_lo, A_lo W_hi: ~2^-11 of the result), k-step by
+          // k-step as the epilogue publishes them, then the four A_hi W_hi instructions.  After the last k-step of a layer is
+          // published only 6 instructions remain to be issued (12 with the large term first).
 #pragma unroll
           for (uint32_t c = 0; c < 4; ++c) {   // slot; stage 2c holds W_hi, stage 2c + 1 W_lo of this K chunk
             const uint32_t a_hi = smem_base + kSmemA + c * kSlotBytes, a_lo = a_hi + kPlane;
             const uint32_t b_hi = smem_base + kSmemW + (2 * c) * kWStageBytes, b_lo = b_hi + kWStageBytes;
-            const uint32_t w_hi = (1u << (16 + 2 * c)) | (1u << (24 + 2 * c)), w_lo = w_hi << 1;
+            const uint32_t w_both = (3u << (16 + 2 * c)) | (3u << (24 + 2 * c));   // my and the peer's halves of both stages
 #pragma unroll
             for (uint32_t ks = 0; ks < 4; ++ks) {
-              need((1u << (4 * c + ks)) | w_hi);
+              need((1u << (4 * c + ks)) | w_both);
               // TMEM hazards (the epilogue's tcgen05.ld / st of earlier layers vs this layer's accumulator writes) are
               // all behind the first operand barrier of a layer: one tcgen05 fence per group is enough
               if (c == 0 && ks == 0) tc_fence_after_sync();
               if (elect_one_sync()) {
                 if (tr && g == 0 && c == 0 && ks == 0) p.trace[((int64_t)blockIdx.x * 5 + 0) * 96 + l] = clock64();
-                umma_f16_pair(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b_hi + 32 * ks, 16, 1024), idesc,
-                               (fresh && g == 0 && c == 0 && ks == 0) ? 0u : 1u);
-                if (c == 0) umma_f16_pair(d, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw128(b_hi + 32 * ks, 16, 1024), idesc, 1u);
+                umma_f16_pair(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b_lo + 32 * ks, 16, 1024), idesc,
+                              (g == 0 && c == 0 && ks == 0) ? 0u : 1u);
+                umma_f16_pair(d, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw128(b_hi + 32 * ks, 16, 1024), idesc, 1u);
               }
             }
-            need(w_lo);   // (probed early: its latency hides behind the MMAs just queued)
             if (elect_one_sync()) {
-              if (c != 0) {
-#pragma unroll
-                for (uint32_t ks = 0; ks < 4; ++ks)
-                  umma_f16_pair(d, umma_desc_sw128(a_lo + 32 * ks, 16, 1024), umma_desc_sw128(b_hi + 32 * ks, 16, 1024), idesc, 1u);
-              }
-              umma_commit_pair(bar(kBarWEmpty + 2 * c));       // W_hi of this chunk has been read
+              umma_commit_pair(bar(kBarWEmpty + 2 * c + 1));       // W_lo of this chunk has been read
 #pragma unroll
               for (uint32_t ks = 0; ks < 4; ++ks)
-                umma_f16_pair(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b_lo + 32 * ks, 16, 1024), idesc, 1u);
-              umma_commit_pair(bar(kBarWEmpty + 2 * c + 1));
+                umma_f16_pair(d, umma_desc_sw128(a_hi + 32 * ks, 16, 1024), umma_desc_sw128(b_hi + 32 * ks, 16, 1024), idesc, 1u);
+              umma_commit_pair(bar(kBarWEmpty + 2 * c));
               if (head) umma_commit_pair(bar(kBarAEmpty + c));   // the head's A chunks recycle through the 4 slots
             }
           }
+          __syncwarp();
         }
         if (elect_one_sync()) {
           umma_commit_pair(bar(kBarAccFull));
@@ -323,13 +324,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
         __syncwarp();
       }
     }
-    if (p.stats && lane == 0) {
-      p.stats[blockIdx.x * 8 + 5] = global_timer_ns();
-      p.stats[blockIdx.x * 8 + 0] = n_probe;     // (the slot the other forms use for the head's operand waits)
-      p.stats[blockIdx.x * 8 + 1] = t_a;
-      p.stats[blockIdx.x * 8 + 2] = t_w;
-      p.stats[blockIdx.x * 8 + 4] = clock64() - t_begin;
-    }
+    if (p.stats && lane == 0) p.stats[blockIdx.x * 8 + 5] = global_timer_ns();
   } else if (warp == 1) {
     // ======================= MMA issuer (pair form: leader CTA only) =======================
     // The whole warp walks the schedule and waits; one elected lane issues.  (Issuing from inside `if (lane == 0)` makes
@@ -508,7 +503,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
       // drain: wait for the writes to land
       bulk_wait_all<0>();
     }
-  } else if (warp >= 4) {
+  }
+  } else {
     // ======================= encoder / epilogue =======================
     const uint32_t ew = warp - 4;
     const uint32_t q = ew & 3u;       // TMEM lane quarter (== warp % 4)
@@ -525,12 +521,13 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
     const float* cumbias = reinterpret_cast<const float*>(p.packed + kPackOffCumBias);
     const float* headb = reinterpret_cast<const float*>(p.packed + kPackOffHeadB);
     const float* b1 = reinterpret_cast<const float*>(p.packed + kPackOffB1);
+    const float* b2 = reinterpret_cast<const float*>(p.packed + kPackOffB2);
     const float* tailw = reinterpret_cast<const float*>(p.packed + kPackOffTailW);
     const float* tailb = reinterpret_cast<const float*>(p.packed + kPackOffTailB);
     float* hrow = p.scratch + ((int64_t)blockIdx.x * kTileM + row) * kWidth;
     uint32_t acc_phase = 0;
     uint32_t saved_phase = 0;   // per-slot parity of kBarASaved
-    (void)cumbias; (void)headb; (void)b1; (void)tailb; (void)tail_smem;
+    (void)cumbias; (void)headb; (void)b1; (void)b2; (void)tailb; (void)tail_smem;
     // Epilogue column ownership inside a 64-column chunk: k-steps g0 = qt>>1 and g0+2, and inside each k-step the
     // 8-column unit u = qt&1, i.e. the 16-byte operand units 2g+u.  K-steps 0/2 belong to the warps with qt in {0,1},
     // k-steps 1/3 to qt in {2,3}: the first 16 columns of a layer's output are ready after 8 warps did 8 columns each.
@@ -693,7 +690,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
             v[4 * i + 3] = fmaf(dl[2], w2.w, fmaf(dl[1], w1.w, dl[0] * w0.w));
           }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(v[i] * kWeightScale);   // Z is kept in accumulator units
+          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(HALF ? v[i] : v[i] * kWeightScale);   // pair / single: Z in accumulator units
           tmem_st8(tmem_row + kTmemZ + tmem_col(c) + 16u * qt, &r[0]);
           tmem_st8(tmem_row + kTmemZ + tmem_col(c) + 16u * qt + 8, &r[8]);
 #pragma unroll
@@ -717,7 +714,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
         const bool relu = !kIsBwd && ((l == 0) || from_h);
         const float* bias = nullptr;
         if constexpr (!kIsBwd)
-          bias = l == 0 ? headb : ((l & 1) ? b1 + (l >> 1) * kWidth : cumbias + (l >> 1) * kWidth);
+          bias = l == 0 ? headb : ((l & 1) ? b1 + (l >> 1) * kWidth : (HALF ? b2 + ((l >> 1) - 1) * kWidth : cumbias + (l >> 1) * kWidth));
         // backward: mask source = hi plane of a saved forward operand image.
         //   even j (da -> dh): a_k with k = 42 - j/2, forward saved chunk index 16 + 4*(2k+1) + c
         //   last (j = 85):     h (= A_z(0), forward saved chunks 16 + c), applied to g_0 + dL/dz_43
@@ -758,6 +755,37 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
 #pragma unroll
           for (uint32_t cc = 0; cc < kMyChunks; ++cc) wait_saved(my_chunk(cc), false);
         }
+        // half form: the GEMM result sits in H or Y; when it joins the stream (!from_h) the stream's current value is read
+        // from Z beside it, the sum is formed in fp32 and written back to Z (the head writes h there).  No MMA touches Z, so
+        // the first chunk's stream values are fetched while the layer's MMAs still run.
+        const bool joins = HALF && !from_h;
+        const bool has_old = joins && (kIsBwd || l > 0);
+        // accumulator -> value: 1 / kWeightScale, times (1 + eps) in the half form to undo in expectation what the tensor
+        // core's truncating accumulation took from the sum (ChainParams::inv_body / inv_head)
+        const float inv = HALF ? ((!kIsBwd && l == 0) ? p.inv_head : p.inv_body) : kInvWeightScale;
+        // The value this thread forms from an accumulator element r is ALWAYS fmaf(r, inv, bq): bq = bias (forward), 0
+        // (backward), plus the stream value when the result joins the stream - added into bq here, before the accumulator
+        // wait, so that the path from "accumulator complete" to the first publish is the same short code in every layer
+        // ((z + b2) + y instead of the reference's (y + b2) + z: one fp32 rounding each, either way).
+        auto add_stream = [&](uint32_t cc) {      // bq += Z[my two units of chunk cc]; warp-uniform branch at the call
+          uint32_t zo[16];
+          const uint32_t tz = tmem_row + kTmemZ + 64u * cc + 8u * uu;
+          tmem_ld8(tz + 16u * g0, &zo[0]);
+          tmem_ld8(tz + 16u * (g0 + 2), &zo[8]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            bq[2 * h].x += __uint_as_float(zo[8 * h + 0]); bq[2 * h].y += __uint_as_float(zo[8 * h + 1]);
+            bq[2 * h].z += __uint_as_float(zo[8 * h + 2]); bq[2 * h].w += __uint_as_float(zo[8 * h + 3]);
+            bq[2 * h + 1].x += __uint_as_float(zo[8 * h + 4]); bq[2 * h + 1].y += __uint_as_float(zo[8 * h + 5]);
+            bq[2 * h + 1].z += __uint_as_float(zo[8 * h + 6]); bq[2 * h + 1].w += __uint_as_float(zo[8 * h + 7]);
+          }
+        };
+        if constexpr (kIsBwd) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) bq[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (has_old) add_stream(0);
         mbar_wait(bar(kBarAccFull), acc_phase);
         acc_phase ^= 1u;
         tc_fence_after_sync();
@@ -766,10 +794,17 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
         for (uint32_t cc = 0; cc < kMyChunks; ++cc) {
           const uint32_t c = my_chunk(cc);
           uint32_t r[16];
-          const uint32_t tacc = tmem_row + (from_h ? kTmemH : kTmemZ) + 64u * cc + 8u * uu;
+          const uint32_t tacc = tmem_row + (from_h ? kTmemH : (HALF ? kTmemY : kTmemZ)) + 64u * cc + 8u * uu;
           tmem_ld8(tacc + 16u * g0, &r[0]);
           tmem_ld8(tacc + 16u * (g0 + 2), &r[8]);
-          if (cc > 0) load_side(c);
+          if (cc > 0) {
+            load_side(c);
+            if constexpr (kIsBwd) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) bq[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (has_old) add_stream(cc);   // (its wait also covers the two accumulator loads just issued)
+          }
           if (produces_chunk) {
             if constexpr (HALF) {
               if (feeds_mma) { arrive_unit(c, 1 - g0); arrive_unit(c, 3 - g0); }   // the k-steps of this chunk I do not write
@@ -786,31 +821,40 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
             float v[8];
             if constexpr (!kIsBwd) {
               // the accumulators hold kWeightScale * (a . W): the rescale is an exact power of two inside the bias add
-              v[0] = fmaf(__uint_as_float(r[8 * h + 0]), kInvWeightScale, bq[2 * h].x);
-              v[1] = fmaf(__uint_as_float(r[8 * h + 1]), kInvWeightScale, bq[2 * h].y);
-              v[2] = fmaf(__uint_as_float(r[8 * h + 2]), kInvWeightScale, bq[2 * h].z);
-              v[3] = fmaf(__uint_as_float(r[8 * h + 3]), kInvWeightScale, bq[2 * h].w);
-              v[4] = fmaf(__uint_as_float(r[8 * h + 4]), kInvWeightScale, bq[2 * h + 1].x);
-              v[5] = fmaf(__uint_as_float(r[8 * h + 5]), kInvWeightScale, bq[2 * h + 1].y);
-              v[6] = fmaf(__uint_as_float(r[8 * h + 6]), kInvWeightScale, bq[2 * h + 1].z);
-              v[7] = fmaf(__uint_as_float(r[8 * h + 7]), kInvWeightScale, bq[2 * h + 1].w);
+              v[0] = fmaf(__uint_as_float(r[8 * h + 0]), inv, bq[2 * h].x);
+              v[1] = fmaf(__uint_as_float(r[8 * h + 1]), inv, bq[2 * h].y);
+              v[2] = fmaf(__uint_as_float(r[8 * h + 2]), inv, bq[2 * h].z);
+              v[3] = fmaf(__uint_as_float(r[8 * h + 3]), inv, bq[2 * h].w);
+              v[4] = fmaf(__uint_as_float(r[8 * h + 4]), inv, bq[2 * h + 1].x);
+              v[5] = fmaf(__uint_as_float(r[8 * h + 5]), inv, bq[2 * h + 1].y);
+              v[6] = fmaf(__uint_as_float(r[8 * h + 6]), inv, bq[2 * h + 1].z);
+              v[7] = fmaf(__uint_as_float(r[8 * h + 7]), inv, bq[2 * h + 1].w);
               if (relu) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
               }
-              if (l == 0) {
-                // z_0 = h: seed the TMEM residual stream and keep h for the outer skip (:543)
-                uint32_t w[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) w[i] = __float_as_uint(v[i] * kWeightScale);   // Z is kept in accumulator units
-                tmem_st8(tmem_row + kTmemZ + tmem_col(c) + 16u * g + 8u * uu, w);
+              if (l == 0) {   // z_0 = h is kept for the outer skip (:543)
                 reinterpret_cast<float4*>(hrow + col)[0] = make_float4(v[0], v[1], v[2], v[3]);
                 reinterpret_cast<float4*>(hrow + col)[1] = make_float4(v[4], v[5], v[6], v[7]);
+              }
+              if constexpr (!HALF) if (l == 0) {   // pair / single: seed the in-place residual stream, in accumulator units
+                uint32_t w[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w[i] = __float_as_uint(v[i] * kWeightScale);
+                tmem_st8(tmem_row + kTmemZ + tmem_col(c) + 16u * g + 8u * uu, w);
                 tmem_st_wait();
               }
             } else {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * h + i]) * kInvWeightScale;
+              // g += dh W1 when the result joins the stream (bq holds g), else bq = 0
+              v[0] = fmaf(__uint_as_float(r[8 * h + 0]), inv, bq[2 * h].x);
+              v[1] = fmaf(__uint_as_float(r[8 * h + 1]), inv, bq[2 * h].y);
+              v[2] = fmaf(__uint_as_float(r[8 * h + 2]), inv, bq[2 * h].z);
+              v[3] = fmaf(__uint_as_float(r[8 * h + 3]), inv, bq[2 * h].w);
+              v[4] = fmaf(__uint_as_float(r[8 * h + 4]), inv, bq[2 * h + 1].x);
+              v[5] = fmaf(__uint_as_float(r[8 * h + 5]), inv, bq[2 * h + 1].y);
+              v[6] = fmaf(__uint_as_float(r[8 * h + 6]), inv, bq[2 * h + 1].z);
+              v[7] = fmaf(__uint_as_float(r[8 * h + 7]), inv, bq[2 * h + 1].w);
               if (last) {  // + dL/dz_43 through the outer skip
                 const float4 s0 = reinterpret_cast<const float4*>(hrow + col)[0];
                 const float4 s1 = reinterpret_cast<const float4*>(hrow + col)[1];
@@ -837,6 +881,14 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
                 make_visible();
                 arrive_sub(g);
                 if (tr && g == 0) p.trace[((int64_t)blockIdx.x * 5 + 3) * 96 + l] = clock64();
+              }
+            }
+            if constexpr (HALF) {
+              if (joins) {   // the stream's new value goes back to Z behind the publish (warp-uniform branch)
+                uint32_t w[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w[i] = __float_as_uint(v[i]);
+                tmem_st8(tmem_row + kTmemZ + 64u * cc + 16u * g + 8u * uu, w);
               }
             }
             if constexpr (!kIsBwd) {
@@ -884,6 +936,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) r2l_chain_kernel(const __gri
             }
           }
         }
+        if (joins) tmem_st_wait();   // the stream values written above are read back by this thread two layers on
         if (tr) p.trace[((int64_t)blockIdx.x * 5 + 4) * 96 + l] = clock64();
       }
       if constexpr (!kIsBwd) {

@@ -21,6 +21,7 @@ struct ChainParams {
   uint8_t* rgb8;          // optional forward out [N,3] uint8 = to8b(rgb) (nerf_raybased.py:16); nullptr = off
   int img_h, img_w;       // kInputPose: frame size; pixel (i = column, j = row) of ray r is r % (H W)
   float focal;            // kInputPose: focal length in pixels
+  float inv_body, inv_head;  // half form: accumulator -> value factors 1 / kWeightScale * (1 + eps), see c_api.cu: g_debias
   float* scratch;         // [gridDim.x][128][256] fp32: head output (fwd) / dL/dz_43 (bwd) for the outer skip
   long long* stats;       // optional [gridDim.x][8] cycle counters (debug), nullptr in production
   long long* trace;       // optional [gridDim.x][5][96] clock64 stamps of the first tile's layers (debug)
@@ -103,6 +104,10 @@ cudaError_t launch_raw2outputs(const float* raw, const float* z_vals, const floa
 cudaError_t launch_sample_pdf_merge(const float* z_vals, const float* weights, const float* u, int64_t u_stride, int64_t n_rays,
                                     int S, int M, float* z_samples, float* z_merged, const float* bins_in, cudaStream_t stream);
 cudaError_t launch_embed(const float* x, float* out, int64_t n, int dim, int L, int style, cudaStream_t stream);
+struct AdamSchedule {
+  double lrate, warmup_start_lr, warmup_end, decay_rate, decay_steps, beta1, beta2;   // warmup_end = 0: no warm-up
+};
+cudaError_t launch_adam_schedule(const AdamSchedule& sc, long long* counters, float* hyper, cudaStream_t stream);
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float w1, float beta2, float w2, float eps,
                         float step_size, float inv_bc2_sqrt, const float* hyper, cudaStream_t stream);
 cudaError_t launch_mse_loss_grad(const float* rgb, const float* target, int64_t n, int target_stride, float grad_scale, float loss_scale,

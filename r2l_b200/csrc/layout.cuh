@@ -32,6 +32,14 @@ constexpr int64_t kNumParams = kOffTailB + kOutDim;                   // 5917187
 __host__ __device__ constexpr int64_t off_body_w(int l) { return kOffBody + (int64_t)l * kLinearStride; }
 __host__ __device__ constexpr int64_t off_body_b(int l) { return off_body_w(l) + (int64_t)kWidth * kWidth; }
 
+// ---- operand format ----
+// Every tensor-core operand plane in this library is IEEE fp16.  A value is carried as two planes x ~= hi + lo (ptx.cuh:
+// split2): 22 significant bits while |x| >= 2^-3, an absolute floor of 2^-25 below (fp16 subnormals).  Weights are therefore
+// packed pre-multiplied by kWeightScale (their lo planes would otherwise sit in the subnormal range: |w| ~ 2^-5 at default
+// init) and every accumulator read multiplies by 1 / kWeightScale, an exact power of two.
+constexpr float kWeightScale = 64.f;
+constexpr float kInvWeightScale = 1.f / kWeightScale;
+
 // ---- tiles ----
 constexpr int kTileM = 128;    // rays per CTA tile = UMMA M = TMEM lanes
 constexpr int kChunkK = 64;    // K elements per 128-byte swizzled row
@@ -56,13 +64,14 @@ constexpr int kNumImages = kImgBodyT + 8 * kBodyLayers; // 1440
 constexpr int64_t kPackedImagesBytes = (int64_t)kNumImages * kWImageBytes;  // 47,185,920
 // fp32 side tables appended after the images
 //   cumbias[44][256] : cumbias[k] = sum_{j<k} b2_j  (the residual stream lives un-biased in TMEM)
-//   headb[256], b1[43][256], tailw[3][256], tailb[4]
+//   headb[256], b1[43][256], tailw[3][256], tailb[4], b2[43][256]
 constexpr int64_t kPackOffCumBias = kPackedImagesBytes;
 constexpr int64_t kPackOffHeadB = kPackOffCumBias + 44 * kWidth * 4;
 constexpr int64_t kPackOffB1 = kPackOffHeadB + kWidth * 4;
 constexpr int64_t kPackOffTailW = kPackOffB1 + kBlocks * kWidth * 4;
 constexpr int64_t kPackOffTailB = kPackOffTailW + kOutDim * kWidth * 4;
-constexpr int64_t kPackedBytes = kPackOffTailB + 16;
+constexpr int64_t kPackOffB2 = kPackOffTailB + 16;                       // b2[43][256]: second-layer biases as they are
+constexpr int64_t kPackedBytes = kPackOffB2 + kBlocks * kWidth * 4;
 
 // Fused-PE feature order inside K-chunk s (= sample point s of the ray), 64 slots:
 //   pair p = c*10 + f (coordinate c, frequency f): slot 2p = sin(x_c 2^f), slot 2p+1 = cos(x_c 2^f)

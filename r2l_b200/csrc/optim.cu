@@ -44,6 +44,31 @@ __global__ void __launch_bounds__(256) r2l_adam_kernel(float* __restrict__ p, co
   }
 }
 
+// Step scalars of the training iteration computed ON THE DEVICE from device-resident counters, so that a replayed CUDA
+// graph (or a host that runs many iterations ahead of the GPU) applies exactly the learning rate and bias corrections of
+// the iteration it executes.  counters[0] = global_step (the LR schedule's argument, main.py:1181-1195), counters[1] =
+// Adam's step; both are incremented here, then
+//   hyper[0] = lr / (1 - beta1^step)   hyper[1] = 1 / sqrt(1 - beta2^step)   hyper[2] = lr
+// in double precision, as torch.optim.Adam and the reference's schedule compute them on the host.
+__global__ void r2l_adam_schedule_kernel(AdamSchedule sc, long long* __restrict__ counters, float* __restrict__ hyper) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const long long gstep = ++counters[0];
+  const long long astep = ++counters[1];
+  double lr;
+  if (sc.warmup_end > 0.0 && (double)gstep < sc.warmup_end)
+    lr = (sc.lrate - sc.warmup_start_lr) / sc.warmup_end * (double)gstep + sc.warmup_start_lr;
+  else
+    lr = sc.lrate * pow(sc.decay_rate, ((double)gstep - sc.warmup_end) / sc.decay_steps);
+  hyper[0] = (float)(lr / (1.0 - pow(sc.beta1, (double)astep)));
+  hyper[1] = (float)(1.0 / sqrt(1.0 - pow(sc.beta2, (double)astep)));
+  hyper[2] = (float)lr;
+}
+
+cudaError_t launch_adam_schedule(const AdamSchedule& sc, long long* counters, float* hyper, cudaStream_t stream) {
+  r2l_adam_schedule_kernel<<<1, 32, 0, stream>>>(sc, counters, hyper);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float w1, float beta2, float w2, float eps,
                         float step_size, float inv_bc2_sqrt, const float* hyper, cudaStream_t stream) {
   int dev = 0, sms = 148;

@@ -14,6 +14,7 @@ __device__ __forceinline__ void pack_tables(const float* __restrict__ params, ui
   float* b1 = reinterpret_cast<float*>(packed + kPackOffB1);
   float* tailw = reinterpret_cast<float*>(packed + kPackOffTailW);
   float* tailb = reinterpret_cast<float*>(packed + kPackOffTailB);
+  float* b2t = reinterpret_cast<float*>(packed + kPackOffB2);
   // every load first (independent, read-only path): the block's run time is one memory round trip, not 43
   float b2[kBlocks], b1v[kBlocks];
 #pragma unroll
@@ -32,6 +33,7 @@ __device__ __forceinline__ void pack_tables(const float* __restrict__ params, ui
     acc = __fadd_rn(acc, b2[k]);
     cum[(k + 1) * kWidth + col] = acc;
     b1[k * kWidth + col] = b1v[k];
+    b2t[k * kWidth + col] = b2[k];
   }
   headb[col] = hb;
 #pragma unroll

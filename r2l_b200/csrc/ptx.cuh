@@ -82,6 +82,17 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
+// Register re-allocation between warp groups (4 consecutive warps; executed by all of their threads): the kernel is
+// launched with 65536 / threads registers per thread, warp groups that need few give some back, the others take them.
+template <uint32_t N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <uint32_t N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 // ----------------------------------------------------------------------------------------------
 // thread-block clusters (CTA pairs) and cross-CTA mbarrier traffic
 // ----------------------------------------------------------------------------------------------
@@ -245,15 +256,6 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   const uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }
-
-// Operand element format of every tensor-core operand plane in this library: IEEE fp16.  A value is carried as two planes
-// x ~= hi + lo (split2 below): 22 significant bits while |x| >= 2^-3, an absolute floor of 2^-25 below (fp16 subnormals).
-// Weights are therefore packed pre-multiplied by kWeightScale (their lo planes would otherwise sit in the subnormal range:
-// |w| ~ 2^-5 at default init) and every accumulator read multiplies by 1 / kWeightScale, an exact power of two.
-// CPU study (tools/cpu_gradient_precision_study.py, 1024 rays): bf16 planes 1.9e-3 flat gradient error, fp16 planes 3.4e-4,
-// fp16 planes with scaled weights 2.5e-6 = the error of plain fp32 arithmetic.
-constexpr float kWeightScale = 64.f;
-constexpr float kInvWeightScale = 1.f / kWeightScale;
 
 // Instruction descriptor (32 bit) for kind::f16, F16 x F16 -> FP32.
 //   [4,6) D fmt (1 = f32)  [7,10) A fmt (0 = f16, 1 = bf16)  [10,13) B fmt  [15] A major (0 = K, 1 = MN)  [16] B major

@@ -152,12 +152,21 @@ class RayShardLoader:
     def next_buffer(self) -> torch.Tensor:
         """The next [shards_per_batch * rows, 9] pinned batch buffer."""
         while len(self._held) >= self.depth - 1:
-            self._free.put(self._held.pop(0))
+            i_old, copied = self._held.pop(0)
+            if copied is not None:
+                copied.synchronize()      # an async H2D copy still reads the buffer: the producer must not refill it yet
+            self._free.put(i_old)
         i, err = self._ready.get()
         if err is not None:
             raise err
-        self._held.append(i)
+        self._held.append([i, None])
         return self.buffers[i]
+
+    def mark_in_flight(self, event) -> None:
+        """Tie the buffer returned by the last next_buffer() to a CUDA event recorded after the asynchronous copy that reads
+        it: the buffer goes back to the producer only once that event has completed (device_batches does this itself; a
+        caller that issues its own non_blocking copies from next_buffer() must, too)."""
+        self._held[-1][1] = event
 
     def __iter__(self):
         return self
@@ -184,6 +193,7 @@ class RayShardLoader:
                 copy_stream.wait_event(consumed[slot])        # the step that read this device buffer has finished
                 dev_bufs[slot].copy_(host, non_blocking=True)
                 events[slot].record(copy_stream)
+            self.mark_in_flight(self._copy_done(copy_stream))   # its own event: events[slot] is re-recorded two batches on
         for s in range(2):
             consumed[s].record(torch.cuda.current_stream(device))
         launch(0)
@@ -195,6 +205,12 @@ class RayShardLoader:
             yield d if packed else (d[:, :3], d[:, 3:6], d[:, 6:9])
             consumed[slot].record(torch.cuda.current_stream(device))
             slot ^= 1
+
+    @staticmethod
+    def _copy_done(stream):
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        return ev
 
     def close(self):
         self._stop = True

@@ -414,6 +414,22 @@ def adam_hyper(lr: float, beta1: float, beta2: float, step: int, out: torch.Tens
     return out
 
 
+def adam_schedule_dev(counters: torch.Tensor, hyper: torch.Tensor, lrate: float, lrate_decay: int, warmup_lr, beta1: float, beta2: float):
+    """Advance the device-resident counters [global_step, adam_step] (int64 CUDA tensor) and write this iteration's Adam
+    scalars into `hyper` (float32 CUDA tensor of >= 3 elements): see r2l_adam_schedule_dev.  Schedule arguments as
+    r2l_b200.trainer.lr_at (main.py:1181-1195)."""
+    if not (counters.is_cuda and counters.dtype == torch.int64 and counters.numel() >= 2 and counters.is_contiguous()):
+        raise RuntimeError("adam_schedule_dev: counters must be a contiguous int64 CUDA tensor of 2 elements")
+    if not (hyper.is_cuda and hyper.dtype == torch.float32 and hyper.numel() >= 3 and hyper.is_contiguous()):
+        raise RuntimeError("adam_schedule_dev: hyper must be a contiguous float32 CUDA tensor of >= 3 elements")
+    start_lr, end_iter = (0.0, 0.0)
+    if warmup_lr:
+        start_lr, end_iter = [float(x) for x in warmup_lr.split(',')]
+    with torch.cuda.device(counters.device):
+        _lib.check(_lib.lib().r2l_adam_schedule_dev(float(lrate), start_lr, end_iter, 0.1, float(lrate_decay) * 1000.0, float(beta1),
+                                                    float(beta2), _ptr(counters), _ptr(hyper), _stream()), "r2l_adam_schedule_dev")
+
+
 def adam_step_dev(params, grads, exp_avg, exp_avg_sq, beta1, beta2, eps, hyper_dev):
     for name, t in (("params", params), ("grads", grads), ("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq), ("hyper", hyper_dev)):
         if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):

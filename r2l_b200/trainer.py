@@ -3,7 +3,7 @@
 
     reference, per iteration                                           here
     ---------------------------------------------------------------   ------------------------------------------------
-    LR schedule, param_group['lr'] = ...            (:1181-1195)       lr_at(step): 8 bytes refreshed per step
+    LR schedule, param_group['lr'] = ...            (:1181-1195)       r2l_adam_schedule_dev: device-side step counters
     hard-ray pool: np.random.permutation + cat      (:1325-1347)       HardRayPool.draw (torch ops on the device)
     sample_train -> positional_embedder -> model    (:1369-1374)       r2l_forward_train (one kernel)
     img2mse * lw_rgb, psnr.item()                   (:1377-1379)       r2l_mse_loss_grad (one kernel, no host sync)
@@ -51,11 +51,16 @@ class HardRayPool:
         else:
             n_in = n_out = int(hard_ratio * batch_size)
         self.n_hard_in, self.n_hard_out = min(n_in, n_out), n_out
-        self.capacity = int(batch_size * hard_mul)
+        if self.n_hard_in <= 0:
+            # the reference's indices[-0:] would append the WHOLE batch every step (main.py:1414 with n_hard_in == 0): a quirk
+            # nobody relies on; refuse instead of silently doing something else
+            raise ValueError(f"HardRayPool: hard_ratio {hard_ratio} selects no ray of a batch of {batch_size}")
+        self.hard_mul = hard_mul
+        self.fill_level = batch_size * hard_mul      # compared as a float, like main.py:1424
         self.batch_size = batch_size
-        # appended in steps of n_hard_in until >= capacity (main.py:1423-1425)
-        step = max(self.n_hard_in, 1)
-        slots = -(-self.capacity // step) * step
+        # appended in steps of n_hard_in until size >= batch_size * hard_mul (main.py:1423-1425)
+        step = self.n_hard_in
+        slots = -(-int(self.fill_level) // step) * step + step
         self.rays = torch.empty((slots, 9), dtype=torch.float32, device=device)
         self.size = 0
         self.full = False
@@ -69,18 +74,19 @@ class HardRayPool:
         self._slots_out = torch.randperm(self.size, device=self.rays.device)[:self.n_hard_out]
         return self.rays[self._slots_out]
 
-    def update(self, rays_o, rays_d, target, per_ray_err):
-        """per_ray_err: mean squared error per ray of the whole batch; only the fresh rays [:batch_size] compete."""
-        if self.n_hard_in <= 0:
-            return
-        order = torch.sort(per_ray_err[:self.batch_size]).indices[-self.n_hard_in:]
+    def update(self, rays_o, rays_d, target, per_ray_err, batch_size=None):
+        """per_ray_err: mean squared error per ray of the whole batch; only the fresh rays [:batch_size] compete (batch_size
+        of THIS call, main.py:1324,:1411-1413; n_hard_in / n_hard_out stay those of the first batch - the ray-shard loader's
+        batches all have N_rand * 4096 rays)."""
+        batch_size = self.batch_size if batch_size is None else int(batch_size)
+        order = torch.sort(per_ray_err[:batch_size]).indices[-self.n_hard_in:]
         hard = torch.cat([rays_o[order], rays_d[order], target[order]], dim=-1)
         if self.full:
             self.rays[self._slots_out[:self.n_hard_in]] = hard
         else:
             self.rays[self.size:self.size + hard.shape[0]] = hard
             self.size += hard.shape[0]
-            if self.size >= self.capacity:
+            if self.size >= batch_size * self.hard_mul:
                 self.full = True
 
 
@@ -109,8 +115,11 @@ class R2LTrainer:
         self.adam_steps = 0
         self.grads = torch.empty(NUM_PARAMS, dtype=torch.float32, device=dev)
         self.packed = ops.pack_weights(model.flat.detach())
-        self.h_hyper = torch.zeros(2, dtype=torch.float32).pin_memory()
-        self.d_hyper = torch.zeros(2, dtype=torch.float32, device=dev)
+        self._flat_seen = (model.flat.data_ptr(), model.flat._version)    # the parameters self.packed was built from
+        # iteration counters [global_step, adam_steps] and the step scalars derived from them live on the DEVICE
+        # (ops.adam_schedule_dev): a host running ahead of the GPU cannot hand an iteration another iteration's learning rate
+        self.d_steps = torch.tensor([start_step, 0], dtype=torch.int64, device=dev)
+        self.d_hyper = torch.zeros(4, dtype=torch.float32, device=dev)
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.h_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
         self.pool = None
@@ -122,7 +131,7 @@ class R2LTrainer:
         n = st["in9"].shape[0]
         if from_host:     # host-fed iteration: the batch comes from the pinned staging rows, the loss goes back to the host
             st["in9"][:st["h9"].shape[0]].copy_(st["h9"], non_blocking=True)
-        self.d_hyper.copy_(self.h_hyper, non_blocking=True)
+        ops.adam_schedule_dev(self.d_steps, self.d_hyper, self.lrate, self.lrate_decay, self.warmup_lr, self.betas[0], self.betas[1])
         kw = dict(rays9=st["in9"])                      # (o | d | rgb) rows: the kernels read the columns in place
         if st["t_rand"] is not None:
             kw.update(t_rand=st["t_rand"], z_lower=self.z_lower, z_diff=self.z_diff)
@@ -180,15 +189,21 @@ class R2LTrainer:
 
     def _begin(self):
         step = self.global_step + 1
-        self.last_lr = lr_at(step, self.lrate, self.lrate_decay, self.warmup_lr)
+        self.last_lr = lr_at(step, self.lrate, self.lrate_decay, self.warmup_lr)   # host mirror, for logs / state_dict only
         self.adam_steps += 1
-        ops.adam_hyper(self.last_lr, self.betas[0], self.betas[1], self.adam_steps, self.h_hyper)
+        # parameters changed behind the trainer's back (model.load_state_dict after construction, a manual write to
+        # model.flat): the packed operand image is stale - rebuild it before this iteration's forward
+        flat = self.model.flat
+        if (flat.data_ptr(), flat._version) != self._flat_seen:
+            ops.pack_weights(flat.detach(), out=self.packed)
+            self._flat_seen = (flat.data_ptr(), flat._version)
 
     def _end(self):
         self.global_step += 1
         # the kernels wrote the parameters and their packed image through raw pointers: tell autograd / the model's cache
         flat = self.model.flat
         torch.autograd.graph.increment_version(flat)
+        self._flat_seen = (flat.data_ptr(), flat._version)
         self.model._packed = self.packed
         self.model._packed_version = (flat.data_ptr(), flat._version, str(flat.device))
 
@@ -211,7 +226,7 @@ class R2LTrainer:
                 st["t_rand"][:batch].copy_(given)
         self._run(st, from_host)
         if self.pool is not None:
-            self.pool.update(st["in9"][:, 0:3], st["in9"][:, 3:6], st["in9"][:, 6:9], st["err"])
+            self.pool.update(st["in9"][:, 0:3], st["in9"][:, 3:6], st["in9"][:, 6:9], st["err"], batch)
         self._end()
         return self.loss
 
@@ -264,3 +279,4 @@ class R2LTrainer:
         self.adam_steps = int(s["step"])
         self.exp_avg.copy_(s["exp_avg"]); self.exp_avg_sq.copy_(s["exp_avg_sq"])
         self.global_step = int(sd.get("global_step", self.global_step))
+        self.d_steps.copy_(torch.tensor([self.global_step, self.adam_steps], dtype=torch.int64))

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert getattr(lib, name) is not None
     assert lib.r2l_abi_version() == 1
-    assert lib.r2l_packed_bytes() == 1440 * 32768 + (44 + 1 + 43 + 3) * 256 * 4 + 16
+    assert lib.r2l_packed_bytes() == 1440 * 32768 + (44 + 1 + 43 + 3) * 256 * 4 + 16 + 43 * 256 * 4
 
 
 def test_c_abi_argument_errors_without_gpu():

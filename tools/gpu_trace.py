@@ -36,3 +36,8 @@ print("  MMA start -> all 48 issued                 ", np.mean(issued[body] - st
 print("  acc complete -> first k-step published     ", np.mean(pub0[body] - accdone[body]))
 print("  first publish -> next layer's first MMA    ", np.mean(start[body + 1] - pub0[body]))
 print("  acc complete -> epilogue done (4 chunks)   ", np.mean(epidone[body] - accdone[body]))
+for name, sel in (("odd layers (first Linear of a block: H -> hidden operand)", body[body % 2 == 1]), ("even layers (second Linear: result joins the stream)", body[body % 2 == 0])):
+    print(name + ": period", np.mean(start[sel + 1] - start[sel]), " MMA start->acc", np.mean(accdone[sel] - start[sel]),
+          " acc->first publish", np.mean(pub0[sel] - accdone[sel]), " publish->next MMA", np.mean(start[sel + 1] - pub0[sel]),
+          " acc->epilogue done", np.mean(epidone[sel] - accdone[sel]))
+
