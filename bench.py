@@ -35,6 +35,35 @@ WORKLOAD = ("lego_noview W256D88 ResMLP train step (fwd+bwd+Adam) on 4096 synthe
             "random-init weights (seed 0), perturb=0")
 
 
+FWD_ALGO_BYTES = 23_668_748 + BATCH * 36   # parameters read once + 24 B in, 12 B out per ray
+
+
+def ncu_page_metrics():
+    """DRAM traffic and tensor-pipe activity of the dominant kernel from the committed `ncu --set full` raw page (profiles/): numbers
+    taken under the profiler are evidence ABOUT the kernel, never bench values."""
+    import csv
+    for name in ("r2_full_4096_raw.csv", "r1_full_4096_raw.csv"):
+        path = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(path):
+            continue
+        try:
+            with open(path, newline="") as f:
+                rows = list(csv.reader(f))
+            head = rows[0]
+            col = {h: i for i, h in enumerate(head)}
+            for r in rows[2:]:
+                if "r2l_chain_kernel<1" in r[col["Kernel Name"]] or "r2l_chain_kernel<(r2l::ChainMode)1" in r[col["Kernel Name"]]:
+                    num = lambda k: float(r[col[k]].replace(",", ""))
+                    unit = lambda k: rows[1][col[k]]
+                    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                    traffic = sum(num(k) * scale.get(unit(k), 1.0) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+                    return {"traffic": traffic, "pipe_active_pct": num("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+                            "source": f"profiles/{name}: dram__bytes_read.sum + dram__bytes_write.sum and sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active (busy SMs) of this kernel at 4096 rays, ncu --set full"}
+        except Exception:
+            continue
+    return {}
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -158,49 +187,84 @@ def cpu_reference_step_fn(n_rays, threads=None):
     return step
 
 
-def best_cpu_threads(n_rays):
-    """The stock PyTorch CPU path does not scale to every core of a big host on these small GEMMs; give the
-    reference its best configuration: try a few intra-op thread counts on one step each and keep the fastest."""
-    import torch
-    cores = os.cpu_count() or 1
-    best = (None, float("inf"))
-    for th in sorted({min(cores, c) for c in (8, 16, 32, 64, cores)}):
-        step = cpu_reference_step_fn(n_rays, th)
-        step()
-        t0 = time.perf_counter()
-        step()
-        dt = time.perf_counter() - t0
-        if dt < best[1]:
-            best = (th, dt)
-        elif dt > 1.5 * best[1]:
-            break   # more threads are only getting slower
-    return best[0]
+def cpu_threads():
+    """Thread policy of the CPU arms, fixed: every host core torch can use, capped at 64 (above that the 256-wide GEMMs
+    of this network only get slower on the hosts of this pool)."""
+    return max(1, min(os.cpu_count() or 1, 64))
+
+
+def base_config(world):
+    """The `config` object both arms print (so that the driver can see they measure the same thing)."""
+    return {"workload": WORKLOAD, "rays_per_gpu": BATCH, "global_batch": BATCH * world,
+            "parallelism": f"dp{world}" if world > 1 else "single"}
 
 
 def run_reference(args):
+    """The reference's own code path on the host cores: stock PyTorch CPU ops (oracle/torch_reference.py restates
+    model/nerf_raybased.py and is pinned bit for bit to fixtures the reference produced, tests/test_host.py), the SAME
+    4096-ray batch and the same step (forward, img2mse, backward, Adam) as our arm; every step is measured, nothing is
+    extrapolated.  Under torchrun only rank 0 works."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
-    sample_rays = 1024   # bounded sample of the 4096-ray batch per step (same per-ray work)
-    threads = best_cpu_threads(sample_rays)
-    step = cpu_reference_step_fn(sample_rays, threads)
+    threads = cpu_threads()
+    step = cpu_reference_step_fn(BATCH, threads)
     for _ in range(max(args.warmup, 1)):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     dt = time.perf_counter() - t0
-    rays_s = sample_rays * args.steps / dt
-    cores = threads
+    rays_s = BATCH * args.steps / dt
+    cfg = base_config(1)
+    cfg["l2"] = "not applicable (CPU arm)"
+    ref_path = ("stock PyTorch CPU ops, oracle/torch_reference.py (restates model/nerf_raybased.py; /root/reference is "
+                "absent on the GPU box and is a Python tree without build metadata: nothing to install)")
     line = {"impl": "reference", "metric": METRIC, "value": rays_s, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps * (BATCH / sample_rays), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "reference code path = stock PyTorch CPU ops (oracle/torch_reference.py restates model/nerf_raybased.py; /root/reference is absent on the GPU box)"},
-            "cpu_baseline": {"value": rays_s, "unit": "rays/s", "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} train steps (fwd+bwd+Adam) on {sample_rays} of the 4096 rays, torch {torch.__version__} CPU, {cores} threads (best of 8/16/32/64/all on this {os.cpu_count()}-core host)"},
+            "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "reference_path": ref_path,
+            "cpu_baseline": {"value": rays_s, "unit": "rays/s", "cores": threads, "kind": "port",
+                             "sample": f"{args.steps} full train steps (fwd + img2mse + bwd + Adam) on the 4096-ray batch, torch {torch.__version__} CPU, "
+                                       f"{threads} threads on this {os.cpu_count()}-core host"},
             "e2e": {"value": rays_s, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def gpu_reference_step_ms(dev, d_ro, d_rd, d_tg, z_vals, reps=10):
+    """The reference's network and train step as stock PyTorch on the GPU ("the meaningful beat-this
+    number"; the reference's own harness is main.py:1124-1133): fp32 (TF32 off) and TF32 matmuls, CUDA events."""
+    import torch
+    from oracle.torch_reference import RefR2L, embed, sample
+    from r2l_b200.nerf_raybased import init_flat_params
+    out = {"what": "oracle/torch_reference.py .cuda(): sample -> embed -> 88 nn.Linear -> img2mse -> backward -> torch.optim.Adam, 4096 rays, CUDA events, "
+                   f"{reps} reps after 3 warm-ups; outside the timed regions of value / e2e", "unit": "ms_per_step"}
+    zt = torch.tensor(z_vals, device=dev)
+    for mode in ("fp32", "tf32"):
+        torch.backends.cuda.matmul.allow_tf32 = mode == "tf32"
+        torch.backends.cudnn.allow_tf32 = mode == "tf32"
+        model = RefR2L().load_flat(init_flat_params(0)).to(dev)
+        opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            loss = ((model(embed(sample(d_ro, d_rd, zt))) - d_tg) ** 2).mean()
+            loss.backward()
+            opt.step()
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            step()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        out[mode] = {"ms_per_step": ms, "rays_per_s": BATCH / (ms * 1e-3)}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -246,8 +310,12 @@ def run_ours(args):
 
     def step_device():
         trainer.step_rays9(d9)
-    # forward chain, loss+grad, backward chain, tail gradients, weight gradients, Adam, pack
-    LAUNCHES_PER_STEP = 7
+    # kernels of ours per iteration, COUNTED by the library on the first (eagerly launched) iteration: schedule scalars,
+    # forward chain, loss + gradient, backward preamble, backward chain, tail gradients, weight gradients, Adam, pack
+    from r2l_b200 import _lib as _l
+    _l.lib().r2l_debug_launch_count(1)
+    step_device()
+    launches_per_step = int(_l.lib().r2l_debug_launch_count(1))
 
     def barrier():
         if world > 1:
@@ -293,10 +361,16 @@ def run_ours(args):
         del ctx
     k_ms /= reps
     achieved_tflops = BATCH * FWD_FLOP_PER_RAY / (k_ms * 1e-3) / 1e12
+    prof = ncu_page_metrics()
+    hbm_gbs = FWD_ALGO_BYTES / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "tensor", "kernel": "r2l_chain_kernel<kFwdTrain, half form> (4096 rays = 32 tiles, one CTA pair per tile: 64 CTAs, tcgen05 cta_group::2 M=128)", "achieved": achieved_tflops,
                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved_tflops / peaks["bf16_tflops"],
-                "traffic": 359.4e6, "traffic_source": "profiles/r1_summary.md section 2c: dram__bytes_read.sum + dram__bytes_write.sum of this kernel at 4096 rays (ncu --set full, profiles/r1_full_4096_raw.csv)", "peak_source": peaks["source"], "kernel_ms": k_ms,
-                "note": "algorithmic fp32 FLOPs; the kernel issues 3x that as bf16 MMAs (hi*hi+lo*hi+hi*lo) to meet the 1e-3 fp32 parity bar, and a 4096-ray batch (32 tiles of 128 rays, two SMs per tile) occupies 64 of 148 SMs"}
+                "traffic": prof.get("traffic"), "traffic_source": prof.get("source"), "peak_source": peaks["source"], "kernel_ms": k_ms,
+                "pipe_active_pct": prof.get("pipe_active_pct"),
+                "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_gbs / peaks["hbm_gbs"],
+                        "algorithmic_bytes": FWD_ALGO_BYTES,
+                        "note": "the weight-read roofline the metric names (23.7 MB of parameters + 36 B/ray): NOT the binding one - arithmetic intensity 2,030 FLOP/B puts this kernel far right of the ridge, the tensor pipe binds (SURVEY.md 8d)"},
+                "note": "algorithmic fp32 FLOPs; the kernel issues 3x that as fp16 MMAs (hi*lo + lo*hi + hi*hi) to meet the 1e-3 fp32 parity bar, and a 4096-ray batch (32 tiles of 128 rays, two SMs per tile) occupies 64 of 148 SMs"}
 
     # ---- the same kernel with every SM busy (148 tiles = 18,944 rays), inference form: kernel quality, not the metric ----
     n_full = 148 * 128
@@ -339,35 +413,40 @@ def run_ours(args):
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    # ---- the reference's code path on the SAME GPU (stock PyTorch: nn.Linear -> cuBLAS, ATen elementwise, torch.optim.Adam): the
+    # number a B200 user of the reference gets today; measured after and outside the timed regions above ----
+    gpu_reference = None
+    if rank == 0 and world == 1:
+        gpu_reference = gpu_reference_step_ms(dev, d_ro, d_rd, d_tg, z_vals)
+
     line = None
     if rank == 0:
         cpu = None
         if world == 1:
-            sample_rays, reps_cpu = 1024, 3
-            cpu_threads = best_cpu_threads(sample_rays)
-            stepc = cpu_reference_step_fn(sample_rays, cpu_threads)
+            reps_cpu, threads = 20, cpu_threads()
+            stepc = cpu_reference_step_fn(BATCH, threads)
             stepc()
             t0 = time.perf_counter()
             for _ in range(reps_cpu):
                 stepc()
             dt = time.perf_counter() - t0
-            cores = cpu_threads
-            cpu = {"value": sample_rays * reps_cpu / dt, "unit": "rays/s", "cores": cores, "kind": "port",
-                   "sample": f"{reps_cpu} train steps on {sample_rays} of the 4096 rays; stock PyTorch CPU ops (oracle/torch_reference.py), {cores} threads (best of 8/16/32/64/all on this {os.cpu_count()}-core host)"}
+            cpu = {"value": BATCH * reps_cpu / dt, "unit": "rays/s", "cores": threads, "kind": "port",
+                   "sample": f"{reps_cpu} full train steps on the 4096-ray batch; stock PyTorch CPU ops (oracle/torch_reference.py), {threads} threads on this {os.cpu_count()}-core host"}
+        cfg = base_config(world)
+        cfg["l2"] = "flushed: a 256 MiB buffer is written between timed iterations (untimed)"
+        timing = {"step": "R2LTrainer.step_rays9 on a resident [N,9] batch: schedule scalars + forward_train + mse loss/grad + backward(chain, dW, tail) + allreduce(N>1) + Adam + pack_weights"
+                          + (" (one CUDA graph replay)" if trainer.use_graph else " (eager launches)")}
         line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32 (bf16x3 split operands, fp32 accumulate)", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "rays_per_gpu": BATCH, "global_batch": n_global,
-                           "parallelism": f"dp{world}" if world > 1 else "single",
-                           "l2": "256 MiB buffer written between timed iterations (L2 flush, untimed)",
-                           "step": "R2LTrainer.step_rays9 on a resident [N,9] batch: forward_train + mse loss/grad + backward(chain, dW, tail) + allreduce(N>1) + Adam + pack_weights"
-                                   + (" (one CUDA graph replay)" if trainer.use_graph else " (eager launches)")},
-                "clocks": sampler.summary(), "gpu_launches": LAUNCHES_PER_STEP * args.steps,
+                "dtype": "f32 (fp16 hi/lo split operands x3 on tcgen05, fp32 accumulate)", "data": "synthetic", "config": cfg, "timing": timing,
+                "clocks": sampler.summary(), "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
                 "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": BATCH * 9 * 4, "d2h_bytes_per_step": 4,
                         "api": "R2LTrainer.step_host: host batch of [N,9] ray-shard rows -> pinned staging -> device every step, one training iteration, loss read back to the host"},
                 "roofline": roofline}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if gpu_reference is not None:
+            line["gpu_reference"] = gpu_reference
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -160,6 +160,10 @@ int r2l_debug_set_stats(long long* stats);
  * *_bytes queries fit every form. */
 int r2l_set_pair_mode(int mode);
 
+/* Kernels launched by this library (or recorded into a CUDA graph under capture) since the last reset; reset != 0 zeroes
+ * the counter.  (r2l_teacher_pack_weights counts as one although it launches two.)  Not thread-safe: a measuring aid. */
+long long r2l_debug_launch_count(int reset);
+
 /* Form 2 multiplies every accumulator it reads by (1 + eps) to undo, in expectation, the round-toward-zero of the tensor
  * core's fp32 accumulation: eps_body for the K = 256 GEMMs, eps_head for the K = 1024 head.  The library's defaults are
  * calibrated on B200 (tools/gpu_accum_calibrate.py); this call overrides them for such measurements.  Process-wide. */

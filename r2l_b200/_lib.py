@@ -52,6 +52,7 @@ _PROTOTYPES = {
     "r2l_mse_loss_grad": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "r2l_debug_set_stats": (c_int, [c_void_p]),
     "r2l_set_pair_mode": (c_int, [c_int]),
+    "r2l_debug_launch_count": (ctypes.c_longlong, [c_int]),
     "r2l_debug_set_accum_debias": (c_int, [c_float, c_float]),
     "r2l_set_deterministic": (c_int, [c_int]),
     "r2l_debug_set_dw_schedule": (c_int, [c_int, c_int, c_int, c_int, c_int]),

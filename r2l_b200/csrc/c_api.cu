@@ -37,6 +37,13 @@ int check(cudaError_t e, const char* what) {
   snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
   return -2;
 }
+// kernels this library has launched (or recorded into a CUDA graph being captured) since the last reset: bench.py counts
+// the launches of one iteration with it instead of asserting a constant
+long long g_launches = 0;
+int check_launch(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) ++g_launches;
+  return check(e, what);
+}
 int sm_count() {
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -146,7 +153,7 @@ size_t r2l_fwd_workspace_bytes(int64_t n_rays) {
 
 int r2l_pack_weights(const float* params, void* packed, void* stream) {
   if (!params || !packed) return fail("r2l_pack_weights: %s", "null pointer");
-  return check(r2l::launch_pack(params, packed, (cudaStream_t)stream), "r2l_pack_weights");
+  return check_launch(r2l::launch_pack(params, packed, (cudaStream_t)stream), "r2l_pack_weights");
 }
 
 namespace {
@@ -190,7 +197,7 @@ int r2l_forward(int input_kind, const float* in0, const float* in1, const float*
   set_debias(p);
   p.stats = g_stats;
   p.trace = g_trace;
-  return check(launch_chain_any(r2l::kFwdInfer, p, fwd_grid(n_rays, r2l::kFwdInfer), (cudaStream_t)stream), "r2l_forward");
+  return check_launch(launch_chain_any(r2l::kFwdInfer, p, fwd_grid(n_rays, r2l::kFwdInfer), (cudaStream_t)stream), "r2l_forward");
 }
 
 int r2l_render_poses(const float* c2w, int64_t n_poses, int height, int width, float focal, const float* z_vals,
@@ -219,7 +226,7 @@ int r2l_render_poses(const float* c2w, int64_t n_poses, int height, int width, f
   set_debias(p);
   p.stats = g_stats;
   p.trace = g_trace;
-  return check(launch_chain_any(r2l::kFwdInfer, p, fwd_grid(n_rays, r2l::kFwdInfer), (cudaStream_t)stream), "r2l_render_poses");
+  return check_launch(launch_chain_any(r2l::kFwdInfer, p, fwd_grid(n_rays, r2l::kFwdInfer), (cudaStream_t)stream), "r2l_render_poses");
 }
 
 size_t r2l_bwd_workspace_bytes(int64_t n_rays) { return r2l_fwd_workspace_bytes(n_rays) + kDwPartialBytes + r2l::kTailPartialBytes; }
@@ -253,7 +260,7 @@ int r2l_forward_train(int input_kind, const float* in0, const float* in1, const 
   set_debias(p);
   p.stats = g_stats;
   p.trace = g_trace;
-  return check(launch_chain_any(r2l::kFwdTrain, p, fwd_grid(n_rays, r2l::kFwdTrain), (cudaStream_t)stream), "r2l_forward_train");
+  return check_launch(launch_chain_any(r2l::kFwdTrain, p, fwd_grid(n_rays, r2l::kFwdTrain), (cudaStream_t)stream), "r2l_forward_train");
 }
 
 int r2l_backward(int input_kind, const void* packed, const float* rgb, const float* grad_rgb, const float* zf,
@@ -315,7 +322,7 @@ int r2l_backward(int input_kind, const void* packed, const float* rgb, const flo
   p.bwd_scale = bwd_scale;
   d.bwd_scale = bwd_scale;
   if (misaligned(grad_rgb)) return fail("r2l_backward: %s", "grad_rgb must be 16-byte aligned");
-  if (int rc = check(r2l::launch_bwd_prep(grad_rgb, n_rays * 3, ready, 254, bwd_scale, st), "r2l_backward(prep)")) return rc;
+  if (int rc = check_launch(r2l::launch_bwd_prep(grad_rgb, n_rays * 3, ready, 254, bwd_scale, st), "r2l_backward(prep)")) return rc;
   // pieces of split units add into the buffer: head + body gradients start at 0 (zeroed on the stream dW runs on)
   const bool zero_grads = !d.deterministic && d.num_items > kDwUnits;
   if (side) {
@@ -323,21 +330,21 @@ int r2l_backward(int input_kind, const void* packed, const float* rgb, const flo
     d.ready = ready;
     if (int rc = check(cudaEventRecord(side->fork, st), "r2l_backward(fork)")) return rc;
     if (int rc = check(cudaStreamWaitEvent(side->stream, side->fork, 0), "r2l_backward(fork wait)")) return rc;
-    if (int rc = check(launch_chain_any(r2l::kBwd, p, grid, st), "r2l_backward(chain)")) return rc;
+    if (int rc = check_launch(launch_chain_any(r2l::kBwd, p, grid, st), "r2l_backward(chain)")) return rc;
     // the tail gradients need only forward results: first on the side stream, on SMs the chain leaves idle
-    if (int rc = check(r2l::launch_tail_grads(t, side->stream), "r2l_backward(tail)")) return rc;
+    if (int rc = check_launch(r2l::launch_tail_grads(t, side->stream), "r2l_backward(tail)")) return rc;
     if (zero_grads)
       if (int rc = check(cudaMemsetAsync(grads, 0, (size_t)r2l::kOffTailW * sizeof(float), side->stream), "r2l_backward(zero grads)")) return rc;
-    if (int rc = check(r2l::launch_dw(d, side->stream), "r2l_backward(dw)")) return rc;
+    if (int rc = check_launch(r2l::launch_dw(d, side->stream), "r2l_backward(dw)")) return rc;
     if (int rc = check(cudaEventRecord(side->join, side->stream), "r2l_backward(join)")) return rc;
     if (int rc = check(cudaStreamWaitEvent(st, side->join, 0), "r2l_backward(join wait)")) return rc;
   } else {
-    if (int rc = check(launch_chain_any(r2l::kBwd, p, grid, st), "r2l_backward(chain)")) return rc;
+    if (int rc = check_launch(launch_chain_any(r2l::kBwd, p, grid, st), "r2l_backward(chain)")) return rc;
     if (zero_grads)
       if (int rc = check(cudaMemsetAsync(grads, 0, (size_t)r2l::kOffTailW * sizeof(float), st), "r2l_backward(zero grads)")) return rc;
-    if (int rc = check(r2l::launch_dw(d, st), "r2l_backward(dw)")) return rc;
+    if (int rc = check_launch(r2l::launch_dw(d, st), "r2l_backward(dw)")) return rc;
   }
-  return side ? 0 : check(r2l::launch_tail_grads(t, st), "r2l_backward(tail)");
+  return side ? 0 : check_launch(r2l::launch_tail_grads(t, st), "r2l_backward(tail)");
 }
 
 int r2l_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, int64_t n_rays, int n_samples,
@@ -348,7 +355,7 @@ int r2l_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, 
   if (!raw || !z_vals || !rays_d || !rgb_map || !disp_map || !acc_map || !weights || !depth_map)
     return fail("r2l_raw2outputs: %s", "null pointer");
   if (misaligned(raw)) return fail("r2l_raw2outputs: %s", "raw must be 16-byte aligned");
-  return check(r2l::launch_raw2outputs(raw, z_vals, rays_d, n_rays, n_samples, white_bkgd, rgb_map, disp_map, acc_map,
+  return check_launch(r2l::launch_raw2outputs(raw, z_vals, rays_d, n_rays, n_samples, white_bkgd, rgb_map, disp_map, acc_map,
                                        weights, depth_map, (cudaStream_t)stream), "r2l_raw2outputs");
 }
 
@@ -358,7 +365,7 @@ int r2l_sample_pdf_merge(const float* z_vals, const float* weights, const float*
   if (n_rays < 0 || n_samples < 3 || n_importance < 1 || n_samples > 1024 || n_importance > 2048 || u_stride < 0)
     return fail("r2l_sample_pdf_merge: %s", "bad sizes");
   if (!z_vals || !weights || !u || !z_samples || !z_merged) return fail("r2l_sample_pdf_merge: %s", "null pointer");
-  return check(r2l::launch_sample_pdf_merge(z_vals, weights, u, u_stride, n_rays, n_samples, n_importance, z_samples, z_merged,
+  return check_launch(r2l::launch_sample_pdf_merge(z_vals, weights, u, u_stride, n_rays, n_samples, n_importance, z_samples, z_merged,
                                             nullptr, (cudaStream_t)stream), "r2l_sample_pdf_merge");
 }
 
@@ -368,7 +375,7 @@ int r2l_sample_pdf(const float* bins, const float* weights, const float* u, int6
   if (n_rays < 0 || n_bins < 2 || n_importance < 1 || n_bins > 1023 || n_importance > 2048 || u_stride < 0)
     return fail("r2l_sample_pdf: %s", "bad sizes");
   if (!bins || !weights || !u || !z_samples) return fail("r2l_sample_pdf: %s", "null pointer");
-  return check(r2l::launch_sample_pdf_merge(nullptr, weights, u, u_stride, n_rays, n_bins + 1, n_importance, z_samples, nullptr,
+  return check_launch(r2l::launch_sample_pdf_merge(nullptr, weights, u, u_stride, n_rays, n_bins + 1, n_importance, z_samples, nullptr,
                                             bins, (cudaStream_t)stream), "r2l_sample_pdf");
 }
 
@@ -377,14 +384,14 @@ int r2l_positional_embed(const float* x, float* out, int64_t n, int dim, int n_f
   if (n < 0 || dim <= 0 || n_freqs <= 0 || n_freqs > 24 || (style != 0 && style != 1))
     return fail("r2l_positional_embed: %s", "bad arguments");
   if (!x || !out) return fail("r2l_positional_embed: %s", "null pointer");
-  return check(r2l::launch_embed(x, out, n, dim, n_freqs, style, (cudaStream_t)stream), "r2l_positional_embed");
+  return check_launch(r2l::launch_embed(x, out, n, dim, n_freqs, style, (cudaStream_t)stream), "r2l_positional_embed");
 }
 
 size_t r2l_teacher_packed_bytes(void) { return (size_t)r2l::kTeacherPackedBytes; }
 
 int r2l_teacher_pack_weights(const float* params, void* packed, void* stream) {
   if (!params || !packed) return fail("r2l_teacher_pack_weights: %s", "null pointer");
-  return check(r2l::launch_teacher_pack(params, packed, (cudaStream_t)stream), "r2l_teacher_pack_weights");
+  return check_launch(r2l::launch_teacher_pack(params, packed, (cudaStream_t)stream), "r2l_teacher_pack_weights");
 }
 
 int r2l_teacher_forward(const float* pts, const float* viewdirs, const float* x_embedded, const void* packed, float* raw,
@@ -405,7 +412,7 @@ int r2l_teacher_forward(const float* pts, const float* viewdirs, const float* x_
   p.n_points = n_points;
   p.samples_per_ray = samples_per_ray > 0 ? samples_per_ray : 1;
   p.num_tiles = num_tiles(n_points);
-  return check(r2l::launch_teacher(p, plain_grid(n_points), (cudaStream_t)stream), "r2l_teacher_forward");
+  return check_launch(r2l::launch_teacher(p, plain_grid(n_points), (cudaStream_t)stream), "r2l_teacher_forward");
 }
 
 int r2l_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
@@ -418,7 +425,7 @@ int r2l_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
   // hyper-parameters arrive as doubles and are combined in double exactly as torch.optim.Adam does on the host
   const double bc1 = 1.0 - std::pow(beta1, (double)step);
   const double bc2 = 1.0 - std::pow(beta2, (double)step);
-  return check(r2l::launch_adam(params, grads, exp_avg, exp_avg_sq, n, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
+  return check_launch(r2l::launch_adam(params, grads, exp_avg, exp_avg_sq, n, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
                                 (float)eps, (float)(lr / bc1), (float)(1.0 / std::sqrt(bc2)), nullptr, (cudaStream_t)stream),
                "r2l_adam_step");
 }
@@ -435,7 +442,7 @@ int r2l_adam_schedule_dev(double lrate, double warmup_start_lr, double warmup_en
   if (!counters || !hyper) return fail("r2l_adam_schedule_dev: %s", "null pointer");
   if (!(decay_steps > 0.0) || warmup_end_iter < 0.0) return fail("r2l_adam_schedule_dev: %s", "bad schedule");
   r2l::AdamSchedule sc{lrate, warmup_start_lr, warmup_end_iter, decay_rate, decay_steps, beta1, beta2};
-  return check(r2l::launch_adam_schedule(sc, reinterpret_cast<long long*>(counters), hyper, (cudaStream_t)stream), "r2l_adam_schedule_dev");
+  return check_launch(r2l::launch_adam_schedule(sc, reinterpret_cast<long long*>(counters), hyper, (cudaStream_t)stream), "r2l_adam_schedule_dev");
 }
 
 int r2l_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double beta1, double beta2,
@@ -445,7 +452,7 @@ int r2l_adam_step_dev(float* params, const float* grads, float* exp_avg, float* 
   if (n < 0) return fail("r2l_adam_step_dev: %s", "bad n");
   if (misaligned(params) || misaligned(grads) || misaligned(exp_avg) || misaligned(exp_avg_sq))
     return fail("r2l_adam_step_dev: %s", "buffers must be 16-byte aligned");
-  return check(r2l::launch_adam(params, grads, exp_avg, exp_avg_sq, n, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
+  return check_launch(r2l::launch_adam(params, grads, exp_avg, exp_avg_sq, n, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
                                 (float)eps, 0.f, 0.f, hyper, (cudaStream_t)stream), "r2l_adam_step_dev");
 }
 
@@ -462,7 +469,7 @@ int r2l_mse_loss_grad(const float* rgb, const float* target, int64_t n_rays, int
                       float* grad_rgb, float* per_ray_err, float* loss, void* scratch, void* stream) {
   if (n_rays < 0 || target_stride < 3) return fail("r2l_mse_loss_grad: %s", "negative n_rays or target_stride < 3");
   if (!loss || !scratch || (n_rays > 0 && (!rgb || !target))) return fail("r2l_mse_loss_grad: %s", "null pointer");
-  return check(r2l::launch_mse_loss_grad(rgb, target, n_rays, target_stride, grad_scale, loss_scale, grad_rgb, per_ray_err, loss,
+  return check_launch(r2l::launch_mse_loss_grad(rgb, target, n_rays, target_stride, grad_scale, loss_scale, grad_rgb, per_ray_err, loss,
                                          static_cast<float*>(scratch), (cudaStream_t)stream), "r2l_mse_loss_grad");
 }
 
@@ -487,6 +494,12 @@ int r2l_debug_set_accum_debias(float eps_body, float eps_head) {
   return 0;
 }
 
+long long r2l_debug_launch_count(int reset) {
+  const long long n = g_launches;
+  if (reset) g_launches = 0;
+  return n;
+}
+
 int r2l_set_pair_mode(int mode) {
   g_form = (mode < 0 || mode > 2) ? -1 : mode;
   return 0;
@@ -500,14 +513,14 @@ int r2l_debug_set_trace(long long* trace) {
 int r2l_debug_mma_rate(int form, int variant, int reps, int grid, long long* out_cycles, void* stream) {
   if (!out_cycles || reps < 1 || grid < 1 || form < 0 || form > 2 || (form > 0 && (grid & 1)))
     return fail("r2l_debug_mma_rate: %s", "bad arguments");
-  return check(r2l::launch_mma_rate(form, variant, reps, grid, out_cycles, (cudaStream_t)stream), "r2l_debug_mma_rate");
+  return check_launch(r2l::launch_mma_rate(form, variant, reps, grid, out_cycles, (cudaStream_t)stream), "r2l_debug_mma_rate");
 }
 
 int r2l_selftest_layer(const float* A, const void* packed, int layer, float* C, void* stream) {
   if (!A || !packed || !C) return fail("r2l_selftest_layer: %s", "null pointer");
   if (layer < 0 || layer >= r2l::kBodyLayers) return fail("r2l_selftest_layer: %s", "layer out of range");
   const uint8_t* images = static_cast<const uint8_t*>(packed) + (int64_t)(r2l::kImgBody + 8 * layer) * r2l::kWImageBytes;
-  return check(r2l::launch_umma_selftest(A, images, C, (cudaStream_t)stream), "r2l_selftest_layer");
+  return check_launch(r2l::launch_umma_selftest(A, images, C, (cudaStream_t)stream), "r2l_selftest_layer");
 }
 
 }  // extern "C"
