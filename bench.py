@@ -448,8 +448,15 @@ def run_ours(args):
         if gpu_reference is not None:
             line["gpu_reference"] = gpu_reference
         print(json.dumps(line))
+    trainer.close()
     if world > 1:
+        sys.stdout.flush()
+        # a process group whose collectives were captured in CUDA graphs can take long to tear down: never let that hold the
+        # launcher (the line above is already printed and flushed)
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        dist.barrier()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 def main():

@@ -75,6 +75,21 @@ int r2l_backward(int input_kind, const void* packed, const float* rgb, const flo
                  const void* fwd_saved, void* bwd_saved, float* grads, void* workspace, size_t workspace_bytes,
                  int64_t n_rays, void* stream);
 
+/* The same backward with the gradient buffer completed in `n_chunks` pieces, TOP of the buffer first (gradients complete
+ * tail -> head): chunk 0 = body layers >= split_layers[0] and the tail, chunk i = body layers in
+ * [split_layers[i], split_layers[i-1]), last chunk = body layers < split_layers[n_chunks-2] and the head
+ * (split_layers: n_chunks - 1 strictly descending body-layer indices in (0, 86); r2l_grad_chunk_range gives the float range
+ * [lo, hi) of a chunk in the flat buffer).  Each chunk but the last is followed by an event on the library's side: a
+ * communication stream that calls r2l_stream_wait_grad_chunk(i, stream) can all-reduce chunk i while the backward still
+ * runs (data-parallel training: replaces the reference's DataParallel reduce-to-GPU-0, main.py:472-479, by chunked,
+ * overlapped all-reduces of ONE flat buffer).  The last chunk is complete when the call's work on `stream` is.
+ * reserve_sms: SMs the weight-gradient launches leave to the collective's kernel.  Capturable in a CUDA graph. */
+int r2l_backward_chunked(int input_kind, const void* packed, const float* rgb, const float* grad_rgb, const float* zf,
+                         const void* fwd_saved, void* bwd_saved, float* grads, void* workspace, size_t workspace_bytes,
+                         int64_t n_rays, void* stream, int n_chunks, const int* split_layers, int reserve_sms);
+int r2l_grad_chunk_range(int n_chunks, const int* split_layers, int chunk, int64_t* lo, int64_t* hi);
+int r2l_stream_wait_grad_chunk(int chunk, void* stream);
+
 /* Teacher NeRF (NeRF.forward :377-401 behind run_network :312-334; D=8, W=256, skips=[4], use_viewdirs, multires 10/4).
  *   params : R2L_TEACHER_NUM_PARAMS floats, state_dict order (pts_linears.0-7, views_linears.0, feature_linear,
  *            alpha_linear, rgb_linear; weight then bias)
@@ -134,6 +149,36 @@ int r2l_adam_schedule_dev(double lrate, double warmup_start_lr, double warmup_en
                           void* stream);
 int r2l_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double beta1, double beta2,
                       double eps, const float* hyper, void* stream);
+
+/* ---- Data-parallel training over NVLink / NVSwitch peer memory (one process per GPU; csrc/dp.cu) ----
+ * Replaces the reference's nn.DataParallel round trip (replicate all parameters, gather outputs, reduce gradients to GPU 0,
+ * torch.optim.Adam there: main.py:37-42, :472-479, :1403-1406) by ONE kernel per iteration: reduce-scatter of the flat
+ * gradient through peer loads, Adam on this rank's 1/world slice, all-gather of the new parameters through peer stores.
+ *   r2l_dp_create     allocates this rank's block (gradient buffer | parameter buffer | flags) and returns its CUDA IPC handle
+ *                     (r2l_dp_handle_bytes() bytes); exchange the handles between the ranks (e.g. torch.distributed
+ *                     all_gather_object) and pass all of them, in rank order, to r2l_dp_connect.
+ *   r2l_dp_grads / r2l_dp_params   this rank's buffers (n_params floats each): the backward writes its gradient into the
+ *                     first, the forward / r2l_pack_weights read the parameters from the second.
+ *   r2l_dp_adam_step  the kernel over the whole buffer; hyper as for r2l_adam_step_dev.  Every rank must call it once per
+ *                     iteration, after its backward on the same stream; capturable in a CUDA graph.  On return of the kernel
+ *                     every rank's parameter buffer holds the same, bit-identical parameters.  A rank that never arrives
+ *                     traps the others after 20 s.
+ *   r2l_dp_adam_step_range   the same for the float range [lo, hi) (lo a multiple of 4) of the buffer, e.g. one gradient chunk of
+ *                     r2l_backward_chunked launched on a communication stream as soon as that chunk is complete, so that only
+ *                     the last chunk's exchange is exposed.  Launches that may run concurrently need distinct `slot`s (0..7);
+ *                     grid = CTAs (0 = two per SM).  r2l_dp_slice: the part [slice_lo, slice_hi) of [lo, hi) this rank updates
+ *                     (only those parts of exp_avg / exp_avg_sq are used on this rank). */
+size_t r2l_dp_handle_bytes(void);
+int r2l_dp_create(int rank, int world, int64_t n_params, void* handle_out);
+int r2l_dp_connect(const void* all_handles);
+void* r2l_dp_grads(void);
+void* r2l_dp_params(void);
+int r2l_dp_slice(int64_t lo, int64_t hi, int64_t* slice_lo, int64_t* slice_hi);
+int r2l_dp_adam_step(float* exp_avg, float* exp_avg_sq, double beta1, double beta2, double eps, const float* hyper, void* stream);
+int r2l_dp_adam_step_range(float* exp_avg, float* exp_avg_sq, double beta1, double beta2, double eps, const float* hyper,
+                           int64_t lo, int64_t hi, int slot, int grid, void* stream);
+int r2l_dp_destroy(void);
+int r2l_debug_set_dp_grid(int grid, int variant);   /* debug: CTAs of r2l_dp_adam_step (0 = default, two per SM) and timing switches (0 = production) */
 
 /* loss[0] = loss_scale * sum((rgb - target)^2), grad_rgb = grad_scale * (rgb - target), per_ray_err[r] = mean_c (rgb - target)^2;
  * target row r starts at target[r * target_stride] (3 for a [N,3] tensor, 9 with target = rays9 + 6 for shard rows).

@@ -34,6 +34,10 @@ _PROTOTYPES = {
                                   c_void_p, c_void_p, c_void_p, c_size_t, c_int64, c_void_p]),
     "r2l_backward": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_size_t, c_int64, c_void_p]),
+    "r2l_backward_chunked": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_size_t, c_int64, c_void_p, c_int, c_void_p, c_int]),
+    "r2l_grad_chunk_range": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "r2l_stream_wait_grad_chunk": (c_int, [c_int, c_void_p]),
     "r2l_teacher_packed_bytes": (c_size_t, []),
     "r2l_teacher_pack_weights": (c_int, [c_void_p, c_void_p, c_void_p]),
     "r2l_teacher_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
@@ -47,6 +51,16 @@ _PROTOTYPES = {
     "r2l_read_ray_shards": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int]),
     "r2l_adam_hyper": (c_int, [c_double, c_double, c_double, c_int64, c_void_p]),
     "r2l_adam_schedule_dev": (c_int, [c_double, c_double, c_double, c_double, c_double, c_double, c_double, c_void_p, c_void_p, c_void_p]),
+    "r2l_dp_handle_bytes": (c_size_t, []),
+    "r2l_dp_create": (c_int, [c_int, c_int, c_int64, c_void_p]),
+    "r2l_dp_connect": (c_int, [c_void_p]),
+    "r2l_dp_grads": (c_void_p, []),
+    "r2l_dp_params": (c_void_p, []),
+    "r2l_dp_slice": (c_int, [c_int64, c_int64, c_void_p, c_void_p]),
+    "r2l_dp_adam_step_range": (c_int, [c_void_p, c_void_p, c_double, c_double, c_double, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "r2l_dp_adam_step": (c_int, [c_void_p, c_void_p, c_double, c_double, c_double, c_void_p, c_void_p]),
+    "r2l_dp_destroy": (c_int, []),
+    "r2l_debug_set_dp_grid": (c_int, [c_int, c_int]),
     "r2l_adam_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_void_p, c_void_p]),
     "r2l_loss_scratch_bytes": (c_size_t, []),
     "r2l_mse_loss_grad": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

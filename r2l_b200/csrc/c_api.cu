@@ -51,9 +51,11 @@ int sm_count() {
   return n;
 }
 // side stream + events per device for the concurrent dW launch of r2l_backward
+constexpr int kMaxGradChunks = 8;
 struct SideStream {
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t chunk_done[kMaxGradChunks] = {};   // r2l_backward_chunked: gradient chunk i of the last call is complete
 };
 std::mutex g_side_mutex;
 SideStream g_side[64];
@@ -66,6 +68,8 @@ SideStream* side_stream() {
     if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    for (int i = 0; i < kMaxGradChunks; ++i)
+      if (cudaEventCreateWithFlags(&s.chunk_done[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
   }
   return &s;
 }
@@ -263,9 +267,64 @@ int r2l_forward_train(int input_kind, const float* in0, const float* in1, const 
   return check_launch(launch_chain_any(r2l::kFwdTrain, p, fwd_grid(n_rays, r2l::kFwdTrain), (cudaStream_t)stream), "r2l_forward_train");
 }
 
+namespace {
+// unit (release order of dw.cu: body layer 85 .. 0, then the head's four column groups) where gradient chunk `chunk`
+// starts, for split layers given in descending order: chunk 0 = body layers >= split[0] (+ the tail), ...,
+// last chunk = body layers < split[last] + the head
+int chunk_first_unit(int n_chunks, const int* split_layers, int chunk) {
+  if (chunk <= 0) return 0;
+  if (chunk >= n_chunks) return kDwUnits;
+  return r2l::kBodyLayers - split_layers[chunk - 1];
+}
+int check_splits(int n_chunks, const int* split_layers, const char* who) {
+  if (n_chunks < 1 || n_chunks > kMaxGradChunks) return fail("%s: n_chunks out of range", who);
+  if (n_chunks > 1 && !split_layers) return fail("%s: split_layers is null", who);
+  for (int i = 0; i + 1 < n_chunks; ++i)
+    if (split_layers[i] <= 0 || split_layers[i] >= r2l::kBodyLayers || (i > 0 && split_layers[i] >= split_layers[i - 1]))
+      return fail("%s: split_layers must be strictly descending body-layer indices in (0, 86)", who);
+  return 0;
+}
+int backward_impl(int input_kind, const void* packed, const float* rgb, const float* grad_rgb, const float* zf,
+                  const void* fwd_saved, void* bwd_saved, float* grads, void* workspace, size_t workspace_bytes,
+                  int64_t n_rays, void* stream, int n_chunks, const int* split_layers, int reserve_sms);
+}  // namespace
+
 int r2l_backward(int input_kind, const void* packed, const float* rgb, const float* grad_rgb, const float* zf,
                  const void* fwd_saved, void* bwd_saved, float* grads, void* workspace, size_t workspace_bytes,
                  int64_t n_rays, void* stream) {
+  return backward_impl(input_kind, packed, rgb, grad_rgb, zf, fwd_saved, bwd_saved, grads, workspace, workspace_bytes, n_rays, stream,
+                       1, nullptr, 0);
+}
+
+int r2l_backward_chunked(int input_kind, const void* packed, const float* rgb, const float* grad_rgb, const float* zf,
+                         const void* fwd_saved, void* bwd_saved, float* grads, void* workspace, size_t workspace_bytes,
+                         int64_t n_rays, void* stream, int n_chunks, const int* split_layers, int reserve_sms) {
+  if (int rc = check_splits(n_chunks, split_layers, "r2l_backward_chunked")) return rc;
+  if (reserve_sms < 0 || reserve_sms > 64) return fail("r2l_backward_chunked: %s", "reserve_sms out of range");
+  return backward_impl(input_kind, packed, rgb, grad_rgb, zf, fwd_saved, bwd_saved, grads, workspace, workspace_bytes, n_rays, stream,
+                       n_chunks, split_layers, reserve_sms);
+}
+
+int r2l_grad_chunk_range(int n_chunks, const int* split_layers, int chunk, int64_t* lo, int64_t* hi) {
+  if (int rc = check_splits(n_chunks, split_layers, "r2l_grad_chunk_range")) return rc;
+  if (chunk < 0 || chunk >= n_chunks || !lo || !hi) return fail("r2l_grad_chunk_range: %s", "bad chunk / null pointer");
+  // flat buffer order: head, body 0 .. 85, tail; chunk 0 is the TOP of the buffer
+  *hi = chunk == 0 ? r2l::kNumParams : r2l::off_body_w(split_layers[chunk - 1]);
+  *lo = chunk == n_chunks - 1 ? 0 : r2l::off_body_w(split_layers[chunk]);
+  return 0;
+}
+
+int r2l_stream_wait_grad_chunk(int chunk, void* stream) {
+  if (chunk < 0 || chunk >= kMaxGradChunks) return fail("r2l_stream_wait_grad_chunk: %s", "bad chunk");
+  SideStream* side = side_stream();
+  if (!side) return fail("r2l_stream_wait_grad_chunk: %s", "no device state");
+  return check(cudaStreamWaitEvent((cudaStream_t)stream, side->chunk_done[chunk], 0), "r2l_stream_wait_grad_chunk");
+}
+
+namespace {
+int backward_impl(int input_kind, const void* packed, const float* rgb, const float* grad_rgb, const float* zf,
+                  const void* fwd_saved, void* bwd_saved, float* grads, void* workspace, size_t workspace_bytes,
+                  int64_t n_rays, void* stream, int n_chunks, const int* split_layers, int reserve_sms) {
   if (n_rays == 0) return 0;
   if (n_rays < 0) return fail("r2l_backward: %s", "negative n_rays");
   if (!packed || !rgb || !grad_rgb || !zf || !fwd_saved || !bwd_saved || !grads || !workspace)
@@ -305,7 +364,7 @@ int r2l_backward(int input_kind, const void* packed, const float* rgb, const flo
   d.ready = nullptr;
   d.partials = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + r2l_fwd_workspace_bytes(n_rays));
   d.tickets = ready + 128;
-  d.queue = ready + 250;
+  d.queue = ready + 240;                  // one claim counter per weight-gradient launch (<= kMaxGradChunks)
   d.times = g_trace ? g_trace + 148 * 5 * 96 : nullptr;   // the dW stamps follow the chain kernel's trace rows
   r2l::TailGradParams t;
   t.zf = zf;
@@ -317,6 +376,30 @@ int r2l_backward(int input_kind, const void* packed, const float* rgb, const flo
   t.n_rays = n_rays;
   dw_schedule(d, side != nullptr);
   d.deterministic = g_deterministic;
+  SideStream* ev_owner = n_chunks > 1 ? side_stream() : nullptr;
+  if (n_chunks > 1 && !ev_owner) return fail("r2l_backward_chunked: %s", "no device state");
+  // one weight-gradient launch per gradient chunk (units in release order), an event behind each but the last: the caller's
+  // communication stream can reduce chunk i across ranks while the chain and the later launches still run.  The launches
+  // leave `reserve_sms` SMs to that collective's kernel.
+  auto launch_dw_chunks = [&](cudaStream_t s) -> int {
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      const int u0 = chunk_first_unit(n_chunks, split_layers, ch), u1 = chunk_first_unit(n_chunks, split_layers, ch + 1);
+      r2l::DwParams dc = d;
+      dc.item_lo = d.unit_first[u0];
+      dc.item_hi = u1 < kDwUnits ? (int)d.unit_first[u1] : d.num_items;
+      dc.queue = d.queue + ch;
+      int g = dc.item_hi - dc.item_lo;
+      // persistent CTAs beyond the SMs the chain leaves free simply start when SMs free up; the collective's kernel gets
+      // its SMs at the launch boundaries through its stream's priority (trainer.py) and / or the SMs reserved here
+      int cap = sm_count() - reserve_sms;
+      if (cap < 8) cap = 8;
+      dc.grid = g < cap ? g : cap;
+      if (int rc = check_launch(r2l::launch_dw(dc, s), "r2l_backward(dw)")) return rc;
+      if (ch + 1 < n_chunks)
+        if (int rc = check(cudaEventRecord(ev_owner->chunk_done[ch], s), "r2l_backward(chunk event)")) return rc;
+    }
+    return 0;
+  };
   // one small kernel instead of a memset: zeroes the flag words and derives the loss scale from max |grad_rgb|
   float* bwd_scale = reinterpret_cast<float*>(ready + 254);
   p.bwd_scale = bwd_scale;
@@ -335,17 +418,20 @@ int r2l_backward(int input_kind, const void* packed, const float* rgb, const flo
     if (int rc = check_launch(r2l::launch_tail_grads(t, side->stream), "r2l_backward(tail)")) return rc;
     if (zero_grads)
       if (int rc = check(cudaMemsetAsync(grads, 0, (size_t)r2l::kOffTailW * sizeof(float), side->stream), "r2l_backward(zero grads)")) return rc;
-    if (int rc = check_launch(r2l::launch_dw(d, side->stream), "r2l_backward(dw)")) return rc;
+    if (int rc = launch_dw_chunks(side->stream)) return rc;
     if (int rc = check(cudaEventRecord(side->join, side->stream), "r2l_backward(join)")) return rc;
     if (int rc = check(cudaStreamWaitEvent(st, side->join, 0), "r2l_backward(join wait)")) return rc;
   } else {
     if (int rc = check_launch(launch_chain_any(r2l::kBwd, p, grid, st), "r2l_backward(chain)")) return rc;
     if (zero_grads)
       if (int rc = check(cudaMemsetAsync(grads, 0, (size_t)r2l::kOffTailW * sizeof(float), st), "r2l_backward(zero grads)")) return rc;
-    if (int rc = check_launch(r2l::launch_dw(d, st), "r2l_backward(dw)")) return rc;
+    // the tail gradients belong to the first chunk (top of the buffer): before the weight-gradient launches here
+    if (int rc = check_launch(r2l::launch_tail_grads(t, st), "r2l_backward(tail)")) return rc;
+    if (int rc = launch_dw_chunks(st)) return rc;
   }
-  return side ? 0 : check_launch(r2l::launch_tail_grads(t, st), "r2l_backward(tail)");
+  return 0;
 }
+}  // namespace
 
 int r2l_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, int64_t n_rays, int n_samples,
                     int white_bkgd, float* rgb_map, float* disp_map, float* acc_map, float* weights, float* depth_map,
@@ -443,6 +529,118 @@ int r2l_adam_schedule_dev(double lrate, double warmup_start_lr, double warmup_en
   if (!(decay_steps > 0.0) || warmup_end_iter < 0.0) return fail("r2l_adam_schedule_dev: %s", "bad schedule");
   r2l::AdamSchedule sc{lrate, warmup_start_lr, warmup_end_iter, decay_rate, decay_steps, beta1, beta2};
   return check_launch(r2l::launch_adam_schedule(sc, reinterpret_cast<long long*>(counters), hyper, (cudaStream_t)stream), "r2l_adam_schedule_dev");
+}
+
+// ---- data-parallel state: one per process (= per GPU), see dp.cu ----
+namespace {
+struct DpState {
+  bool active = false;
+  int rank = 0, world = 1, device = -1;
+  int64_t n = 0;
+  void* local = nullptr;                 // one cudaMalloc block: [grads n | params n (padded to 256 B) | flags + state]
+  void* peer[r2l::kDpMaxWorld] = {};     // IPC mappings of the other ranks' blocks (peer[rank] = local)
+  size_t off_params = 0, off_flags = 0, bytes = 0;
+} g_dp;
+int g_dp_grid = 0, g_dp_variant = 0;   // debug overrides (r2l_debug_set_dp_grid)
+size_t dp_round(size_t x) { return (x + 255) & ~(size_t)255; }
+}  // namespace
+
+size_t r2l_dp_handle_bytes(void) { return sizeof(cudaIpcMemHandle_t); }
+
+int r2l_dp_create(int rank, int world, int64_t n_params, void* handle_out) {
+  if (g_dp.active) return fail("r2l_dp_create: %s", "already created in this process");
+  if (world < 1 || world > r2l::kDpMaxWorld || rank < 0 || rank >= world || n_params <= 0 || !handle_out)
+    return fail("r2l_dp_create: %s", "bad arguments");
+  DpState d;
+  d.rank = rank; d.world = world; d.n = n_params;
+  if (int rc = check(cudaGetDevice(&d.device), "r2l_dp_create(device)")) return rc;
+  d.off_params = dp_round((size_t)n_params * sizeof(float));
+  d.off_flags = d.off_params + dp_round((size_t)n_params * sizeof(float));
+  d.bytes = d.off_flags + 4096;          // flag words [0, 256): 8 launch slots x 32; state words from 512
+  if (int rc = check(cudaMalloc(&d.local, d.bytes), "r2l_dp_create(cudaMalloc)")) return rc;
+  if (int rc = check(cudaMemset(d.local, 0, d.bytes), "r2l_dp_create(memset)")) return rc;
+  if (int rc = check(cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(handle_out), d.local), "r2l_dp_create(cudaIpcGetMemHandle)")) return rc;
+  d.peer[rank] = d.local;
+  d.active = true;
+  g_dp = d;
+  return 0;
+}
+
+int r2l_dp_connect(const void* all_handles) {
+  if (!g_dp.active || !all_handles) return fail("r2l_dp_connect: %s", "r2l_dp_create first / null pointer");
+  const cudaIpcMemHandle_t* h = static_cast<const cudaIpcMemHandle_t*>(all_handles);
+  for (int r = 0; r < g_dp.world; ++r) {
+    if (r == g_dp.rank) continue;
+    if (int rc = check(cudaIpcOpenMemHandle(&g_dp.peer[r], h[r], cudaIpcMemLazyEnablePeerAccess), "r2l_dp_connect(cudaIpcOpenMemHandle)")) return rc;
+  }
+  return 0;
+}
+
+void* r2l_dp_grads(void) { return g_dp.active ? g_dp.local : nullptr; }
+void* r2l_dp_params(void) { return g_dp.active ? static_cast<uint8_t*>(g_dp.local) + g_dp.off_params : nullptr; }
+
+namespace {
+// slice of the float range [lo, hi) rank `g_dp.rank` owns: equal float4-aligned parts in rank order
+void dp_slice(int64_t lo, int64_t hi, int64_t* slo, int64_t* shi) {
+  const int64_t per = ((((hi - lo) + g_dp.world - 1) / g_dp.world) + 3) & ~(int64_t)3;
+  int64_t a = lo + per * g_dp.rank, b = lo + per * (g_dp.rank + 1);
+  *slo = a < hi ? a : hi;
+  *shi = b < hi ? b : hi;
+}
+}  // namespace
+
+int r2l_dp_slice(int64_t lo, int64_t hi, int64_t* slice_lo, int64_t* slice_hi) {
+  if (!g_dp.active || !slice_lo || !slice_hi) return fail("r2l_dp_slice: %s", "r2l_dp_create first / null pointer");
+  if (lo < 0 || hi > g_dp.n || lo > hi || (lo & 3)) return fail("r2l_dp_slice: %s", "bad range (lo must be a multiple of 4)");
+  dp_slice(lo, hi, slice_lo, slice_hi);
+  return 0;
+}
+
+int r2l_dp_adam_step_range(float* exp_avg, float* exp_avg_sq, double beta1, double beta2, double eps, const float* hyper,
+                           int64_t lo, int64_t hi, int slot, int grid, void* stream) {
+  if (!g_dp.active) return fail("r2l_dp_adam_step: %s", "r2l_dp_create / r2l_dp_connect first");
+  if (!exp_avg || !exp_avg_sq || !hyper) return fail("r2l_dp_adam_step: %s", "null pointer");
+  if (misaligned(exp_avg) || misaligned(exp_avg_sq)) return fail("r2l_dp_adam_step: %s", "moment buffers must be 16-byte aligned");
+  if (lo < 0 || hi > g_dp.n || lo >= hi || (lo & 3) || slot < 0 || slot >= 8) return fail("r2l_dp_adam_step: %s", "bad range / slot");
+  r2l::DpParams p;
+  memset(&p, 0, sizeof(p));
+  for (int r = 0; r < g_dp.world; ++r) {
+    if (!g_dp.peer[r]) return fail("r2l_dp_adam_step: %s", "a peer buffer is not connected");
+    p.grads[r] = static_cast<float*>(g_dp.peer[r]);
+    p.params[r] = reinterpret_cast<float*>(static_cast<uint8_t*>(g_dp.peer[r]) + g_dp.off_params);
+    p.flags[r] = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(g_dp.peer[r]) + g_dp.off_flags);
+  }
+  p.flag_base = 32 * slot;
+  p.state = p.flags[g_dp.rank] + 512 + 2 * slot;
+  p.exp_avg = exp_avg; p.exp_avg_sq = exp_avg_sq; p.hyper = hyper;
+  dp_slice(lo, hi, &p.shard_lo, &p.shard_hi);
+  p.w1 = (float)(1.0 - beta1); p.beta2 = (float)beta2; p.w2 = (float)(1.0 - beta2); p.eps = (float)eps;
+  p.rank = g_dp.rank; p.world = g_dp.world;
+  p.variant = g_dp_variant;
+  if (grid <= 0) grid = 2 * sm_count();    // two CTAs of 256 threads per SM
+  if (grid <= 0) grid = 148;
+  if (g_dp_grid > 0) grid = g_dp_grid;
+  return check_launch(r2l::launch_dp_adam(p, grid, (cudaStream_t)stream), "r2l_dp_adam_step");
+}
+
+int r2l_dp_adam_step(float* exp_avg, float* exp_avg_sq, double beta1, double beta2, double eps, const float* hyper, void* stream) {
+  return r2l_dp_adam_step_range(exp_avg, exp_avg_sq, beta1, beta2, eps, hyper, 0, g_dp.active ? g_dp.n : 0, 0, 0, stream);
+}
+
+int r2l_debug_set_dp_grid(int grid, int variant) {
+  g_dp_grid = grid;
+  g_dp_variant = variant;
+  return 0;
+}
+
+int r2l_dp_destroy(void) {
+  if (!g_dp.active) return 0;
+  cudaDeviceSynchronize();
+  for (int r = 0; r < g_dp.world; ++r)
+    if (r != g_dp.rank && g_dp.peer[r]) cudaIpcCloseMemHandle(g_dp.peer[r]);
+  cudaFree(g_dp.local);
+  g_dp = DpState();
+  return 0;
 }
 
 int r2l_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double beta1, double beta2,

@@ -117,8 +117,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) r2l_dw_kernel(const __grid_cons
       uint32_t git = 0;   // stage counter over all items of this CTA (the stage ring never restarts)
       for (uint32_t k = 0;; ++k) {
         mbar_wait(bar(kDwBarItemEmpty + (k & 1u)), ((k >> 1) & 1u) ^ 1u);
-        int item = atomicAdd(p.queue, 1);
-        if (item >= p.num_items) item = -1;
+        int item = p.item_lo + atomicAdd(p.queue, 1);
+        if (item >= p.item_hi) item = -1;
         item_ring[k & 1u] = item;
         mbar_arrive(bar(kDwBarItemFull + (k & 1u)));   // release: the ring entry is visible to whoever sees the phase
         if (item < 0) break;
@@ -129,9 +129,13 @@ __global__ void __launch_bounds__(kDwThreads, 1) r2l_dw_kernel(const __grid_cons
           // the dY operand of this unit's layer (group index = position of that layer in the backward sweep)
           const int group = w.is_head ? kBodyLayers : w.ob;
           unsigned ns = 32;
+          const long long t_wait0 = global_timer_ns();
           while (flag_acquire_load(p.ready + group) < p.ready_target) {
             __nanosleep(ns);
             if (ns < 1024) ns <<= 1;
+            // the chain kernel this launch runs beside never became resident (SMs taken by another process / MPS client):
+            // fail loudly instead of hanging the device (the GPU is expected to be exclusive)
+            if (global_timer_ns() - t_wait0 > 4000000000ll) __trap();
           }
           asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy acquire -> async-proxy (TMA) reads
         }

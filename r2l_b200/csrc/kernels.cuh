@@ -57,6 +57,7 @@ struct DwParams {
   uint16_t unit_first[kBodyLayers + 4];
   int deterministic;      // split units: 1 = partials in scratch + ordered sum by the last piece, 0 = L2 reductions into grads
   int num_items;          // work items = pieces of all units, numbered in release order (item = "CTA" above)
+  int item_lo, item_hi;   // the items THIS launch processes (one launch per gradient chunk, see r2l_backward_chunked)
   int grid;               // persistent CTAs (<= SMs); they claim items in order from `queue`
   int* queue;             // zeroed counter
   float* partials;        // [num_items][256*256 + 256] scratch (only slots of split units are used)
@@ -104,6 +105,22 @@ cudaError_t launch_raw2outputs(const float* raw, const float* z_vals, const floa
 cudaError_t launch_sample_pdf_merge(const float* z_vals, const float* weights, const float* u, int64_t u_stride, int64_t n_rays,
                                     int S, int M, float* z_samples, float* z_merged, const float* bins_in, cudaStream_t stream);
 cudaError_t launch_embed(const float* x, float* out, int64_t n, int dim, int L, int style, cudaStream_t stream);
+constexpr int kDpMaxWorld = 16;
+struct DpParams {           // dp.cu: reduce-scatter + Adam + all-gather over peer memory
+  float* grads[kDpMaxWorld];     // every rank's gradient buffer (mine and the peers' IPC mappings)
+  float* params[kDpMaxWorld];    // every rank's parameter buffer
+  uint32_t* flags[kDpMaxWorld];  // every rank's flag block: [0,16) "gradient of rank s complete", [16,32) "slice of rank s written"
+  uint32_t* state;               // local, per launch slot: [0] epochs completed, [1] CTA completion counter
+  int flag_base;                 // first flag word of this launch slot (32 words per slot)
+  float* exp_avg;                // local full-size moment buffers; only [shard_lo, shard_hi) is used on this rank
+  float* exp_avg_sq;
+  const float* hyper;            // device: {lr / bias_correction1, 1 / sqrt(bias_correction2)} (r2l_adam_schedule_dev)
+  int64_t shard_lo, shard_hi;
+  float w1, beta2, w2, eps;
+  int rank, world;
+  int variant;                   // DEBUG timing switches (r2l_debug_set_dp_grid's second argument), 0 in production
+};
+cudaError_t launch_dp_adam(const DpParams& p, int grid, cudaStream_t stream);
 struct AdamSchedule {
   double lrate, warmup_start_lr, warmup_end, decay_rate, decay_steps, beta1, beta2;   // warmup_end = 0: no warm-up
 };

@@ -222,9 +222,29 @@ def _checked_workspace(workspace, dev, nbytes):
     return workspace
 
 
+def grad_chunk_ranges(split_layers):
+    """[(lo, hi)] float ranges of the flat gradient buffer per chunk of backward(..., split_layers=...), chunk 0 first."""
+    n = len(split_layers) + 1
+    arr = (ctypes.c_int * max(len(split_layers), 1))(*split_layers)
+    out = []
+    for c in range(n):
+        lo, hi = ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(_lib.lib().r2l_grad_chunk_range(n, arr, c, ctypes.byref(lo), ctypes.byref(hi)), "r2l_grad_chunk_range")
+        out.append((lo.value, hi.value))
+    return out
+
+
+def stream_wait_grad_chunk(chunk: int, stream: "torch.cuda.Stream") -> None:
+    """Make `stream` wait until gradient chunk `chunk` of the last chunked backward on this device is complete."""
+    _lib.check(_lib.lib().r2l_stream_wait_grad_chunk(int(chunk), ctypes.c_void_p(stream.cuda_stream)), "r2l_stream_wait_grad_chunk")
+
+
 def backward(packed: torch.Tensor, ctx: TrainContext, grad_rgb: torch.Tensor, grads: torch.Tensor | None = None,
-             bwd_saved: torch.Tensor | None = None, workspace: torch.Tensor | None = None) -> torch.Tensor:
-    """dL/dparams (flat, state_dict order) for dL/drgb = grad_rgb.  `grads` is overwritten if given."""
+             bwd_saved: torch.Tensor | None = None, workspace: torch.Tensor | None = None, split_layers=None,
+             reserve_sms: int = 0) -> torch.Tensor:
+    """dL/dparams (flat, state_dict order) for dL/drgb = grad_rgb.  `grads` is overwritten if given.
+    split_layers (descending body-layer indices): complete the buffer in len + 1 chunks, top first, with an event behind
+    each but the last (stream_wait_grad_chunk) so that a communication stream can reduce them while the backward runs."""
     L = _lib.lib()
     grad_rgb = _require_cuda_f32(grad_rgb, "grad_rgb", (3,))
     if grad_rgb.shape[0] != ctx.n:
@@ -245,9 +265,15 @@ def backward(packed: torch.Tensor, ctx: TrainContext, grad_rgb: torch.Tensor, gr
             raise ValueError(f"bwd_saved: expected a uint8 buffer of >= {nsaved} bytes on {dev}")
         wbytes = int(L.r2l_bwd_workspace_bytes(ctx.n))
         ws = _checked_workspace(workspace, dev, wbytes)
-        _lib.check(L.r2l_backward(ctx.kind, _ptr(packed), _ptr(ctx.rgb), _ptr(grad_rgb), _ptr(ctx.zf),
-                                  _ptr(ctx.fwd_saved), _ptr(bwd_saved), _ptr(grads), _ptr(ws), wbytes, ctx.n,
-                                  _stream()), "r2l_backward")
+        if split_layers:
+            arr = (ctypes.c_int * len(split_layers))(*[int(v) for v in split_layers])
+            _lib.check(L.r2l_backward_chunked(ctx.kind, _ptr(packed), _ptr(ctx.rgb), _ptr(grad_rgb), _ptr(ctx.zf),
+                                              _ptr(ctx.fwd_saved), _ptr(bwd_saved), _ptr(grads), _ptr(ws), wbytes, ctx.n,
+                                              _stream(), len(split_layers) + 1, arr, int(reserve_sms)), "r2l_backward_chunked")
+        else:
+            _lib.check(L.r2l_backward(ctx.kind, _ptr(packed), _ptr(ctx.rgb), _ptr(grad_rgb), _ptr(ctx.zf),
+                                      _ptr(ctx.fwd_saved), _ptr(bwd_saved), _ptr(grads), _ptr(ws), wbytes, ctx.n,
+                                      _stream()), "r2l_backward")
     return grads
 
 

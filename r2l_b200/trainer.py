@@ -8,13 +8,15 @@
     sample_train -> positional_embedder -> model    (:1369-1374)       r2l_forward_train (one kernel)
     img2mse * lw_rgb, psnr.item()                   (:1377-1379)       r2l_mse_loss_grad (one kernel, no host sync)
     optimizer.zero_grad(); loss.backward()          (:1403-1404)       r2l_backward (chain + weight gradients)
-    [DataParallel reduce to GPU 0]                  (:472-479)         ONE all-reduce of the flat gradient (N > 1)
+    [DataParallel reduce to GPU 0]                  (:472-479)         chunked, overlapped all-reduce of ONE flat buffer (N > 1)
     optimizer.step()  (Adam over 176 tensors)       (:1406)            r2l_adam_step_dev + r2l_pack_weights
     torch.sort of per-ray errors, pool update       (:1410-1425)       HardRayPool.update (device, no sync)
 
 No arithmetic of the network happens in torch; torch provides buffers, streams, the CUDA-graph capture and NCCL.
 """
 from __future__ import annotations
+
+import os
 
 import torch
 import torch.distributed as dist
@@ -95,16 +97,41 @@ class R2LTrainer:
     lives on the device.  `model` is a r2l_b200 NeRF_v3_2 on CUDA, `point_sampler` its PointSampler."""
 
     def __init__(self, model, point_sampler, lrate=5e-4, lrate_decay=500, warmup_lr=None, lw_rgb=1.0, perturb=0.0,
-                 hard_ratio=0, hard_mul=1, betas=(0.9, 0.999), eps=1e-8, use_graph=True, group=None, start_step=0):
+                 hard_ratio=0, hard_mul=1, betas=(0.9, 0.999), eps=1e-8, use_graph=True, group=None, start_step=0,
+                 grad_split_layers=(64, 43, 21), comm_sms=0, dp_mode=None):
         if not model.flat.is_cuda:
             raise RuntimeError("R2LTrainer: the model must live on a CUDA device (no CPU fallback)")
         self.model, self.sampler = model, point_sampler
         self.lrate, self.lrate_decay, self.warmup_lr, self.lw_rgb = lrate, lrate_decay, warmup_lr, float(lw_rgb)
         self.perturb, self.betas, self.eps = float(perturb), betas, eps
         self.hard_ratio, self.hard_mul = hard_ratio, hard_mul
-        self.group = group
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
-        self.use_graph = bool(use_graph) and self.world == 1
+        # N > 1: "peer" = the fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory (csrc/dp.cu, the default
+        # where the GPUs of the group can map each other's memory), "nccl" = chunked, overlapped NCCL all-reduces + local Adam
+        self.dp_mode = None
+        if self.world > 1:
+            self.dp_mode = dp_mode or os.environ.get("R2L_DP_MODE") or "peer"
+            if self.dp_mode not in ("peer", "nccl"):
+                raise ValueError(f"R2LTrainer: dp_mode must be 'peer' or 'nccl', got {self.dp_mode!r}")
+        if self.world > 1 and self.dp_mode == "nccl" and group is None and dist.get_backend() == "nccl":
+            # own communicator whose NCCL stream has HIGH priority: its kernels are dispatched ahead of the pending CTAs of
+            # the weight-gradient launches whenever SMs free up, so the chunk all-reduces really overlap the backward
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.is_high_priority_stream = True
+            group = dist.new_group(backend="nccl", pg_options=opts)
+        self.group = group
+        self.use_graph = bool(use_graph)
+        # data parallel: the flat gradient is completed and all-reduced in chunks, top of the buffer first (gradients complete
+        # tail -> head), on a communication stream while the backward still runs; only the last chunk's reduction is exposed
+        # both data-parallel modes complete the gradient buffer in chunks (top first: gradients complete tail -> head) and
+        # exchange a chunk on a HIGH-PRIORITY communication stream as soon as it is complete, while the backward still runs;
+        # only the last chunk's exchange is exposed
+        dp = self.world > 1
+        self.split_layers = list(grad_split_layers) if dp else []
+        self.reserve_sms = int(comm_sms) if dp else 0
+        self.chunk_ranges = ops.grad_chunk_ranges(self.split_layers) if dp else []
+        self.comm_stream = torch.cuda.Stream(model.flat.device, priority=-1) if dp else None
+        self.comm_grid = int(os.environ.get("R2L_DP_CHUNK_GRID", "64"))    # CTAs of an overlapped chunk exchange (peer mode)
         self.global_step = start_step          # iterations done; the next one is global_step + 1 (main.py:1175 `start + 1`)
         dev = self.dev = model.flat.device
         self.z_vals = point_sampler.z_vals.tolist()
@@ -113,7 +140,16 @@ class R2LTrainer:
         self.exp_avg = torch.zeros(NUM_PARAMS, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(NUM_PARAMS, dtype=torch.float32, device=dev)
         self.adam_steps = 0
-        self.grads = torch.empty(NUM_PARAMS, dtype=torch.float32, device=dev)
+        self.peer = None
+        if self.dp_mode == "peer":
+            from .parallel import PeerDataParallel
+            self.peer = PeerDataParallel(NUM_PARAMS, dev, group)
+            with torch.no_grad():      # the parameters move into this rank's peer-visible buffer; the module keeps using them there
+                self.peer.params.copy_(model.flat.detach())
+                model.flat.data = self.peer.params
+            self.grads = self.peer.grads
+        else:
+            self.grads = torch.empty(NUM_PARAMS, dtype=torch.float32, device=dev)
         self.packed = ops.pack_weights(model.flat.detach())
         self._flat_seen = (model.flat.data_ptr(), model.flat._version)    # the parameters self.packed was built from
         # iteration counters [global_step, adam_steps] and the step scalars derived from them live on the DEVICE
@@ -141,10 +177,37 @@ class R2LTrainer:
         n_global = n * self.world
         ops.mse_loss_grad(rgb, st["in9"][:, 6:9], 2.0 * self.lw_rgb / (3 * n_global), self.lw_rgb / (3 * n), grad_rgb=st["grad_rgb"],
                           per_ray_err=st["err"], loss=self.loss)
-        ops.backward(self.packed, ctx, st["grad_rgb"], self.grads, bwd_saved=st["bwd_saved"], workspace=st["workspace"])
-        if self.world > 1:
-            dist.all_reduce(self.grads, group=self.group)       # ONE all-reduce of the flat 23.7 MB buffer
+        ops.backward(self.packed, ctx, st["grad_rgb"], self.grads, bwd_saved=st["bwd_saved"], workspace=st["workspace"],
+                     split_layers=self.split_layers, reserve_sms=self.reserve_sms)
         flat = self.model.flat.data
+        if self.peer is not None:
+            # gradients of all ranks -> my slice -> Adam -> new parameters into every rank's buffer: one kernel per chunk over
+            # NVLink peer memory, no NCCL; the chunks that complete early are exchanged beside the rest of the backward
+            main = torch.cuda.current_stream(self.dev)
+            args = (self.exp_avg, self.exp_avg_sq, self.betas[0], self.betas[1], self.eps, self.d_hyper)
+            for i, (lo, hi) in enumerate(self.chunk_ranges[:-1]):
+                ops.stream_wait_grad_chunk(i, self.comm_stream)
+                self.peer.adam_step(*args, lo=lo, hi=hi, slot=i, grid=self.comm_grid, stream=self.comm_stream)
+            lo, hi = self.chunk_ranges[-1]
+            self.peer.adam_step(*args, lo=lo, hi=hi, slot=len(self.chunk_ranges) - 1, stream=main)
+            if len(self.chunk_ranges) > 1:
+                main.wait_stream(self.comm_stream)
+            ops.pack_weights(flat, out=self.packed)
+            if from_host:
+                self.h_loss.copy_(self.loss, non_blocking=True)
+            return
+        if self.world > 1:
+            # ONE flat 23.7 MB gradient buffer, summed over ranks piece by piece as the pieces complete (same collectives in
+            # the same order on every rank; NCCL runs them on its own stream in issue order)
+            main = torch.cuda.current_stream(self.dev)
+            for i, (lo, hi) in enumerate(self.chunk_ranges[:-1]):
+                ops.stream_wait_grad_chunk(i, self.comm_stream)
+                with torch.cuda.stream(self.comm_stream):
+                    dist.all_reduce(self.grads[lo:hi], group=self.group)
+            lo, hi = self.chunk_ranges[-1]
+            dist.all_reduce(self.grads[lo:hi], group=self.group)     # the head's piece: complete only when the backward is
+            if len(self.chunk_ranges) > 1:
+                main.wait_stream(self.comm_stream)
         ops.adam_step_dev(flat, self.grads, self.exp_avg, self.exp_avg_sq, self.betas[0], self.betas[1], self.eps, self.d_hyper)
         ops.pack_weights(flat, out=self.packed)                 # operands of the next forward (training or rendering)
         if from_host:
@@ -268,9 +331,41 @@ class R2LTrainer:
         torch.cuda.current_stream(self.dev).synchronize()
         return float(self.h_loss[0])
 
+    def close(self):
+        """Drop the captured CUDA graphs and static buffers (call before torch.distributed.destroy_process_group(): graphs that
+        captured NCCL collectives must be released while the communicator is alive)."""
+        torch.cuda.synchronize(self.dev)
+        for st in self._static.values():
+            st["graph"] = st["graph_host"] = None
+        self._static.clear()
+        torch.cuda.synchronize(self.dev)
+        if self.peer is not None:
+            # the module's parameters must not point into the buffer that is about to be freed
+            with torch.no_grad():
+                self.model.flat.data = self.model.flat.data.clone()
+            self.grads = None
+            self.peer.close()
+            self.peer = None
+
+    def _full_moments(self):
+        """Adam moments as full-size tensors: in the peer data-parallel mode every rank holds only its slice (collective call)."""
+        if self.peer is None:
+            return self.exp_avg, self.exp_avg_sq
+        out = []
+        for t in (self.exp_avg, self.exp_avg_sq):
+            full = torch.zeros_like(t)
+            for lo, hi in self.chunk_ranges:
+                a, b = self.peer.slice_of(lo, hi)
+                full[a:b] = t[a:b]
+            dist.all_reduce(full, group=self.group)
+            out.append(full)
+        return out
+
     def state_dict(self):
-        """Optimizer-side state in torch.optim.Adam's layout for the single flat parameter (ckpt['optimizer_state_dict'])."""
-        return {"state": {0: {"step": self.adam_steps, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}},
+        """Optimizer-side state in torch.optim.Adam's layout for the single flat parameter (ckpt['optimizer_state_dict']).
+        (Collective in the peer data-parallel mode: the moments are gathered from the ranks' slices.)"""
+        exp_avg, exp_avg_sq = self._full_moments()
+        return {"state": {0: {"step": self.adam_steps, "exp_avg": exp_avg, "exp_avg_sq": exp_avg_sq}},
                 "param_groups": [{"lr": self.last_lr if self.last_lr is not None else self.lrate, "betas": self.betas,
                                   "eps": self.eps, "params": [0]}], "global_step": self.global_step}
 
