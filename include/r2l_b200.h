@@ -191,6 +191,23 @@ size_t r2l_loss_scratch_bytes(void);
 int r2l_mse_loss_grad(const float* rgb, const float* target, int64_t n_rays, int target_stride, float grad_scale, float loss_scale,
                       float* grad_rgb, float* per_ray_err, float* loss, void* scratch, void* stream);
 
+/* ---- Hard-example ray pool on the device (main.py:1325-1347 draw, :1410-1425 update); both calls are one launch, need no
+ * host sync and can be captured in a CUDA graph together with the rest of the iteration.
+ *   pool_rows  : [capacity, 9] fp32 rows (o | d | rgb);   pool_state : int32[1] = rays currently in the pool (device).
+ * r2l_pool_draw   (pool full): dst_rows[j] = pool_rows[slots_out[j]], j < n_out <= size, slots_out = the first n_out values of a
+ *   pseudo-random permutation of [0, size) keyed by `seed` and counters[0] (the device-resident iteration counter of
+ *   r2l_adam_schedule_dev): replaces np.random.permutation(len(pool))[:n_hard_out] + the host-side cat (:1330-1340).
+ * r2l_pool_update: the n_hard_in rays with the largest per_ray_err among the first n_fresh rows of rays9[.,9] (the fresh part
+ *   of the batch, :1411-1414; ties: lowest ray index first) are appended at row pool_state[0] (slots_out == NULL; the kernel
+ *   advances pool_state[0]) or overwrite rows slots_out[0 .. n_hard_in) (pool full, :1416-1418).  picked (optional):
+ *   int32[n_hard_in] out, the selected ray indices (all rays above the k-th error in index order, then the ties). */
+int r2l_pool_draw(const float* pool_rows, const int32_t* pool_state, int n_out, uint64_t seed, const int64_t* counters,
+                  float* dst_rows, int32_t* slots_out, void* stream);
+int r2l_pool_update(const float* rays9, const float* per_ray_err, int64_t n_fresh, int n_hard_in, float* pool_rows, int32_t* pool_state,
+                    const int32_t* slots_out, int32_t* picked, void* stream);
+/* HOST: slot j of the permutation r2l_pool_draw uses for a pool of `size` rays at iteration counter `step` (-1 on bad arguments). */
+int64_t r2l_pool_slot_host(int64_t j, int64_t size, uint64_t seed, int64_t step);
+
 /* Debug: device buffer [grid][8] of int64 cycle counters filled by the next r2l_forward calls (NULL = off):
  * [0] MMA wait on head A chunks, [1] on body A chunks, [2] on weight stages, [3] producer wait on free stages,
  * [4] MMA-thread total. */

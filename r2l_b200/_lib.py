@@ -64,6 +64,9 @@ _PROTOTYPES = {
     "r2l_adam_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_void_p, c_void_p]),
     "r2l_loss_scratch_bytes": (c_size_t, []),
     "r2l_mse_loss_grad": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "r2l_pool_draw": (c_int, [c_void_p, c_void_p, c_int, ctypes.c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "r2l_pool_update": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "r2l_pool_slot_host": (c_int64, [c_int64, c_int64, ctypes.c_uint64, c_int64]),
     "r2l_debug_set_stats": (c_int, [c_void_p]),
     "r2l_set_pair_mode": (c_int, [c_int]),
     "r2l_debug_launch_count": (ctypes.c_longlong, [c_int]),

@@ -671,6 +671,29 @@ int r2l_mse_loss_grad(const float* rgb, const float* target, int64_t n_rays, int
                                          static_cast<float*>(scratch), (cudaStream_t)stream), "r2l_mse_loss_grad");
 }
 
+int r2l_pool_draw(const float* pool_rows, const int32_t* pool_state, int n_out, uint64_t seed, const int64_t* counters,
+                  float* dst_rows, int32_t* slots_out, void* stream) {
+  if (n_out == 0) return 0;
+  if (n_out < 0) return fail("r2l_pool_draw: %s", "negative n_out");
+  if (!pool_rows || !pool_state || !counters || !dst_rows || !slots_out) return fail("r2l_pool_draw: %s", "null pointer");
+  return check_launch(r2l::launch_pool_draw(pool_rows, pool_state, n_out, seed, reinterpret_cast<const long long*>(counters), dst_rows,
+                                            slots_out, (cudaStream_t)stream), "r2l_pool_draw");
+}
+
+int64_t r2l_pool_slot_host(int64_t j, int64_t size, uint64_t seed, int64_t step) {
+  if (size <= 0 || size > 0x7fffffff || j < 0 || j >= size) return -1;
+  return (int64_t)r2l::pool_slot_host((uint32_t)j, (uint32_t)size, seed, (uint64_t)step);
+}
+
+int r2l_pool_update(const float* rays9, const float* per_ray_err, int64_t n_fresh, int n_hard_in, float* pool_rows, int32_t* pool_state,
+                    const int32_t* slots_out, int32_t* picked, void* stream) {
+  if (n_hard_in == 0) return 0;
+  if (n_hard_in < 0 || n_fresh < n_hard_in || n_fresh > 0x7fffffff) return fail("r2l_pool_update: %s", "need 0 <= n_hard_in <= n_fresh < 2^31");
+  if (!rays9 || !per_ray_err || !pool_rows || !pool_state) return fail("r2l_pool_update: %s", "null pointer");
+  return check_launch(r2l::launch_pool_update(rays9, per_ray_err, (int)n_fresh, n_hard_in, pool_rows, pool_state, slots_out, picked,
+                                              (cudaStream_t)stream), "r2l_pool_update");
+}
+
 int r2l_debug_set_stats(long long* stats) {
   g_stats = stats;
   return 0;

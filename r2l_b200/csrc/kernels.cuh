@@ -121,6 +121,12 @@ struct DpParams {           // dp.cu: reduce-scatter + Adam + all-gather over pe
   int variant;                   // DEBUG timing switches (r2l_debug_set_dp_grid's second argument), 0 in production
 };
 cudaError_t launch_dp_adam(const DpParams& p, int grid, cudaStream_t stream);
+// pool.cu: hard-example ray pool (main.py:1325-1347, :1410-1425)
+cudaError_t launch_pool_draw(const float* pool_rows, const int* state, int n_out, uint64_t seed, const long long* counters,
+                             float* dst_rows, int* slots_out, cudaStream_t stream);
+uint32_t pool_slot_host(uint32_t j, uint32_t size, uint64_t seed, uint64_t step);
+cudaError_t launch_pool_update(const float* rays9, const float* err, int n, int k, float* pool_rows, int* state, const int* slots_out,
+                               int* picked, cudaStream_t stream);
 struct AdamSchedule {
   double lrate, warmup_start_lr, warmup_end, decay_rate, decay_steps, beta1, beta2;   // warmup_end = 0: no warm-up
 };

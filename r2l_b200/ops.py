@@ -463,3 +463,57 @@ def adam_step_dev(params, grads, exp_avg, exp_avg_sq, beta1, beta2, eps, hyper_d
     with torch.cuda.device(params.device):
         _lib.check(_lib.lib().r2l_adam_step_dev(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), params.numel(), float(beta1),
                                                 float(beta2), float(eps), _ptr(hyper_dev), _stream()), "r2l_adam_step_dev")
+
+
+# ------------------------------------------------------------------------------------------------
+# hard-example ray pool (main.py:1325-1347, :1410-1425) as two graph-capturable launches
+# ------------------------------------------------------------------------------------------------
+def _require_cuda_i32(t, name, numel=None):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.int32 and t.is_contiguous()):
+        raise RuntimeError(f"{name}: expected a contiguous int32 CUDA tensor (no CPU fallback)")
+    if numel is not None and t.numel() < numel:
+        raise ValueError(f"{name}: expected >= {numel} elements, got {t.numel()}")
+    return t
+
+
+def pool_draw(pool_rows: torch.Tensor, pool_state: torch.Tensor, n_out: int, seed: int, counters: torch.Tensor,
+              dst_rows: torch.Tensor, slots_out: torch.Tensor) -> None:
+    """dst_rows[j] = pool_rows[slots_out[j]] for the first n_out values of the (seed, counters[0])-keyed permutation of the
+    pool's slots (r2l_pool_draw).  dst_rows: a contiguous [n_out, 9] view, e.g. the tail rows of the batch buffer."""
+    pool_rows = _require_cuda_f32(pool_rows, "pool_rows", (9,))
+    if not (dst_rows.is_cuda and dst_rows.dtype == torch.float32 and dst_rows.is_contiguous() and tuple(dst_rows.shape) == (n_out, 9)):
+        raise ValueError(f"dst_rows: expected a contiguous float32 CUDA tensor [{n_out}, 9]")
+    _require_cuda_i32(pool_state, "pool_state", 1)
+    _require_cuda_i32(slots_out, "slots_out", n_out)
+    if not (counters.is_cuda and counters.dtype == torch.int64 and counters.is_contiguous()):
+        raise RuntimeError("pool_draw: counters must be a contiguous int64 CUDA tensor")
+    with torch.cuda.device(pool_rows.device):
+        _lib.check(_lib.lib().r2l_pool_draw(_ptr(pool_rows), _ptr(pool_state), int(n_out), int(seed) & (2 ** 64 - 1), _ptr(counters),
+                                            _ptr(dst_rows), _ptr(slots_out), _stream()), "r2l_pool_draw")
+
+
+def pool_update(rays9: torch.Tensor, per_ray_err: torch.Tensor, n_fresh: int, n_hard_in: int, pool_rows: torch.Tensor,
+                pool_state: torch.Tensor, slots_out: torch.Tensor | None = None, picked: torch.Tensor | None = None) -> None:
+    """The n_hard_in rays of rays9[:n_fresh] with the largest per_ray_err go into the pool: appended at pool_state[0]
+    (slots_out None) or over rows slots_out[:n_hard_in] (r2l_pool_update)."""
+    rays9 = _require_cuda_f32(rays9, "rays9", (9,))
+    per_ray_err = _require_cuda_f32(per_ray_err, "per_ray_err")
+    pool_rows = _require_cuda_f32(pool_rows, "pool_rows", (9,))
+    if rays9.shape[0] < n_fresh or per_ray_err.numel() < n_fresh:
+        raise ValueError("pool_update: rays9 / per_ray_err hold fewer than n_fresh rays")
+    _require_cuda_i32(pool_state, "pool_state", 1)
+    if slots_out is not None:
+        _require_cuda_i32(slots_out, "slots_out", n_hard_in)
+    if picked is not None:
+        _require_cuda_i32(picked, "picked", n_hard_in)
+    with torch.cuda.device(rays9.device):
+        _lib.check(_lib.lib().r2l_pool_update(_ptr(rays9), _ptr(per_ray_err), int(n_fresh), int(n_hard_in), _ptr(pool_rows),
+                                              _ptr(pool_state), _ptr(slots_out), _ptr(picked), _stream()), "r2l_pool_update")
+
+
+def pool_slot_host(j: int, size: int, seed: int, step: int) -> int:
+    """Slot j of the permutation pool_draw uses (host evaluation of the same function: tests, replaying a run)."""
+    v = int(_lib.lib().r2l_pool_slot_host(int(j), int(size), int(seed) & (2 ** 64 - 1), int(step)))
+    if v < 0:
+        raise ValueError("pool_slot_host: need 0 <= j < size < 2^31")
+    return v

@@ -4,13 +4,13 @@
     reference, per iteration                                           here
     ---------------------------------------------------------------   ------------------------------------------------
     LR schedule, param_group['lr'] = ...            (:1181-1195)       r2l_adam_schedule_dev: device-side step counters
-    hard-ray pool: np.random.permutation + cat      (:1325-1347)       HardRayPool.draw (torch ops on the device)
+    hard-ray pool: np.random.permutation + cat      (:1325-1347)       r2l_pool_draw (one kernel, inside the graph)
     sample_train -> positional_embedder -> model    (:1369-1374)       r2l_forward_train (one kernel)
     img2mse * lw_rgb, psnr.item()                   (:1377-1379)       r2l_mse_loss_grad (one kernel, no host sync)
     optimizer.zero_grad(); loss.backward()          (:1403-1404)       r2l_backward (chain + weight gradients)
     [DataParallel reduce to GPU 0]                  (:472-479)         chunked, overlapped all-reduce of ONE flat buffer (N > 1)
     optimizer.step()  (Adam over 176 tensors)       (:1406)            r2l_adam_step_dev + r2l_pack_weights
-    torch.sort of per-ray errors, pool update       (:1410-1425)       HardRayPool.update (device, no sync)
+    torch.sort of per-ray errors, pool update       (:1410-1425)       r2l_pool_update (one kernel, inside the graph)
 
 No arithmetic of the network happens in torch; torch provides buffers, streams, the CUDA-graph capture and NCCL.
 """
@@ -38,16 +38,20 @@ def lr_at(global_step: int, lrate: float, lrate_decay: int, warmup_lr: str | Non
 
 
 class HardRayPool:
-    """Hard-example pool of main.py:1325-1347 (draw) and :1410-1425 (update), kept on the device.
+    """Hard-example pool of main.py:1325-1347 (draw) and :1410-1425 (update), kept on the device and maintained by two
+    kernels of the library (csrc/pool.cu) that are part of the captured iteration: no ATen launch, no host sync.
 
-    The reference sorts the per-ray errors, reads indices back implicitly and draws replacement slots with
-    np.random.permutation on the host every step; here both the top-n selection and the slot permutation are device ops,
-    so a step never waits for the host.  Semantics kept: the n_hard_in rays with the largest mean squared error of the
-    FRESH part of the batch enter; until the pool holds batch_size * hard_mul rays they are appended, afterwards they
-    overwrite the first n_hard_in of the n_hard_out slots drawn this step.  (The slot permutation comes from torch's device
-    generator instead of numpy's host generator: same distribution, different stream of numbers.)"""
+    The reference sorts the per-ray errors and draws replacement slots with np.random.permutation on the host every step.
+    Semantics kept: the n_hard_in rays with the largest mean squared error of the FRESH part of the batch enter; until the
+    pool holds batch_size * hard_mul rays they are appended, afterwards they overwrite the first n_hard_in of the n_hard_out
+    slots drawn this step.  Deliberate differences: the slots are the first n_hard_out values of a keyed pseudo-random
+    permutation evaluated on the device (same distribution, another stream of numbers than numpy's), and rays with EQUAL
+    error at the selection threshold enter lowest index first (torch.sort leaves that order unspecified).
 
-    def __init__(self, batch_size: int, hard_ratio, hard_mul: float, device):
+    The host keeps only a mirror of the fill state (`size`, `full`): it follows from the call sequence alone, so deciding
+    the batch size of the next iteration never reads device memory."""
+
+    def __init__(self, batch_size: int, hard_ratio, hard_mul: float, device, seed: int = 0):
         if isinstance(hard_ratio, (list, tuple)):
             n_in, n_out = int(hard_ratio[0] * batch_size), int(hard_ratio[1] * batch_size)
         else:
@@ -63,31 +67,32 @@ class HardRayPool:
         # appended in steps of n_hard_in until size >= batch_size * hard_mul (main.py:1423-1425)
         step = self.n_hard_in
         slots = -(-int(self.fill_level) // step) * step + step
-        self.rays = torch.empty((slots, 9), dtype=torch.float32, device=device)
-        self.size = 0
+        self.seed = int(seed)
+        self.rays = torch.zeros((slots, 9), dtype=torch.float32, device=device)
+        self.state = torch.zeros(1, dtype=torch.int32, device=device)            # rays in the pool, advanced by the update kernel
+        self.slots_out = torch.zeros(max(self.n_hard_out, 1), dtype=torch.int32, device=device)   # slots of the last draw
+        self.size = 0            # host mirror of state[0]
         self.full = False
-        self._slots_out = None
 
-    def draw(self):
-        """Rays [n_hard_out, 9] (o | d | target) to append to the batch, or None while the pool is filling."""
-        if not self.full:
-            self._slots_out = None
-            return None
-        self._slots_out = torch.randperm(self.size, device=self.rays.device)[:self.n_hard_out]
-        return self.rays[self._slots_out]
+    def n_extra(self) -> int:
+        """Pool rays the next batch carries (0 while the pool is filling)."""
+        return self.n_hard_out if self.full else 0
 
-    def update(self, rays_o, rays_d, target, per_ray_err, batch_size=None):
-        """per_ray_err: mean squared error per ray of the whole batch; only the fresh rays [:batch_size] compete (batch_size
-        of THIS call, main.py:1324,:1411-1413; n_hard_in / n_hard_out stay those of the first batch - the ray-shard loader's
-        batches all have N_rand * 4096 rays)."""
+    def enqueue_draw(self, dst_rows, counters):
+        """Pool full: n_hard_out pool rows -> dst_rows [n_hard_out, 9] (the tail of the batch buffer); one launch."""
+        ops.pool_draw(self.rays, self.state, self.n_hard_out, self.seed, counters, dst_rows, self.slots_out)
+
+    def enqueue_update(self, rays9, per_ray_err, batch_size, full):
+        """per_ray_err: mean squared error per ray of the whole batch; only the fresh rays [:batch_size] compete (batch_size of
+        THIS call, main.py:1324,:1411-1413; n_hard_in / n_hard_out stay those of the first batch - the ray-shard loader's
+        batches all have N_rand * 4096 rays).  One launch; the host mirror is advanced separately (advance)."""
+        ops.pool_update(rays9, per_ray_err, batch_size, self.n_hard_in, self.rays, self.state, self.slots_out if full else None)
+
+    def advance(self, batch_size=None):
+        """Host mirror of one update (main.py:1419-1425): call once per iteration whose update was enqueued or replayed."""
         batch_size = self.batch_size if batch_size is None else int(batch_size)
-        order = torch.sort(per_ray_err[:batch_size]).indices[-self.n_hard_in:]
-        hard = torch.cat([rays_o[order], rays_d[order], target[order]], dim=-1)
-        if self.full:
-            self.rays[self._slots_out[:self.n_hard_in]] = hard
-        else:
-            self.rays[self.size:self.size + hard.shape[0]] = hard
-            self.size += hard.shape[0]
+        if not self.full:
+            self.size += self.n_hard_in
             if self.size >= batch_size * self.hard_mul:
                 self.full = True
 
@@ -98,13 +103,13 @@ class R2LTrainer:
 
     def __init__(self, model, point_sampler, lrate=5e-4, lrate_decay=500, warmup_lr=None, lw_rgb=1.0, perturb=0.0,
                  hard_ratio=0, hard_mul=1, betas=(0.9, 0.999), eps=1e-8, use_graph=True, group=None, start_step=0,
-                 grad_split_layers=(64, 43, 21), comm_sms=0, dp_mode=None):
+                 grad_split_layers=(64, 43, 21), comm_sms=0, dp_mode=None, pool_seed=0):
         if not model.flat.is_cuda:
             raise RuntimeError("R2LTrainer: the model must live on a CUDA device (no CPU fallback)")
         self.model, self.sampler = model, point_sampler
         self.lrate, self.lrate_decay, self.warmup_lr, self.lw_rgb = lrate, lrate_decay, warmup_lr, float(lw_rgb)
         self.perturb, self.betas, self.eps = float(perturb), betas, eps
-        self.hard_ratio, self.hard_mul = hard_ratio, hard_mul
+        self.hard_ratio, self.hard_mul, self.pool_seed = hard_ratio, hard_mul, int(pool_seed)
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         # N > 1: "peer" = the fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory (csrc/dp.cu, the default
         # where the GPUs of the group can map each other's memory), "nccl" = chunked, overlapped NCCL all-reduces + local Adam
@@ -167,6 +172,9 @@ class R2LTrainer:
         n = st["in9"].shape[0]
         if from_host:     # host-fed iteration: the batch comes from the pinned staging rows, the loss goes back to the host
             st["in9"][:st["h9"].shape[0]].copy_(st["h9"], non_blocking=True)
+        batch, pool = st["batch"], self.pool
+        if pool is not None and st["pool_full"]:        # hard rays of this iteration -> rows [batch:] (main.py:1325-1347)
+            pool.enqueue_draw(st["in9"][batch:], self.d_steps)
         ops.adam_schedule_dev(self.d_steps, self.d_hyper, self.lrate, self.lrate_decay, self.warmup_lr, self.betas[0], self.betas[1])
         kw = dict(rays9=st["in9"])                      # (o | d | rgb) rows: the kernels read the columns in place
         if st["t_rand"] is not None:
@@ -177,6 +185,8 @@ class R2LTrainer:
         n_global = n * self.world
         ops.mse_loss_grad(rgb, st["in9"][:, 6:9], 2.0 * self.lw_rgb / (3 * n_global), self.lw_rgb / (3 * n), grad_rgb=st["grad_rgb"],
                           per_ray_err=st["err"], loss=self.loss)
+        if pool is not None:                            # hardest fresh rays -> pool (main.py:1410-1425)
+            pool.enqueue_update(st["in9"], st["err"], batch, st["pool_full"])
         ops.backward(self.packed, ctx, st["grad_rgb"], self.grads, bwd_saved=st["bwd_saved"], workspace=st["workspace"],
                      split_layers=self.split_layers, reserve_sms=self.reserve_sms)
         flat = self.model.flat.data
@@ -215,10 +225,14 @@ class R2LTrainer:
 
     MAX_BATCH_SIZES = 4    # static buffer sets (and graphs) kept; a 4096-ray set is ~1 GB of saved operand images
 
-    def _static_for(self, n):
+    def _static_for(self, n, batch=None, pool_full=False):
+        batch = n if batch is None else batch
         st = self._static.get(n)
         if st is not None:
             self._static[n] = self._static.pop(n)        # most recently used last
+            if (st["batch"], st["pool_full"]) != (batch, pool_full):   # same total, another fresh / pool split: re-capture
+                st["graph"] = st["graph_host"] = None
+                st["batch"], st["pool_full"] = batch, pool_full
         if st is None:
             while len(self._static) >= self.MAX_BATCH_SIZES:   # e.g. ragged last batches: drop the least recently used set
                 old = self._static.pop(next(iter(self._static)))
@@ -230,7 +244,8 @@ class R2LTrainer:
                       fwd_saved=torch.empty(nf, dtype=torch.uint8, device=dev), bwd_saved=torch.empty(nb, dtype=torch.uint8, device=dev),
                       workspace=torch.empty(nw, dtype=torch.uint8, device=dev),
                       t_rand=torch.zeros((n, N_SAMPLES), device=dev) if self.perturb > 0 else None,
-                      grad_rgb=torch.empty((n, 3), device=dev), err=torch.empty(n, device=dev), graph=None, graph_host=None, warm=0)
+                      grad_rgb=torch.empty((n, 3), device=dev), err=torch.empty(n, device=dev), graph=None, graph_host=None, warm=0,
+                      batch=batch, pool_full=pool_full)
             self._static[n] = st
         return st
 
@@ -271,17 +286,16 @@ class R2LTrainer:
         self.model._packed_version = (flat.data_ptr(), flat._version, str(flat.device))
 
     def _iterate(self, batch, fill, from_host=False):
-        """Common part of the entry points: pool draw, static buffers of the batch size, `fill(st, batch)` puts the fresh rays
-        into rows [:batch] of the [n, 9] input buffer (or its pinned staging), the iteration, the pool update."""
+        """Common part of the entry points: static buffers of the batch size (fresh rays + the pool rays the iteration will
+        draw), `fill(st, batch)` puts the fresh rays into rows [:batch] of the [n, 9] input buffer (or its pinned staging),
+        the iteration (pool draw and pool update are launches inside it)."""
         self._begin()
         if self.hard_ratio and self.pool is None:
-            self.pool = HardRayPool(batch, self.hard_ratio, self.hard_mul, self.dev)
-        extra = self.pool.draw() if self.pool is not None else None
-        n = batch + (extra.shape[0] if extra is not None else 0)
-        st = self._static_for(n)
+            self.pool = HardRayPool(batch, self.hard_ratio, self.hard_mul, self.dev, seed=self.pool_seed)
+        pool_full = self.pool is not None and self.pool.full
+        n = batch + (self.pool.n_extra() if self.pool is not None else 0)
+        st = self._static_for(n, batch, pool_full)
         fill(st, batch)
-        if extra is not None:
-            st["in9"][batch:].copy_(extra)
         if st["t_rand"] is not None:
             st["t_rand"].uniform_()           # sample_train's torch.rand (nerf_raybased.py:122), drawn on the device
             given = st.pop("t_rand_given", None)
@@ -289,7 +303,7 @@ class R2LTrainer:
                 st["t_rand"][:batch].copy_(given)
         self._run(st, from_host)
         if self.pool is not None:
-            self.pool.update(st["in9"][:, 0:3], st["in9"][:, 3:6], st["in9"][:, 6:9], st["err"], batch)
+            self.pool.advance(batch)
         self._end()
         return self.loss
 

@@ -144,22 +144,105 @@ def test_trainer_graph_eager_and_host_paths_are_identical(flat_seed0):
     assert float((upd - upd0).norm() / upd0.norm()) < 1e-2
 
 
+@pytest.mark.parametrize("n,k", [(40, 8), (640, 128), (4096, 819), (5000, 1), (81920, 16384), (1030, 1030)])
+def test_pool_update_kernel_selects_like_the_reference_sort(n, k):
+    """r2l_pool_update against the numpy restatement of main.py:1410-1425 (oracle hard_pool_update): same SET of rays enters
+    the pool (errors are distinct here, so the top-k set is unique), appended while filling, over the first k drawn slots once
+    full; rows outside the written range / slots stay untouched."""
+    rng = np.random.RandomState(n + k)
+    rays9 = rng.rand(n + 57, 9).astype(np.float32)            # 57 trailing rows = pool rays of the batch: must not compete
+    err = rng.permutation(n + 57).astype(np.float32) / 7.0      # distinct errors
+    err[n:] = 1e9                                               # the largest errors sit in the part that does not compete
+    cap = 3 * k + 5
+    pool = torch.full((cap, 9), -1.0, device=DEV)
+    state = torch.tensor([k], dtype=torch.int32, device=DEV)    # k rows already there
+    picked = torch.zeros(k, dtype=torch.int32, device=DEV)
+    d9, derr = torch.from_numpy(rays9).to(DEV), torch.from_numpy(err).to(DEV)
+    ops.pool_update(d9, derr, n, k, pool, state, None, picked)
+    want = np.sort(np.argsort(err[:n], kind="stable")[-k:])
+    got = picked.cpu().numpy()
+    assert np.array_equal(np.sort(got), want)                   # the same set of rays ...
+    assert np.array_equal(got[:-1], np.sort(got[:-1]))          # ... those above the k-th error in index order, the k-th last
+    out = pool.cpu().numpy()
+    assert int(state) == 2 * k
+    assert np.array_equal(out[k:2 * k], rays9[got]) and (out[:k] == -1).all() and (out[2 * k:] == -1).all()
+    # the reference's append (torch.sort(...).indices[-n_hard_in:], main.py:1413-1414) gives the same rows in ascending-error order
+    ref_rows = rays9[np.argsort(err[:n], kind="stable")[-k:]]
+    assert {r.tobytes() for r in ref_rows} == {r.tobytes() for r in out[k:2 * k]}
+    # pool full: rows go to the first k drawn slots
+    slots = torch.from_numpy(rng.permutation(cap)[:k + 3].astype(np.int32)).to(DEV)
+    before = pool.clone()
+    ops.pool_update(d9, derr, n, k, pool, state, slots)
+    out2, sl = pool.cpu().numpy(), slots.cpu().numpy()
+    assert int(state) == 2 * k                                  # size unchanged once full
+    assert np.array_equal(out2[sl[:k]], rays9[got])
+    untouched = np.setdiff1d(np.arange(cap), sl[:k])
+    assert np.array_equal(out2[untouched], before.cpu().numpy()[untouched])
+
+
+def test_pool_update_kernel_ties_nan_and_zero():
+    """Equal errors at the threshold: lowest ray index first; -0.0 == +0.0; NaN sorts as the largest (torch.sort)."""
+    err = np.array([0.5, 0.25, 0.5, -0.0, 0.5, np.nan, 0.0, 0.5, 0.125], np.float32)
+    rays9 = np.arange(9 * 9, dtype=np.float32).reshape(9, 9)
+    for k, want in ((1, [5]), (2, [5, 0]), (3, [5, 0, 2]), (5, [5, 0, 2, 4, 7]), (8, [0, 1, 2, 4, 5, 7, 8, 3]), (9, [0, 1, 2, 4, 5, 7, 8, 3, 6])):
+        pool = torch.zeros((16, 9), device=DEV)
+        state = torch.zeros(1, dtype=torch.int32, device=DEV)
+        picked = torch.zeros(k, dtype=torch.int32, device=DEV)
+        ops.pool_update(torch.from_numpy(rays9).to(DEV), torch.from_numpy(err).to(DEV), 9, k, pool, state, None, picked)
+        assert picked.cpu().tolist() == want, (k, picked.cpu().tolist())
+        assert np.array_equal(pool.cpu().numpy()[:k], rays9[want])
+
+
+def test_pool_draw_kernel_matches_the_host_permutation():
+    """r2l_pool_draw: slot j = the host-evaluable permutation (tests/test_train_host.py checks it is a bijection), rows are
+    copies of the pool rows at those slots, keyed by the DEVICE iteration counter."""
+    rng = np.random.RandomState(5)
+    for size, n_out in ((640, 128), (1000, 1000), (81920, 16384), (7, 3)):
+        rows = rng.rand(size + 9, 9).astype(np.float32)
+        pool, state = torch.from_numpy(rows).to(DEV), torch.tensor([size], dtype=torch.int32, device=DEV)
+        dst = torch.zeros((n_out + 2, 9), device=DEV)
+        slots = torch.zeros(n_out, dtype=torch.int32, device=DEV)
+        for step in (0, 12345):
+            counters = torch.tensor([step, 1], dtype=torch.int64, device=DEV)
+            ops.pool_draw(pool, state, n_out, 42, counters, dst[1:1 + n_out], slots)
+            sl = slots.cpu().numpy()
+            probe = list(range(min(n_out, 50))) + [n_out - 1]
+            assert [int(sl[j]) for j in probe] == [ops.pool_slot_host(j, size, 42, step) for j in probe]
+            assert len(set(sl.tolist())) == n_out and sl.min() >= 0 and sl.max() < size
+            out = dst.cpu().numpy()
+            assert np.array_equal(out[1:1 + n_out], rows[sl]) and (out[0] == 0).all() and (out[-1] == 0).all()
+
+
 def test_trainer_hard_ray_pool_and_perturb(flat_seed0):
     """hard_ratio 0.2, hard_mul 1: the pool fills in 5 iterations of 640 fresh rays, then every batch carries 128 pool rays
-    (768 rays: a second graph is captured for the new size); perturb > 0 draws the jitter on the device."""
+    (768 rays: a second graph is captured for the new size); perturb > 0 draws the jitter on the device.  Pool draw and
+    update are kernels of the captured iteration: every pool row is a row of some batch, the device-side fill count agrees
+    with the host mirror, and the drawn rows are the pool rows at the drawn slots."""
     model, ps = make_model(flat_seed0)
     tr = R2LTrainer(model, ps, hard_ratio=0.2, hard_mul=1, perturb=1.0, use_graph=True)
-    sizes = []
-    for it in range(1, 10):
+    sizes, fed = [], set()
+    for it in range(1, 12):
         o, d, t = rays(640, 100 + it)
+        fed |= {r.tobytes() for r in torch.cat([o, d, t], -1).numpy()}
+        pool_before = tr.pool.rays.clone() if tr.pool is not None else None
         loss = float(tr.step(o.to(DEV), d.to(DEV), t.to(DEV)))
         assert np.isfinite(loss)
         sizes.append(max(tr._static))
-    assert tr.pool.full and tr.pool.size == 640 and sizes[0] == 640 and sizes[-1] == 768
+        if sizes[-1] == 768:
+            st = tr._static[768]
+            sl = tr.pool.slots_out.cpu().numpy()
+            assert len(set(sl.tolist())) == 128 and sl.max() < 640
+            assert np.array_equal(st["in9"][640:].cpu().numpy(), pool_before.cpu().numpy()[sl])      # the draw
+            err = st["err"][:640].cpu().numpy()
+            top = np.argsort(err, kind="stable")[-128:]
+            if len(np.unique(err)) == 640:                                                                # the update
+                assert ({r.tobytes() for r in tr.pool.rays.cpu().numpy()[sl]} == {r.tobytes() for r in st["in9"][:640].cpu().numpy()[top]})
+    assert tr.pool.full and tr.pool.size == 640 and int(tr.pool.state) == 640 and sizes[0] == 640 and sizes[-1] == 768
     assert set(tr._static) == {640, 768}
     assert bool(torch.isfinite(model.flat).all())
     # the pool holds rays that were in some batch (o | d | target rows)
-    assert tr.pool.rays[:tr.pool.size].shape == (640, 9)
+    rows = tr.pool.rays[:tr.pool.size].cpu().numpy()
+    assert rows.shape == (640, 9) and all(r.tobytes() in fed for r in rows)
 
 
 def test_shard_loader_device_batches(tmp_path):

@@ -102,29 +102,52 @@ def test_lr_schedule_matches_reference_formula():
     assert lr_at(1000, 5e-4, 500, "0.0001,2000") == pytest.approx(3e-4)
 
 
-def test_hard_ray_pool_follows_the_reference_update():
-    """HardRayPool against the numpy restatement of main.py:1410-1425 with the same drawn slots."""
+def test_hard_ray_pool_host_mirror_follows_the_reference_fill():
+    """The host mirror of the pool (sizes, fullness, rays carried per batch) against the numpy restatement of
+    main.py:1410-1425; the device side (selection, slots, row moves) is tests/test_gpu_train.py."""
     rng = np.random.RandomState(0)
-    batch, hard_ratio, hard_mul = 40, 0.2, 1
-    pool = HardRayPool(batch, hard_ratio, hard_mul, torch.device("cpu"))
-    n_in = int(hard_ratio * batch)
-    ref_rays, ref_full = np.zeros((0, 9), np.float32), False
-    torch.manual_seed(0)
-    for it in range(12):
-        o, d, t = (rng.rand(batch, 3).astype(np.float32) for _ in range(3))
-        extra = pool.draw()
-        assert (extra is not None) == ref_full
-        slots = None
-        if extra is not None:
-            slots = pool._slots_out.numpy()
-            assert np.array_equal(extra.numpy(), ref_rays[slots])
-            o, d, t = (np.concatenate([a, extra.numpy()[:, 3 * k:3 * k + 3]]) for k, a in enumerate((o, d, t)))
-        rgb = rng.rand(o.shape[0], 3).astype(np.float32)
-        pool.update(torch.from_numpy(o), torch.from_numpy(d), torch.from_numpy(t), torch.from_numpy(orc.per_ray_error(rgb, t)))
-        ref_rays, ref_full = orc.hard_pool_update(ref_rays, ref_full, o, d, t, rgb, batch, n_in, hard_mul, slots)
-        assert pool.full == ref_full and pool.size == ref_rays.shape[0]
-        assert np.array_equal(pool.rays[:pool.size].numpy(), ref_rays)
-    assert pool.full
+    for batch, hard_ratio, hard_mul in ((40, 0.2, 1), (40, 0.2, 2.5), (64, [0.1, 0.3], 1), (50, 0.33, 1.3)):
+        pool = HardRayPool(batch, hard_ratio, hard_mul, torch.device("cpu"))
+        if isinstance(hard_ratio, list):
+            n_in, n_out = int(hard_ratio[0] * batch), int(hard_ratio[1] * batch)
+        else:
+            n_in = n_out = int(hard_ratio * batch)
+        assert (pool.n_hard_in, pool.n_hard_out) == (n_in, n_out)
+        ref_rays, ref_full = np.zeros((0, 9), np.float32), False
+        for it in range(40):
+            assert pool.full == ref_full and pool.n_extra() == (n_out if ref_full else 0)
+            n = batch + pool.n_extra()
+            o, d, t, rgb = (rng.rand(n, 3).astype(np.float32) for _ in range(4))
+            slots = rng.permutation(ref_rays.shape[0])[:n_out] if ref_full else None
+            ref_rays, ref_full = orc.hard_pool_update(ref_rays, ref_full, o, d, t, rgb, batch, n_in, hard_mul, slots)
+            pool.advance(batch)
+            assert pool.full == ref_full and pool.size == ref_rays.shape[0] <= pool.rays.shape[0]
+        assert pool.full
+    with pytest.raises(ValueError):
+        HardRayPool(4, 0.2, 1, torch.device("cpu"))       # int(0.8) == 0 rays: refused (see the class docstring)
+
+
+def test_pool_slot_permutation_is_a_bijection_and_varies_with_the_step():
+    """r2l_pool_slot_host = the function r2l_pool_draw evaluates per drawn ray (csrc/pool.cu: pool_slot, same code on host and
+    device): for every pool size it is a permutation of [0, size), so the n_hard_out drawn slots are distinct
+    (np.random.permutation(n)[:n_hard_out], main.py:1330-1332); it changes with the iteration counter and the seed, and every
+    slot is drawn about equally often."""
+    from r2l_b200 import ops
+    for size in (1, 2, 3, 5, 16, 17, 640, 1000, 4097):
+        perm = [ops.pool_slot_host(j, size, 7, 3) for j in range(size)]
+        assert sorted(perm) == list(range(size)), size
+    a = [ops.pool_slot_host(j, 640, 0, 10) for j in range(128)]
+    b = [ops.pool_slot_host(j, 640, 0, 11) for j in range(128)]
+    c = [ops.pool_slot_host(j, 640, 1, 10) for j in range(128)]
+    assert a != b and a != c and len(set(a)) == 128
+    assert 10 < len(set(a) & set(b)) < 50                 # two independent 128-subsets of 640 share 25.6 slots on average
+    # first-drawn slot over 4000 iterations of a 100-slot pool: 40 hits per slot expected, sigma 6.3
+    hits = np.bincount([ops.pool_slot_host(0, 100, 0, s) for s in range(4000)], minlength=100)
+    assert hits.min() >= 15 and hits.max() <= 70, (hits.min(), hits.max())
+    chi2 = float(((hits - 40.0) ** 2 / 40.0).sum())
+    assert chi2 < 160, chi2                               # 99 degrees of freedom: mean 99, sigma 14
+    with pytest.raises(ValueError):
+        ops.pool_slot_host(5, 5, 0, 0)
 
 
 def test_camera_poses_and_rays_match_the_reference(tmp_path):
