@@ -101,6 +101,12 @@ int r2l_teacher_pack_weights(const float* params, void* packed, void* stream);
 int r2l_teacher_forward(const float* pts, const float* viewdirs, const float* x_embedded, const void* packed, float* raw,
                         int64_t n_points, int64_t samples_per_ray, void* stream);
 
+/* The same query with the sample points built in the kernel: point (r, s) = rays_o[r] + rays_d[r] * z_vals[r, s]
+ * (render_rays, utils/create_data.py:486-487 coarse, :517 fine: the reference materialises pts[N,S,3] first).
+ * rays_o, rays_d, viewdirs: [N,3]; z_vals: [N,samples_per_ray]; raw: [N,samples_per_ray,4]. */
+int r2l_teacher_forward_rays(const float* rays_o, const float* rays_d, const float* viewdirs, const float* z_vals, const void* packed,
+                             float* raw, int64_t n_rays, int64_t samples_per_ray, void* stream);
+
 /* raw2outputs (nerf_raybased.py:226-295, raw_noise_std = 0): raw[N,S,4], z_vals[N,S], rays_d[N,3] ->
  * rgb_map[N,3], disp_map[N], acc_map[N], weights[N,S], depth_map[N].  One warp per ray, one pass over HBM. */
 int r2l_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, int64_t n_rays, int n_samples,

@@ -41,6 +41,7 @@ _PROTOTYPES = {
     "r2l_teacher_packed_bytes": (c_size_t, []),
     "r2l_teacher_pack_weights": (c_int, [c_void_p, c_void_p, c_void_p]),
     "r2l_teacher_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    "r2l_teacher_forward_rays": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "r2l_raw2outputs": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p]),
     "r2l_sample_pdf_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),

@@ -501,6 +501,26 @@ int r2l_teacher_forward(const float* pts, const float* viewdirs, const float* x_
   return check_launch(r2l::launch_teacher(p, plain_grid(n_points), (cudaStream_t)stream), "r2l_teacher_forward");
 }
 
+int r2l_teacher_forward_rays(const float* rays_o, const float* rays_d, const float* viewdirs, const float* z_vals, const void* packed,
+                             float* raw, int64_t n_rays, int64_t samples_per_ray, void* stream) {
+  if (n_rays == 0) return 0;
+  if (n_rays < 0 || samples_per_ray <= 0) return fail("r2l_teacher_forward_rays: %s", "bad sizes");
+  if (!rays_o || !rays_d || !viewdirs || !z_vals || !packed || !raw) return fail("r2l_teacher_forward_rays: %s", "null pointer");
+  if (misaligned(packed) || misaligned(raw)) return fail("r2l_teacher_forward_rays: %s", "packed/raw must be 16-byte aligned");
+  r2l::TeacherParams p;
+  memset(&p, 0, sizeof(p));
+  p.rays_o = rays_o;
+  p.rays_d = rays_d;
+  p.z_vals = z_vals;
+  p.viewdirs = viewdirs;
+  p.packed = static_cast<const uint8_t*>(packed);
+  p.raw = raw;
+  p.n_points = n_rays * samples_per_ray;
+  p.samples_per_ray = samples_per_ray;
+  p.num_tiles = num_tiles(p.n_points);
+  return check_launch(r2l::launch_teacher(p, plain_grid(p.n_points), (cudaStream_t)stream), "r2l_teacher_forward_rays");
+}
+
 int r2l_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
                   double beta2, double eps, int64_t step, void* stream) {
   if (n == 0) return 0;

@@ -82,6 +82,9 @@ constexpr size_t kTailPartialBytes = (size_t)256 * 771 * sizeof(float);
 struct TeacherParams {
   const float* pts;          // [P,3] sample points (ray-major: point p belongs to ray p / samples_per_ray)
   const float* viewdirs;     // [P / samples_per_ray, 3] normalised view directions
+  const float* rays_o;       // alternative to pts: rays_o[R,3], rays_d[R,3], z_vals[R,samples_per_ray]; the point is built in-kernel
+  const float* rays_d;
+  const float* z_vals;
   const float* x_embedded;   // alternative input: [P,90] already embedded (pts 63 | views 27); pts/viewdirs unused
   const uint8_t* packed;
   float* raw;                // [P,4] = (rgb, sigma) before any activation

@@ -78,6 +78,75 @@ __global__ void __launch_bounds__(256) r2l_raw2outputs_kernel(const float* __res
   }
 }
 
+// The same arithmetic in the same order (bit-identical results) for S <= 256 samples per ray, G = ceil(S / 32): every
+// load of the ray is issued before the first use (G 512-byte raw rows + G 128-byte z rows in flight per warp instead of
+// one), the depth of the next sample comes from the neighbouring lane instead of a second load, streaming cache hints on
+// data that is read / written exactly once.  (The one-group-at-a-time kernel above measured 24 % of the HBM peak at
+// 32,768 x 192 - profiles/r1_summary.md section 5: a dependent warp scan sat between consecutive loads.)
+template <int G>
+__global__ void __launch_bounds__(256) r2l_raw2outputs_unrolled_kernel(const float* __restrict__ raw, const float* __restrict__ z_vals,
+                                                                       const float* __restrict__ rays_d, int64_t n_rays, int n_samples,
+                                                                       int white_bkgd, float* __restrict__ rgb_map,
+                                                                       float* __restrict__ disp_map, float* __restrict__ acc_map,
+                                                                       float* __restrict__ weights, float* __restrict__ depth_map) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (ray >= n_rays) return;
+  const float4* rw = reinterpret_cast<const float4*>(raw + ray * n_samples * 4);
+  const float* zv = z_vals + ray * n_samples;
+  float4 r4[G];
+  float z[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const int i = 32 * g + lane;
+    const bool in = i < n_samples;
+    r4[g] = in ? __ldcs(rw + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    z[g] = in ? __ldcs(zv + i) : 0.f;
+  }
+  const float dx = rays_d[ray * 3], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
+  const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);        // torch.norm(rays_d) :255
+  float carry = 1.f;
+  float sr = 0.f, sg = 0.f, sb = 0.f, sdepth = 0.f, sacc = 0.f;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const int i = 32 * g + lane;
+    const bool in = i < n_samples;
+    float zn = __shfl_down_sync(0xffffffffu, z[g], 1);
+    const float z_first_of_next = __shfl_sync(0xffffffffu, z[g + 1 < G ? g + 1 : g], 0);
+    if (lane == 31) zn = z_first_of_next;
+    float alpha = 0.f;
+    if (in) {
+      const float dist = ((i + 1 < n_samples) ? (zn - z[g]) : 1e10f) * dnorm;   // :249-257
+      alpha = 1.f - expf(-fmaxf(r4[g].w, 0.f) * dist);                           // raw2alpha :246
+    }
+    const float t = in ? (1.f - alpha + 1e-10f) : 1.f;                           // :281-283
+    const float incl = warp_incl_prod(t, lane);
+    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 1.f;
+    const float w = alpha * (carry * excl);
+    carry *= __shfl_sync(0xffffffffu, incl, 31);
+    if (in) {
+      __stcs(weights + ray * n_samples + i, w);
+      sr += w / (1.f + expf(-r4[g].x));                                          // sigmoid :259
+      sg += w / (1.f + expf(-r4[g].y));
+      sb += w / (1.f + expf(-r4[g].z));
+      sdepth += w * z[g];
+      sacc += w;
+    }
+  }
+  sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb); sdepth = warp_sum(sdepth); sacc = warp_sum(sacc);
+  if (lane == 0) {
+    const float q = sdepth / sacc;
+    disp_map[ray] = (q != q) ? q : 1.f / fmaxf(1e-10f, q);     // NaN for a fully transparent ray, like the reference (see above)
+    acc_map[ray] = sacc;
+    depth_map[ray] = sdepth;
+    const float bg = white_bkgd ? (1.f - sacc) : 0.f;
+    rgb_map[ray * 3 + 0] = sr + bg;
+    rgb_map[ray * 3 + 1] = sg + bg;
+    rgb_map[ray * 3 + 2] = sb + bg;
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // dense positional encodings (only for callers that really want the tensor; the fused MLP kernels never do)
 //   style 0 (PositionalEmbedder, R2L): per coordinate [sin(x f_0..f_{L-1}), cos(...), x]   -> [N, D*(2L+1)]
@@ -204,8 +273,19 @@ cudaError_t launch_raw2outputs(const float* raw, const float* z_vals, const floa
                                float* depth_map, cudaStream_t stream) {
   const int warps = 8;
   const int64_t blocks = (n_rays + warps - 1) / warps;
-  r2l_raw2outputs_kernel<<<(unsigned)blocks, warps * 32, 0, stream>>>(raw, z_vals, rays_d, n_rays, n_samples, white_bkgd, rgb_map,
-                                                                    disp_map, acc_map, weights, depth_map);
+#define R2L_R2O(G)                                                                                                              \
+  case G:                                                                                                                      \
+    r2l_raw2outputs_unrolled_kernel<G><<<(unsigned)blocks, warps * 32, 0, stream>>>(raw, z_vals, rays_d, n_rays, n_samples,     \
+                                                                                    white_bkgd, rgb_map, disp_map, acc_map,    \
+                                                                                    weights, depth_map);                       \
+    break;
+  switch ((n_samples + 31) / 32) {
+    R2L_R2O(1) R2L_R2O(2) R2L_R2O(3) R2L_R2O(4) R2L_R2O(5) R2L_R2O(6) R2L_R2O(7) R2L_R2O(8)
+    default:      // more than 256 samples per ray: one group at a time
+      r2l_raw2outputs_kernel<<<(unsigned)blocks, warps * 32, 0, stream>>>(raw, z_vals, rays_d, n_rays, n_samples, white_bkgd, rgb_map,
+                                                                        disp_map, acc_map, weights, depth_map);
+  }
+#undef R2L_R2O
   return cudaGetLastError();
 }
 

@@ -202,11 +202,18 @@ __global__ void __launch_bounds__(kTThreads, 1) r2l_teacher_kernel(const __grid_
       float x[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
       if (valid && !p.x_embedded) {
         const int64_t ray = pt / p.samples_per_ray;
+        if (p.rays_o) {
+          // sample point built here: pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]
+          // (utils/create_data.py:486-487, :517): one rounded product and one rounded sum, as torch evaluates it
+          const float z = __ldg(p.z_vals + pt);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          x[c] = __ldg(p.pts + pt * 3 + c);
-          dir[c] = __ldg(p.viewdirs + ray * 3 + c);
+          for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(__ldg(p.rays_o + ray * 3 + c), __fmul_rn(__ldg(p.rays_d + ray * 3 + c), z));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) x[c] = __ldg(p.pts + pt * 3 + c);
         }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) dir[c] = __ldg(p.viewdirs + ray * 3 + c);
       }
       float enc[32];
       // embedded-input mode (NeRF.forward called directly with the [P,90] tensor of run_network :66-72): gather the

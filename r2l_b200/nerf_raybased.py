@@ -452,6 +452,41 @@ def batchify(fn, chunk):
     return lambda inputs: torch.cat([fn(inputs[i:i + chunk]) for i in range(0, inputs.shape[0], chunk)], 0)
 
 
+class RayPoints:
+    """What render_rays hands to network_query_fn instead of `pts = rays_o[..., None, :] + rays_d[..., None, :] *
+    z_vals[..., :, None]` (utils/create_data.py:486-487, :517): the three operands and the promise of the [N,S,3] tensor.
+    run_network + the stock teacher consume it without the points ever existing in HBM (the teacher kernel builds each
+    point in its prologue); any other consumer - a torch function, indexing, a custom query function - gets the real
+    tensor, evaluated with exactly the reference's expression."""
+
+    def __init__(self, rays_o: torch.Tensor, rays_d: torch.Tensor, z_vals: torch.Tensor):
+        self.rays_o, self.rays_d, self.z_vals = rays_o, rays_d, z_vals
+
+    shape = property(lambda self: torch.Size([self.z_vals.shape[0], self.z_vals.shape[1], 3]))
+    device = property(lambda self: self.z_vals.device)
+    dtype = property(lambda self: self.z_vals.dtype)
+    is_cuda = property(lambda self: self.z_vals.is_cuda)
+
+    def dim(self):
+        return 3
+
+    def materialize(self) -> torch.Tensor:
+        return self.rays_o[..., None, :] + self.rays_d[..., None, :] * self.z_vals[..., :, None]
+
+    def __getitem__(self, idx):
+        return self.materialize()[idx]
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        def real(a):
+            if isinstance(a, RayPoints):
+                return a.materialize()
+            if isinstance(a, (list, tuple)):
+                return type(a)(real(v) for v in a)
+            return a
+        return func(*real(tuple(args)), **{k: real(v) for k, v in (kwargs or {}).items()})
+
+
 def _default_embedder(fn, n_freqs):
     eo = (getattr(fn, "__defaults__", None) or (None,))[0]
     return isinstance(eo, Embedder) and eo._kernel_ok and eo.n_freqs == n_freqs
@@ -464,7 +499,11 @@ def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64
     net = getattr(fn, "module", fn)
     if (isinstance(net, NeRF) and net.fused_ok and viewdirs is not None and inputs.is_cuda and inputs.dim() == 3
             and inputs.dtype == torch.float32 and _default_embedder(embed_fn, 10) and _default_embedder(embeddirs_fn, 4)):
+        if isinstance(inputs, RayPoints):
+            return net.query_rays(inputs.rays_o, inputs.rays_d, inputs.z_vals, viewdirs)
         return net.query(inputs, viewdirs)
+    if isinstance(inputs, RayPoints):
+        inputs = inputs.materialize()
     flat = torch.reshape(inputs, [-1, inputs.shape[-1]])
     embedded = embed_fn(flat)
     if viewdirs is not None:
@@ -540,6 +579,11 @@ class NeRF(nn.Module):
         """Fused run_network: pts[N,S,3], viewdirs[N,3] -> raw[N,S,4]."""
         self._check()
         return ops.teacher_forward(self.packed_weights(), pts=pts, viewdirs=viewdirs)
+
+    def query_rays(self, rays_o, rays_d, z_vals, viewdirs):
+        """Fused run_network on the points rays_o + rays_d * z_vals[N,S] (built in-kernel) -> raw[N,S,4]."""
+        self._check()
+        return ops.teacher_forward_rays(self.packed_weights(), rays_o, rays_d, z_vals, viewdirs)
 
     def load_weights_from_keras(self, weights):
         """TF-NeRF .npy weight list -> parameters (reference :403-440)."""

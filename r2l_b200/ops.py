@@ -351,6 +351,23 @@ def teacher_forward(packed: torch.Tensor, *, pts=None, viewdirs=None, x_embedded
     return raw
 
 
+def teacher_forward_rays(packed: torch.Tensor, rays_o, rays_d, z_vals, viewdirs) -> torch.Tensor:
+    """raw[N,S,4] of the teacher MLP at the points rays_o + rays_d * z_vals[N,S], built in the kernel (no pts tensor)."""
+    rays_o = _require_cuda_f32(rays_o, "rays_o", (3,))
+    rays_d = _require_cuda_f32(rays_d, "rays_d", (3,))
+    viewdirs = _require_cuda_f32(viewdirs, "viewdirs", (3,))
+    z_vals = _require_cuda_f32(z_vals, "z_vals")
+    n = rays_o.shape[0]
+    if z_vals.dim() != 2 or z_vals.shape[0] != n or rays_d.shape[0] != n or viewdirs.shape[0] != n:
+        raise ValueError("rays_o / rays_d / viewdirs / z_vals disagree on the number of rays")
+    s = z_vals.shape[1]
+    raw = torch.empty((n, s, 4), dtype=torch.float32, device=rays_o.device)
+    with torch.cuda.device(rays_o.device):
+        _lib.check(_lib.lib().r2l_teacher_forward_rays(_ptr(rays_o), _ptr(rays_d), _ptr(viewdirs), _ptr(z_vals), _ptr(packed), _ptr(raw),
+                                                       n, s, _stream()), "r2l_teacher_forward_rays")
+    return raw
+
+
 def sample_pdf_merge(z_vals: torch.Tensor, weights: torch.Tensor, n_importance: int, u: torch.Tensor | None = None):
     """(z_samples[N,M], z_merged[N,S+M]) : inverse-CDF resampling of the coarse weights + sorted merge, on the GPU.
     u None = deterministic linspace (perturb == 0); else uniforms [N,M] or [M]."""

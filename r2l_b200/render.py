@@ -21,6 +21,14 @@ def sample_pdf(bins, weights, N_samples, det=False, pytest=False):
     return ops.sample_pdf(bins, weights, N_samples, u)
 
 
+def _ray_points(rays_o, rays_d, z_vals):
+    """pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None] (utils/create_data.py:486-487, :517) as a lazy
+    nb.RayPoints: the fused teacher query builds the points in its prologue, anything else gets the real tensor."""
+    if z_vals.is_cuda and z_vals.dtype == torch.float32 and rays_o.dtype == torch.float32:
+        return nb.RayPoints(rays_o, rays_d, z_vals)
+    return rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]
+
+
 def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False, lindisp=False, perturb=0.,
                 N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0., verbose=False, pytest=False):
     """Volumetric rendering of a ray batch [N, 8 or 11] = (o, d, near, far[, viewdir]); returns the reference's dict."""
@@ -44,14 +52,14 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
         lower = torch.cat([z_vals[..., :1], mids], -1)
         z_vals = lower + (upper - lower) * torch.rand(z_vals.shape).to(dev)
     z_vals = z_vals.contiguous()
-    pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]
+    pts = _ray_points(rays_o, rays_d, z_vals)
     raw = network_query_fn(pts, viewdirs, network_fn)
     rgb_map, disp_map, acc_map, weights, depth_map = nb.raw2outputs(raw, z_vals, rays_d, raw_noise_std, white_bkgd)
     if N_importance > 0:
         rgb_map_0, disp_map_0, acc_map_0 = rgb_map, disp_map, acc_map
         u = None if perturb == 0. else torch.rand(n_rays, N_importance).to(dev)
         z_samples, z_vals = ops.sample_pdf_merge(z_vals, weights, N_importance, u)     # sample_pdf + sort(cat(...))
-        pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]
+        pts = _ray_points(rays_o, rays_d, z_vals)
         run_fn = network_fn if network_fine is None else network_fine
         raw = network_query_fn(pts, viewdirs, run_fn)
         rgb_map, disp_map, acc_map, weights, depth_map = nb.raw2outputs(raw, z_vals, rays_d, raw_noise_std, white_bkgd)

@@ -452,6 +452,42 @@ def test_sample_pdf_merge_golden_and_properties(golden_teacher):
     assert np.mean(np.abs(zs.cpu().numpy() - ref) > 1e-4) < 0.01
 
 
+@pytest.mark.parametrize("s", [1, 2, 31, 32, 33, 64, 100, 256, 257, 300])
+def test_raw2outputs_ragged_sample_counts_vs_oracle(s):
+    """Every sample-count class of the compositing kernel (1..8 groups of 32 with all loads in flight; > 256 samples: the
+    one-group-at-a-time kernel), ragged ray counts, against the numpy oracle."""
+    torch.manual_seed(s)
+    n = 1237
+    raw = torch.randn(n, s, 4) * 2
+    z = torch.sort(torch.rand(n, s) * 4 + 2, dim=-1).values
+    d = torch.randn(n, 3)
+    outs = ops.raw2outputs(raw.to(DEV), z.to(DEV), d.to(DEV), False)
+    ref = orc.raw2outputs(raw.numpy(), z.numpy(), d.numpy(), False)
+    for got, want, tol in zip(outs, ref, (3e-5, 1e-3, 3e-5, 3e-6, 3e-5)):
+        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-4, atol=tol)
+
+
+def test_teacher_query_on_rays_equals_query_on_points(teacher):
+    """r2l_teacher_forward_rays builds pts = rays_o + rays_d * z_vals in its prologue with torch's rounding (one product, one
+    sum): bit-identical raw to the query on the materialised points; the lazy nb.RayPoints that render_rays passes
+    through run_network takes that path, and behaves like the real tensor for everybody else."""
+    torch.manual_seed(11)
+    n, s = 301, 192
+    o = (torch.tensor([0., 0., 4.]) + torch.randn(n, 3) * 0.05).to(DEV)
+    d = (torch.randn(n, 3) * 0.2 + torch.tensor([0., 0., -1.])).to(DEV)
+    z = torch.sort(torch.rand(n, s) * 4 + 2, dim=-1).values.to(DEV)
+    vd = d / d.norm(dim=-1, keepdim=True)
+    pts = o[..., None, :] + d[..., None, :] * z[..., :, None]
+    want = teacher.query(pts.contiguous(), vd)
+    got = teacher.query_rays(o, d, z, vd)
+    assert torch.equal(got, want)
+    embed_fn, _ = nb.get_embedder(10, 0)
+    embeddirs_fn, _ = nb.get_embedder(4, 0)
+    lazy = nb.RayPoints(o, d, z)
+    assert torch.equal(nb.run_network(lazy, vd, teacher, embed_fn, embeddirs_fn), want)
+    assert lazy.shape == pts.shape and torch.equal(torch.reshape(lazy, [-1, 3]), pts.reshape(-1, 3)) and torch.equal(lazy[3:5], pts[3:5])
+
+
 def test_teacher_render_rays_vs_oracle(teacher):
     """Config 4 path end to end (coarse 64 + fine 64+128, white background, perturb 0) against the numpy oracle."""
     from r2l_b200 import render as rr
