@@ -1,4 +1,5 @@
-"""Data-parallel plumbing: one process per GPU, rays sharded, ONE all-reduce of the flat gradient per step.
+"""Data-parallel plumbing: one process per GPU, rays sharded; training = ONE exchange of the flat gradient per step,
+rendering = no collective but the final gather of the frames (BASELINE config 5).
 
 Replaces the reference's single-process nn.DataParallel (main.py:37-42, :472-479), which re-broadcasts all 23.7 MB of
 parameters every forward and reduces gradients to GPU 0.  Rays are independent, so the forward needs no collective; the
@@ -32,16 +33,69 @@ def allreduce_flat_grads(grads: torch.Tensor, group=None) -> torch.Tensor:
     return grads
 
 
-def gather_rgb(rgb_local: torch.Tensor, n: int, group=None) -> torch.Tensor:
-    """Inference: every rank renders its ray range; rank order concatenation restores the frame."""
+def gather_rows(local: torch.Tensor, n: int, group=None) -> torch.Tensor:
+    """Inference: every rank holds rows [shard_range(n, rank, world)) of an [n, ...] result; returns the whole result on
+    every rank (rank-order concatenation).  One all_gather of equal-size (padded) pieces; with a gloo group CUDA rows are
+    staged through the host."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return rgb_local
+        return local
     world = dist.get_world_size(group)
-    sizes = [shard_range(n, r, world) for r in range(world)]
-    parts = [torch.empty((hi - lo, 3), dtype=rgb_local.dtype, device=rgb_local.device) for lo, hi in sizes]
-    dist.all_gather(parts, rgb_local.contiguous(), group=group) if len({hi - lo for lo, hi in sizes}) == 1 else \
-        [dist.broadcast(parts[r] if r != dist.get_rank(group) else parts[r].copy_(rgb_local), src=r, group=group) for r in range(world)]
-    return torch.cat(parts, 0)
+    sizes = [hi - lo for lo, hi in (shard_range(n, r, world) for r in range(world))]
+    if local.shape[0] != sizes[dist.get_rank(group)]:
+        raise ValueError(f"gather_rows: this rank holds {local.shape[0]} rows, its shard of {n} has {sizes[dist.get_rank(group)]}")
+    via_host = local.is_cuda and dist.get_backend(group) == "gloo"
+    piece = torch.zeros((max(sizes),) + tuple(local.shape[1:]), dtype=local.dtype, device="cpu" if via_host else local.device)
+    piece[:local.shape[0]].copy_(local)
+    parts = [torch.empty_like(piece) for _ in range(world)]
+    dist.all_gather(parts, piece, group=group)
+    out = torch.cat([p[:k] for p, k in zip(parts, sizes)], 0)
+    return out.to(local.device) if via_host else out
+
+
+gather_rgb = gather_rows     # name used by the round-1 tests
+
+
+def render_poses_shard(model, c2w: torch.Tensor, point_sampler, focal: float, rank: int, world: int) -> torch.Tensor:
+    """Rank `rank`'s share of rendering the poses c2w[P,3,4] with `world` ranks, as rows [k, 3] of the [P*H*W, 3] result:
+
+      * P >= world: contiguous pose ranges, whole frames through the pose -> frame kernel (r2l_render_poses);
+      * P <  world: (one frame at a time is latency-critical) the P*H*W rays are cut into contiguous ranges and run through the
+        rays -> rgb kernel on PointSampler's own rays_o / rays_d.
+
+    Rays are independent (main.py:300-309), so no collective is needed to render; gather_rows assembles the frames."""
+    if c2w.dim() == 2:
+        c2w = c2w[None]
+    n_poses, hw = c2w.shape[0], point_sampler.H * point_sampler.W
+    if n_poses >= world:
+        lo, hi = shard_range(n_poses, rank, world)
+        if hi == lo:
+            return torch.empty((0, 3), dtype=torch.float32, device=model.flat.device)
+        return model.render_poses(c2w[lo:hi], point_sampler, focal).reshape(-1, 3)
+    lo, hi = shard_range(n_poses * hw, rank, world)
+    parts = []
+    for k in range(lo // hw, (hi - 1) // hw + 1 if hi > lo else lo // hw):
+        a, b = max(lo, k * hw) - k * hw, min(hi, (k + 1) * hw) - k * hw
+        rays_o, rays_d = point_sampler._pose_rays(c2w[k].to(model.flat.device, torch.float32))
+        with torch.no_grad():
+            parts.append(model.forward_rays(rays_o[a:b].contiguous(), rays_d[a:b].contiguous(), point_sampler))
+    return torch.cat(parts, 0) if parts else torch.empty((0, 3), dtype=torch.float32, device=model.flat.device)
+
+
+def render_poses_sharded(model, c2w: torch.Tensor, point_sampler, focal: float, group=None) -> torch.Tensor:
+    """render_test on all GPUs of the job (the reference renders on ONE GPU: main.py:473 "when rendering, use just one GPU"):
+    every rank renders its share (render_poses_shard) and all ranks get the frames [P,H,W,3]."""
+    on = dist.is_available() and dist.is_initialized()
+    rank, world = (dist.get_rank(group), dist.get_world_size(group)) if on else (0, 1)
+    single = c2w.dim() == 2
+    n_poses = 1 if single else c2w.shape[0]
+    hw = point_sampler.H * point_sampler.W
+    local = render_poses_shard(model, c2w, point_sampler, focal, rank, world)
+    if n_poses >= world:      # whole frames per rank: gather in units of frames so that shard sizes follow the pose ranges
+        frames = gather_rows(local.reshape(-1, hw, 3), n_poses, group)
+    else:
+        frames = gather_rows(local, n_poses * hw, group)
+    frames = frames.reshape(n_poses, point_sampler.H, point_sampler.W, 3)
+    return frames[0] if single else frames
 
 
 class _DeviceBlob:

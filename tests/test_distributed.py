@@ -33,7 +33,16 @@ def _worker(rank, world, port, n, out_dir):
     _, g_local, rgb_local, _ = orc.r2l_loss_and_grads(flat, x[lo:hi], target[lo:hi])
     g = torch.from_numpy(g_local * ((hi - lo) / n))
     parallel.allreduce_flat_grads(g)
-    rgb = parallel.gather_rgb(torch.from_numpy(rgb_local), n)
+    rgb = parallel.gather_rows(torch.from_numpy(rgb_local), n)
+    # frames gathered in units of whole frames (config 5, P >= world): 3 poses over 2 ranks = 2 + 1
+    plo, phi = parallel.shard_range(3, rank, world)
+    frames = parallel.gather_rows(torch.arange(3 * 4 * 3, dtype=torch.float32).reshape(3, 4, 3)[plo:phi], 3)
+    assert torch.equal(frames, torch.arange(3 * 4 * 3, dtype=torch.float32).reshape(3, 4, 3))
+    stub, ps = _StubModel(), _stub_sampler()
+    for n_poses in (1, 3):
+        c2w = torch.from_numpy(np.random.RandomState(n_poses).randn(n_poses, 3, 4).astype(np.float32))
+        got = parallel.render_poses_sharded(stub, c2w, ps, 10.0)
+        assert torch.equal(got, stub.render_poses(c2w, ps, 10.0))
     if rank == 0:
         _, g_full, rgb_full, _ = orc.r2l_loss_and_grads(flat, x, target)
         np.save(os.path.join(out_dir, "err.npy"), np.array([
@@ -43,6 +52,42 @@ def _worker(rank, world, port, n, out_dir):
         assert torch.allclose(gr, torch.from_numpy((rgb_local - target[lo:hi]) * 2.0 / (3 * n)))
     dist.barrier()
     dist.destroy_process_group()
+
+
+class _StubModel:
+    """Stands in for NeRF_v3_2 in the sharding tests: rgb = a fixed function of the ray, through the same two entry points."""
+    flat = torch.zeros(1)
+
+    @staticmethod
+    def _shade(o, d):
+        return o * 0.25 + d * 2.0           # exact scalings + one rounding: the same bits whatever the slice length
+
+    def render_poses(self, c2w, ps, focal):
+        c2w = c2w[None] if c2w.dim() == 2 else c2w
+        return torch.stack([self._shade(*ps._pose_rays(c)).reshape(ps.H, ps.W, 3) for c in c2w])
+
+    def forward_rays(self, rays_o, rays_d, ps):
+        return self._shade(rays_o, rays_d)
+
+
+def _stub_sampler():
+    from r2l_b200 import nerf_raybased as nb
+    nb.device = torch.device("cpu")
+    return nb.PointSampler(5, 7, 10.0, 16, 2.0, 6.0)
+
+
+def test_render_shards_tile_the_frames():
+    """Config 5 sharding arithmetic: for every world size the ranks' shares, concatenated in rank order, are the frames -
+    whole poses per rank when there are enough poses, contiguous ray ranges of the frames otherwise."""
+    stub, ps = _StubModel(), _stub_sampler()
+    for n_poses in (1, 2, 5, 8, 11):
+        c2w = torch.from_numpy(np.random.RandomState(n_poses).randn(n_poses, 3, 4).astype(np.float32))
+        full = stub.render_poses(c2w, ps, 10.0).reshape(-1, 3)
+        for world in (1, 2, 3, 4, 8):
+            parts = [parallel.render_poses_shard(stub, c2w, ps, 10.0, r, world) for r in range(world)]
+            assert torch.equal(torch.cat(parts, 0), full), (n_poses, world)
+            if n_poses < world:
+                assert max(p.shape[0] for p in parts) - min(p.shape[0] for p in parts) <= 1
 
 
 def test_shard_range_partitions():

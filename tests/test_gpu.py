@@ -126,6 +126,35 @@ def test_render_poses_module_surface_and_full_frame(packed, flat_seed0):
     assert u8.dtype == torch.uint8 and np.array_equal(u8.cpu().numpy(), orc.to8b(frames.cpu().numpy()))
 
 
+def test_render_shards_of_a_frame_equal_the_single_gpu_frame(flat_seed0):
+    """BASELINE config 5 (render_test over several GPUs; the reference uses one, main.py:473): the shares
+    parallel.render_poses_shard gives to the ranks of a 2- or 3-GPU job, rendered here one after the other on this GPU and
+    concatenated in rank order, are bit-identical to the frames rendered in one piece - pose ranges through the pose -> frame
+    kernel, ray ranges of a single frame through the rays -> rgb kernel (every share stays in the launch form of the
+    whole: > 9,472 rays).  tools/render_sweep.py runs the same check across real ranks (profiles/r2_render_sweep_*.log)."""
+    from r2l_b200 import parallel
+    nb.device = torch.device(DEV)
+    model = nb.NeRF_v3_2(nb.readme_args(), 1008, 3).to(DEV)
+    with torch.no_grad():
+        model.flat.copy_(torch.from_numpy(flat_seed0).to(DEV))
+    focal = 555.5555155968841 / 2
+    ps = nb.PointSampler(200, 200, focal, 16, 2.0, 6.0)
+    g = torch.Generator().manual_seed(5)
+    poses = torch.randn(4, 3, 4, generator=g) * 0.5
+    poses[:, :, 3] = torch.tensor([0., 0., 4.])
+    poses = poses.to(DEV)
+    with torch.no_grad():
+        frames = model.render_poses(poses, ps, focal)
+        one = model.forward_rays(*[t.contiguous() for t in ps._pose_rays(poses[0])], ps)
+        for world in (2, 3):
+            parts = [parallel.render_poses_shard(model, poses, ps, focal, r, world) for r in range(world)]
+            assert torch.equal(torch.cat(parts, 0).reshape(4, 200, 200, 3), frames)
+            parts = [parallel.render_poses_shard(model, poses[0], ps, focal, r, world) for r in range(world)]
+            assert [p.shape[0] for p in parts] == [hi - lo for lo, hi in (parallel.shard_range(40000, r, world) for r in range(world))]
+            assert torch.equal(torch.cat(parts, 0), one)
+        assert torch.equal(parallel.render_poses_sharded(model, poses, ps, focal), frames)     # no process group: one rank
+
+
 def test_forward_nchw_branch_matches_the_reference(golden_surface, flat_seed0):
     """NeRF_v3_2.forward's channels-first branch (:540-541): x [n, 1008, h, w] is permuted to channels-last; the reference's
     output on the fixture (seed-0 weights) is [n, h, w, 3]."""
