@@ -126,6 +126,47 @@ def test_render_poses_module_surface_and_full_frame(packed, flat_seed0):
     assert u8.dtype == torch.uint8 and np.array_equal(u8.cpu().numpy(), orc.to8b(frames.cpu().numpy()))
 
 
+def test_c_program_drives_forward_and_backward_through_the_header(tmp_path, golden_r2l, flat_seed0, packed):
+    """The boundary is a C ABI: tests/c_probe/forward_probe.c (plain C99 + the CUDA runtime's C API, no torch, no Python)
+    packs the weights, runs r2l_forward and r2l_forward_train -> r2l_mse_loss_grad -> r2l_backward on the golden batch.
+    Its RGB is bit-identical to the same calls made through the Python binding and within the parity bar of the
+    reference's; its gradient meets the same bound as test_backward_golden_vs_fp64."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, "r2l_b200", "csrc")
+    exe = str(tmp_path / "forward_probe")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    res = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(cuda, "include"),
+                          os.path.join(root, "tests", "c_probe", "forward_probe.c"), "-o", exe, "-L" + csrc, "-lr2l_b200",
+                          "-L" + os.path.join(cuda, "lib64"), "-lcudart", "-Wl,-rpath," + csrc], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    g = golden_r2l
+    n = g["rays_o"].shape[0]
+    files = {}
+    for name, arr in (("params", flat_seed0), ("rays_o", g["rays_o"]), ("rays_d", g["rays_d"]), ("target", g["target"]), ("z_vals", g["z_vals"])):
+        files[name] = str(tmp_path / (name + ".f32"))
+        np.ascontiguousarray(arr, dtype=np.float32).tofile(files[name])
+    out_rgb, out_grads = str(tmp_path / "rgb.f32"), str(tmp_path / "grads.f32")
+    run = subprocess.run([exe, files["params"], files["rays_o"], files["rays_d"], files["target"], files["z_vals"], str(n), out_rgb, out_grads],
+                         capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, (run.stdout, run.stderr)
+    print(run.stdout.strip())
+    rgb = np.fromfile(out_rgb, dtype=np.float32).reshape(n, 3)
+    ro, rd = torch.from_numpy(g["rays_o"]).to(DEV), torch.from_numpy(g["rays_d"]).to(DEV)
+    assert np.array_equal(rgb, ops.forward(packed, rays_o=ro, rays_d=rd, z_vals=g["z_vals"].tolist()).cpu().numpy())
+    assert relerr(rgb, g["rgb"]) < FWD_TOL
+    grads = np.fromfile(out_grads, dtype=np.float32).astype(np.float64)
+    sub = grads[g["grad_idx"]]
+    err = np.linalg.norm(sub - g["grad_f64_sub"]) / np.linalg.norm(g["grad_f64_sub"])
+    assert err < 1e-3 and err < 3 * float(g["grad_f32_vs_f64_rel"]), err
+    loss = float(run.stdout.split("loss")[1].split()[0])
+    assert abs(loss - float(g["loss"])) < 1e-5
+
+
 def test_render_shards_of_a_frame_equal_the_single_gpu_frame(flat_seed0):
     """BASELINE config 5 (render_test over several GPUs; the reference uses one, main.py:473): the shares
     parallel.render_poses_shard gives to the ranks of a 2- or 3-GPU job, rendered here one after the other on this GPU and

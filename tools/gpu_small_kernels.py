@@ -23,3 +23,40 @@ print(f"pack_weights        {timed(lambda: ops.pack_weights(flat, out=packed)):7
 print(f"mse_loss_grad       {timed(lambda: ops.mse_loss_grad(rgb, tgt, 1e-4, 1e-4, want_per_ray=True)):7.2f} us")
 print(f"adam_step_dev       {timed(lambda: ops.adam_step_dev(flat, g, m, v, 0.9, 0.999, 1e-8, hd)):7.2f} us")
 print(f"adam + pack         {timed(lambda: (ops.adam_step_dev(flat, g, m, v, 0.9, 0.999, 1e-8, hd), ops.pack_weights(flat, out=packed))):7.2f} us")
+
+# ---- teacher-side kernels (config 4 sizes: a 32,768-ray chunk, 64 coarse / 192 fine samples) and the hard-ray pool ----
+quick = len(sys.argv) > 1 and sys.argv[1] == "ncu"        # under ncu: each kernel a couple of times, no timing loops
+reps = 2 if quick else 20
+from r2l_b200 import nerf_raybased as nb
+nb.device = dev
+torch.manual_seed(0)
+HBM = 6552.0
+for S in (64, 192):
+    N = 32768
+    raw = torch.randn(N, S, 4, device=dev); zv = torch.sort(torch.rand(N, S, device=dev) * 4 + 2, dim=-1).values; rd = torch.randn(N, 3, device=dev)
+    us = timed(lambda: ops.raw2outputs(raw, zv, rd, True), reps)
+    nbytes = N * (4 * (5 * S + 3) + 4 * (6 + S))
+    print(f"raw2outputs {N} x {S}: {us:7.2f} us = {nbytes / us / 1e3:6.0f} GB/s algorithmic = {nbytes / us / 1e3 / HBM:.2f} of the HBM peak (incl. output allocation)")
+N, S, M = 32768, 64, 128
+zv = torch.sort(torch.rand(N, S, device=dev) * 4 + 2, dim=-1).values; w = torch.rand(N, S, device=dev)
+us = timed(lambda: ops.sample_pdf_merge(zv, w, M, None), reps)
+nbytes = N * (4 * 2 * S + 4 * (2 * M + S))
+print(f"sample_pdf_merge {N} x {S} -> {M}: {us:7.2f} us = {nbytes / us / 1e3:6.0f} GB/s algorithmic")
+teacher = nb.NeRF(8, 256, 63, 27, 4, [4], True).to(dev)
+N, S = (2048, 192) if quick else (32768, 192)
+o = torch.randn(N, 3, device=dev) * 0.1 + torch.tensor([0., 0., 4.], device=dev); d = torch.randn(N, 3, device=dev) * 0.3
+zv = torch.sort(torch.rand(N, S, device=dev) * 4 + 2, dim=-1).values; vd = d / d.norm(dim=-1, keepdim=True)
+with torch.no_grad():
+    pts = (o[:, None, :] + d[:, None, :] * zv[..., None]).contiguous()
+    us_p = timed(lambda: teacher.query(pts, vd), 2 if quick else 5)
+    us_r = timed(lambda: teacher.query_rays(o, d, zv, vd), 2 if quick else 5)
+    us_m = timed(lambda: (o[:, None, :] + d[:, None, :] * zv[..., None]), reps)
+print(f"teacher query {N} x {S}: on points {us_p / 1e3:.3f} ms (+ {us_m / 1e3:.3f} ms to build them in torch), on rays {us_r / 1e3:.3f} ms = "
+      f"{N * S / us_r:.1f} M points/s = {N * S * 2 * 593408 / us_r / 1e6:.0f} TFLOP/s algorithmic")
+for nfresh, k in ((4096, 819), (81920, 16384)):
+    rays9 = torch.rand(nfresh + k, 9, device=dev); err = torch.rand(nfresh + k, device=dev)
+    pool = torch.zeros(20 * nfresh, 9, device=dev); state = torch.tensor([10 * nfresh], dtype=torch.int32, device=dev)
+    slots = torch.zeros(k, dtype=torch.int32, device=dev); counters = torch.tensor([5, 5], dtype=torch.int64, device=dev)
+    us_d = timed(lambda: ops.pool_draw(pool, state, k, 0, counters, rays9[nfresh:], slots), reps)
+    us_u = timed(lambda: ops.pool_update(rays9, err, nfresh, k, pool, state, slots), reps)
+    print(f"hard-ray pool, {nfresh} fresh rays, {k} in / out: draw {us_d:6.2f} us, update (select + scatter) {us_u:6.2f} us")
