@@ -242,9 +242,19 @@ def run_network(inputs: np.ndarray, viewdirs: np.ndarray, params: list, multires
     return out.reshape(list(inputs.shape[:-1]) + [out.shape[-1]])
 
 
-def raw2outputs(raw: np.ndarray, z_vals: np.ndarray, rays_d: np.ndarray, white_bkgd: bool = False):
-    """raw2outputs :226-295 with raw_noise_std = 0.  Returns rgb_map, disp_map, acc_map, weights, depth_map."""
+def raw_noise_pytest(shape, raw_noise_std: float) -> np.ndarray:
+    """The deterministic density noise of raw2outputs(pytest=True) (:267-270): np.random.seed(0); rand(*shape) * std, as fp32."""
+    np.random.seed(0)
+    return (np.random.rand(*shape) * raw_noise_std).astype(np.float32)
+
+
+def raw2outputs(raw: np.ndarray, z_vals: np.ndarray, rays_d: np.ndarray, white_bkgd: bool = False, noise: np.ndarray | None = None):
+    """raw2outputs :226-295; `noise` [N,S] = the density noise of raw_noise_std > 0 (:262-272, added to raw[..., 3] before the
+    relu), None for raw_noise_std = 0.  Returns rgb_map, disp_map, acc_map, weights, depth_map."""
     dt = raw.dtype.type
+    if noise is not None:
+        raw = raw.copy()
+        raw[..., 3] = raw[..., 3] + noise.astype(raw.dtype)
     dists = z_vals[..., 1:] - z_vals[..., :-1]
     dists = np.concatenate([dists, np.broadcast_to(dt(1e10), dists[..., :1].shape)], -1)       # :249-252
     dists = dists * np.linalg.norm(rays_d[..., None, :], axis=-1).astype(raw.dtype)            # :255-257

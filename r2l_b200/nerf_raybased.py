@@ -517,9 +517,17 @@ def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkgd=False, pytest=F
     """Alpha compositing of the teacher's raw predictions (reference :226-295) in one warp-per-ray kernel.
     Returns rgb_map, disp_map, acc_map, weights, depth_map."""
     if raw_noise_std > 0.:
-        raise NotImplementedError("r2l_b200 raw2outputs: raw_noise_std > 0 is not implemented (the README teacher flow uses 0)")
+        # density noise (:262-272), drawn where the reference draws it: torch's CPU generator, or numpy's seeded generator
+        # under pytest=True; added to the density channel before the kernel's relu
+        if pytest:
+            np.random.seed(0)
+            noise = torch.Tensor(np.random.rand(*list(raw[..., 3].shape)) * raw_noise_std)
+        else:
+            noise = torch.randn(raw[..., 3].shape) * raw_noise_std
+        raw = raw.clone()
+        raw[..., 3] += noise.to(raw.device)
     outs = ops.raw2outputs(raw, z_vals.expand(raw.shape[0], raw.shape[1]), rays_d, white_bkgd)
-    if global_step % 100 == 0:  # the reference's periodic alpha dump (:275-279)
+    if global_step % 100 == 0:  # the reference's periodic alpha dump (:275-279; `raw` carries the noise here, like its alpha)
         dists = torch.cat([z_vals[..., 1:] - z_vals[..., :-1], torch.full_like(z_vals[..., :1], 1e10)], -1)
         alpha = 1. - torch.exp(-torch.relu(raw[..., 3]) * dists * torch.norm(rays_d[..., None, :], dim=-1))
         for i_ray in range(0, alpha.shape[0], 100):

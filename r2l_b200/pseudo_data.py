@@ -36,14 +36,7 @@ def get_rand_pose(rng=None, radius: float = 4.0) -> torch.Tensor:
     return pose_spherical(theta, phi, radius)
 
 
-def get_rays(H: int, W: int, focal: float, c2w: torch.Tensor):
-    """rays_o, rays_d [H,W,3] of utils/run_nerf_raybased_helpers.py:231-257 (trans_origin ''), on c2w's device."""
-    dev = c2w.device
-    i, j = torch.meshgrid(torch.linspace(0, W - 1, W), torch.linspace(0, H - 1, H), indexing="ij")
-    i, j = i.t().to(dev), j.t().to(dev)
-    dirs = torch.stack([(i - W * .5) / focal, -(j - H * .5) / focal, -torch.ones_like(i)], -1)
-    rays_d = torch.sum(dirs.unsqueeze(dim=-2) * c2w[:3, :3], -1)
-    return c2w[:3, -1].expand(rays_d.shape), rays_d
+get_rays = rr.get_rays      # utils/run_nerf_raybased_helpers.py:231-257 (lives with render() since round 2)
 
 
 def render_pseudo_frame(pose, H, W, focal, teacher, teacher_fine, near=2., far=6., N_samples=64, N_importance=128,

@@ -36,6 +36,12 @@ def golden_surface():
 
 
 @pytest.fixture(scope="session")
+def golden_holes():
+    """tests/golden/make_golden_round2.py: raw2outputs with density noise, sample_pdf's pytest hook, ndc_rays - run by the reference."""
+    return dict(np.load(os.path.join(GOLDEN, "holes_seed0.npz"), allow_pickle=False))
+
+
+@pytest.fixture(scope="session")
 def golden_grad_ref():
     """tests/golden/make_golden_round2.py: the reference's own fp32-vs-fp64 gradient errors at 200 / 1000 / 4096 rays."""
     return dict(np.load(os.path.join(GOLDEN, "grad_ref_seed0.npz"), allow_pickle=False))

@@ -522,10 +522,12 @@ def test_sample_pdf_merge_golden_and_properties(golden_teacher):
     assert np.mean(np.abs(zs.cpu().numpy() - ref) > 1e-4) < 0.01
 
 
-@pytest.mark.parametrize("s", [1, 2, 31, 32, 33, 64, 100, 256, 257, 300])
+@pytest.mark.parametrize("s", [2, 31, 32, 33, 64, 100, 256, 257, 300])
 def test_raw2outputs_ragged_sample_counts_vs_oracle(s):
     """Every sample-count class of the compositing kernel (1..8 groups of 32 with all loads in flight; > 256 samples: the
-    one-group-at-a-time kernel), ragged ray counts, against the numpy oracle."""
+    one-group-at-a-time kernel), ragged ray counts, against the numpy oracle.  (One sample per ray is outside the
+    reference's domain: its `expand(dists[..., :1].shape)` of an empty tensor, nerf_raybased.py:250-252, leaves no sample at
+    all and every output is 0; the kernel composites the single sample.)"""
     torch.manual_seed(s)
     n = 1237
     raw = torch.randn(n, s, 4) * 2
@@ -535,6 +537,49 @@ def test_raw2outputs_ragged_sample_counts_vs_oracle(s):
     ref = orc.raw2outputs(raw.numpy(), z.numpy(), d.numpy(), False)
     for got, want, tol in zip(outs, ref, (3e-5, 1e-3, 3e-5, 3e-6, 3e-5)):
         np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-4, atol=tol)
+
+
+def test_raw2outputs_density_noise_and_pytest_hooks(golden_holes):
+    """The determinism hooks of the teacher flow against reference-run fixtures: raw2outputs(raw_noise_std > 0) with
+    pytest=True (numpy noise, :267-270) and with torch.randn's draw after a seed (:264), sample_pdf(pytest=True)
+    (utils/run_nerf_raybased_helpers.py:299-307)."""
+    from r2l_b200 import render as rr
+    h = golden_holes
+    raw, z, d = (torch.from_numpy(h[k]).to(DEV) for k in ("raw", "z_vals", "rays_d"))
+    torch.manual_seed(33)
+    cases = (("noise_seed33", dict(raw_noise_std=0.7)), ("noise_pytest", dict(raw_noise_std=1.0, pytest=True)),
+             ("noise_pytest_white", dict(raw_noise_std=0.5, white_bkgd=True, pytest=True)))
+    for tag, kw in cases:
+        outs = nb.raw2outputs(raw, z, d, **kw)
+        for got, name, atol in zip(outs, ("rgb", "disp", "acc", "weights", "depth"), (3e-6, 1e-6, 3e-6, 3e-7, 3e-6)):
+            np.testing.assert_allclose(got.cpu().numpy(), h[f"r2o_{tag}_{name}"], rtol=3e-4 if name == "disp" else 2e-5, atol=atol, equal_nan=True)
+    bins, w = torch.from_numpy(h["pdf_bins"]).to(DEV), torch.from_numpy(h["pdf_weights"]).to(DEV)
+    np.testing.assert_allclose(rr.sample_pdf(bins, w, 24, det=False, pytest=True).cpu().numpy(), h["pdf_pytest_random"], rtol=1e-5, atol=1.5e-4)
+    np.testing.assert_allclose(rr.sample_pdf(bins, w, 24, det=True, pytest=True).cpu().numpy(), h["pdf_pytest_det"], rtol=1e-5, atol=1.5e-4)
+
+
+def test_render_from_a_pose_equals_render_from_its_rays(teacher):
+    """render(c2w=...) (utils/create_data.py:133-135: get_rays inside) against render(rays=get_rays(...)), and the NDC branch
+    (:152-154) against explicitly warped rays; pytest=True makes perturb > 0 reproducible (:473-476)."""
+    from r2l_b200 import render as rr
+    embed_fn, _ = nb.get_embedder(10, 0)
+    embeddirs_fn, _ = nb.get_embedder(4, 0)
+    query = lambda inputs, viewdirs, network_fn: nb.run_network(inputs, viewdirs, network_fn, embed_fn, embeddirs_fn, 1024 * 64)
+    kw = dict(network_fn=teacher, network_query_fn=query, N_samples=64, N_importance=32, white_bkgd=True, perturb=1., pytest=True)
+    H, W, focal = 9, 7, 11.0
+    c2w = torch.tensor([[-0.9, 0.2, -0.3, -1.3], [-0.4, -0.5, 0.7, 3.0], [0.0, 0.8, 0.5, 2.2]], device=DEV)
+    a = rr.render(H, W, focal, chunk=40, c2w=c2w, ndc=False, near=2., far=6., use_viewdirs=True, **kw)
+    rays = rr.get_rays(H, W, focal, c2w)
+    b = rr.render(H, W, focal, chunk=40, rays=rays, ndc=False, near=2., far=6., use_viewdirs=True, **kw)
+    assert a[0].shape == (H, W, 3) and torch.equal(a[0], b[0]) and torch.equal(a[2], b[2])
+    n1 = rr.render(H, W, focal, chunk=64, c2w=c2w, ndc=True, near=0., far=1., use_viewdirs=True, **kw)
+    warped = rr.ndc_rays(H, W, focal, 1., *rays)
+    vd = rays[1] / rays[1].norm(dim=-1, keepdim=True)
+    # the same thing by hand: warped rays, view directions of the unwarped ones
+    batch = torch.cat([warped[0].reshape(-1, 3), warped[1].reshape(-1, 3), torch.zeros(H * W, 1, device=DEV), torch.ones(H * W, 1, device=DEV),
+                       vd.reshape(-1, 3)], -1)
+    n2 = rr.batchify_rays(batch, 64, **kw)
+    assert torch.equal(n1[0].reshape(-1, 3), n2["rgb_map"]) and bool(torch.isfinite(n1[0]).all())
 
 
 def test_teacher_query_on_rays_equals_query_on_points(teacher):

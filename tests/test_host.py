@@ -266,3 +266,15 @@ def test_torch_reference_port_is_pinned_to_the_reference(golden_r2l, flat_seed0)
     ((m64(x.double()) - torch.from_numpy(g["target"]).double()) ** 2).mean().backward()
     sub = m64.flat_grads().numpy()[g["grad_idx"]]
     assert np.linalg.norm(sub - g["grad_f64_sub"]) <= 1e-12 * np.linalg.norm(g["grad_f64_sub"])
+
+
+def test_ndc_rays_and_pose_rays_match_the_reference(golden_holes):
+    """render(c2w=..., ndc=True) builds its rays with get_rays / ndc_rays (utils/run_nerf_raybased_helpers.py:231-280): host glue
+    of the teacher flow, bit-compared with the reference's own outputs."""
+    from r2l_b200 import render as rr
+    h = golden_holes
+    H, W, focal = int(h["ndc_H"]), int(h["ndc_W"]), float(h["ndc_focal"])
+    ro, rd = rr.get_rays(H, W, focal, torch.from_numpy(h["ndc_c2w"]))
+    assert np.array_equal(ro.numpy(), h["ndc_in_o"]) and np.array_equal(rd.numpy(), h["ndc_in_d"])
+    no, nd = rr.ndc_rays(H, W, focal, 1., ro, rd)
+    assert np.array_equal(no.numpy(), h["ndc_rays_o"]) and np.array_equal(nd.numpy(), h["ndc_rays_d"])

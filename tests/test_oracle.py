@@ -126,6 +126,32 @@ def test_raw2outputs(golden_teacher):
     assert np.isnan(t["r2o_synth_disp"][0])  # the transparent ray: 0/0 propagates through torch.max (Appendix A)
 
 
+def test_raw2outputs_with_density_noise(golden_holes):
+    """raw_noise_std > 0 (:262-272): the pytest hook's numpy noise, and torch.randn's first draw after a seed."""
+    import torch
+    h = golden_holes
+    n, s = h["z_vals"].shape
+    torch.manual_seed(33)
+    randn = (torch.randn(n, s) * 0.7).numpy()
+    for tag, wb, noise in (("noise_pytest", False, orc.raw_noise_pytest((n, s), 1.0)), ("noise_pytest_white", True, orc.raw_noise_pytest((n, s), 0.5)),
+                           ("noise_seed33", False, randn)):
+        outs = orc.raw2outputs(h["raw"], h["z_vals"], h["rays_d"], wb, noise=noise)
+        for got, name, atol in zip(outs, ("rgb", "disp", "acc", "weights", "depth"), (3e-6, 1e-6, 3e-6, 3e-7, 3e-6)):
+            np.testing.assert_allclose(got, h[f"r2o_{tag}_{name}"], rtol=3e-4 if name == "disp" else 2e-5, atol=atol, equal_nan=True)
+    plain = orc.raw2outputs(h["raw"], h["z_vals"], h["rays_d"], False)
+    assert np.abs(plain[3] - h["r2o_noise_pytest_weights"]).max() > 1e-2        # the noise does change the result
+
+
+def test_sample_pdf_pytest_hook(golden_holes):
+    """sample_pdf(pytest=True) (utils/run_nerf_raybased_helpers.py:299-307): uniforms from numpy's generator seeded with 0."""
+    h = golden_holes
+    n = h["pdf_bins"].shape[0]
+    np.random.seed(0)
+    u = np.random.rand(n, 24).astype(np.float32)
+    np.testing.assert_allclose(orc.sample_pdf(h["pdf_bins"], h["pdf_weights"], 24, u), h["pdf_pytest_random"], rtol=1e-5, atol=1.5e-4)
+    np.testing.assert_allclose(orc.sample_pdf(h["pdf_bins"], h["pdf_weights"], 24), h["pdf_pytest_det"], rtol=1e-5, atol=1.5e-4)
+
+
 def test_sample_pdf(golden_teacher):
     t = golden_teacher
     zs = orc.sample_pdf(t["pdf_bins"], t["pdf_weights"], 32)
