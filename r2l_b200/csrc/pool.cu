@@ -121,14 +121,33 @@ __global__ void __launch_bounds__(kPoolThreads, 1) r2l_pool_update_kernel(const 
       if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
     }
     __syncthreads();
-    if (tid == 0) {
-      int remaining = s_remaining, b = 255;
-      for (; b > 0; --b) {                 // walk down from the largest digit
-        if (hist[b] >= remaining) break;
-        remaining -= hist[b];
+    if (tid < 32) {
+      // warp 0 finds the digit whose bin holds the remaining-th largest key: lane l owns bins 8l .. 8l+7, a suffix sum over
+      // the lanes gives the keys in higher bins (a serial walk over 256 shared-memory words by one thread cost 4 us per pass)
+      int c[8], mine = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { c[j] = hist[8 * tid + j]; mine += c[j]; }
+      int incl = mine;                     // keys in the bins of lanes >= this one
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_down_sync(0xffffffffu, incl, d);
+        if (tid + d < 32) incl += o;
       }
-      s_remaining = remaining;             // how many keys with this digit (and the prefix so far) are still to be taken
-      s_prefix = prefix | ((uint32_t)b << shift);
+      const int above = incl - mine, remaining = s_remaining;
+      __syncwarp();
+      if (above < remaining && remaining <= above + mine) {       // exactly one lane (k <= n keeps remaining <= matching keys)
+        int rem = remaining - above, b = 0;
+        bool found = false;
+#pragma unroll
+        for (int j = 7; j >= 1; --j) {     // walk down from the lane's largest digit
+          if (!found) {
+            if (c[j] >= rem) { b = j; found = true; }
+            else rem -= c[j];
+          }
+        }
+        s_remaining = rem;                 // how many keys with this digit (and the prefix so far) are still to be taken
+        s_prefix = prefix | ((uint32_t)(8 * tid + b) << shift);
+      }
     }
     mask |= 255u << shift;
     __syncthreads();

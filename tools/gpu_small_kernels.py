@@ -25,8 +25,13 @@ print(f"adam_step_dev       {timed(lambda: ops.adam_step_dev(flat, g, m, v, 0.9,
 print(f"adam + pack         {timed(lambda: (ops.adam_step_dev(flat, g, m, v, 0.9, 0.999, 1e-8, hd), ops.pack_weights(flat, out=packed))):7.2f} us")
 
 # ---- teacher-side kernels (config 4 sizes: a 32,768-ray chunk, 64 coarse / 192 fine samples) and the hard-ray pool ----
-quick = len(sys.argv) > 1 and sys.argv[1] == "ncu"        # under ncu: each kernel a couple of times, no timing loops
-reps = 2 if quick else 20
+quick = len(sys.argv) > 1 and sys.argv[1] == "ncu"        # under ncu: each kernel ONCE (the printed times mean nothing then)
+reps = 1 if quick else 20
+if quick:
+    def timed(fn, reps=1):
+        fn()
+        torch.cuda.synchronize()
+        return 1.0
 from r2l_b200 import nerf_raybased as nb
 nb.device = dev
 torch.manual_seed(0)
