@@ -105,7 +105,7 @@ def test_teacher_embed_and_mlp(golden_teacher):
     t = golden_teacher
     np.testing.assert_allclose(orc.teacher_embed(t["pts"].reshape(-1, 3)[:8], 10), t["embed_pts_first8"], rtol=0, atol=5e-7)
     import torch
-    from r2l_b200.teacher import init_teacher_params
+    from oracle.torch_reference import init_teacher_params
     params = [p.numpy() for p in init_teacher_params(0)]
     sums = [float(p.astype(np.float64).sum()) for p in params]
     # state_dict order of the reference: pts_linears, views_linears, feature, alpha, rgb
