@@ -83,6 +83,11 @@ __global__ void __launch_bounds__(256) r2l_raw2outputs_kernel(const float* __res
 // one), the depth of the next sample comes from the neighbouring lane instead of a second load, streaming cache hints on
 // data that is read / written exactly once.  (The one-group-at-a-time kernel above measured 24 % of the HBM peak at
 // 32,768 x 192 - profiles/r1_summary.md section 5: a dependent warp scan sat between consecutive loads.)
+// rgb = sigmoid(raw[..., :3]) (:259) inside the weighted sum: ex2.approx + rcp.approx (each <= 2 ulp; the three channels of
+// 192 samples were 45 % of the kernel's instructions with IEEE expf and division, and the kernel is issue-bound).  The
+// density path (alpha = 1 - exp(-sigma dist), :246) keeps the accurate expf: 1 - exp(-x) amplifies its error for small x.
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+
 template <int G>
 __global__ void __launch_bounds__(256) r2l_raw2outputs_unrolled_kernel(const float* __restrict__ raw, const float* __restrict__ z_vals,
                                                                        const float* __restrict__ rays_d, int64_t n_rays, int n_samples,
@@ -127,9 +132,9 @@ __global__ void __launch_bounds__(256) r2l_raw2outputs_unrolled_kernel(const flo
     carry *= __shfl_sync(0xffffffffu, incl, 31);
     if (in) {
       __stcs(weights + ray * n_samples + i, w);
-      sr += w / (1.f + expf(-r4[g].x));                                          // sigmoid :259
-      sg += w / (1.f + expf(-r4[g].y));
-      sb += w / (1.f + expf(-r4[g].z));
+      sr += w * fast_sigmoid(r4[g].x);                                           // sigmoid :259
+      sg += w * fast_sigmoid(r4[g].y);
+      sb += w * fast_sigmoid(r4[g].z);
       sdepth += w * z[g];
       sacc += w;
     }

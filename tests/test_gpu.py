@@ -122,6 +122,14 @@ def test_render_poses_module_surface_and_full_frame(packed, flat_seed0):
             assert float(((frames[k] - ref).abs() / ref).max()) < 2e-4
     one = model.render_poses(poses[1], ps, focal)
     assert torch.equal(one, frames[1])
+    # 2,000 random pixels of the 400x400 frames against the numpy oracle's restatement of sample_test -> embedder -> network
+    rng = np.random.RandomState(0)
+    dirs, z = orc.sampler_dirs(400, 400, focal), orc.sampler_z_vals(2.0, 6.0)
+    for k in range(2):
+        pix = rng.choice(160000, size=1000, replace=False)
+        pts = orc.sample_test(dirs, poses[k].cpu().numpy(), z)[pix]
+        want = orc.r2l_forward(flat_seed0, orc.positional_embed(pts))
+        assert relerr(frames[k].reshape(-1, 3)[torch.from_numpy(pix).to(DEV)].cpu().numpy(), want) < FWD_TOL
     u8 = model.render_poses(poses, ps, focal, as_uint8=True)
     assert u8.dtype == torch.uint8 and np.array_equal(u8.cpu().numpy(), orc.to8b(frames.cpu().numpy()))
 
