@@ -528,6 +528,16 @@ def test_sample_pdf_merge_golden_and_properties(golden_teacher):
     assert float(zs.min()) >= float(zz.min()) and float(zs.max()) <= float(zz.max())
     ref = orc.sample_pdf((.5 * (zz[:, 1:] + zz[:, :-1])).cpu().numpy(), ww[:, 1:-1].cpu().numpy(), m, u.cpu().numpy())
     assert np.mean(np.abs(zs.cpu().numpy() - ref) > 1e-4) < 0.01
+    # every path of the merge (ranks by binary search where a list ascends, by comparison where it does not), ties included:
+    # depths ascending / not, samples ascending (sorted uniforms) / not, and a ray whose depths are all equal
+    for asc_z in (True, False):
+        for asc_u in (True, False):
+            z2 = zz.clone() if asc_z else zz[:, torch.randperm(s, device=DEV)].contiguous()
+            z2[5] = 3.0
+            z2[6, 10:20] = z2[6, 10:11]
+            u2 = torch.sort(u, -1).values if asc_u else u
+            zs2, zm2 = ops.sample_pdf_merge(z2, ww, m, u2)
+            assert torch.equal(zm2, torch.sort(torch.cat([z2, zs2], -1), -1).values), (asc_z, asc_u)
 
 
 @pytest.mark.parametrize("s", [2, 31, 32, 33, 64, 100, 256, 257, 300])
