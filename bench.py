@@ -231,6 +231,33 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def cpu_baseline_leg(reps_cpu=20):
+    """The `cpu_baseline` object of our arm's line: the reference arm itself (`bench.py --impl reference`), run in a FRESH
+    process and parsed - so both numbers come from one code path in one environment.  (Measured on the pool's boxes: the same
+    20 CPU steps inside this process, after the CUDA context exists, ran 4.6x slower than in a fresh process - 8.1 k against
+    37 k rays/s on the same 16-core host; an in-process number would understate the baseline.)  Falls back to the
+    in-process measurement, and says so, if the child cannot be run."""
+    threads = cpu_threads()
+    try:
+        env = dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0")
+        res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(reps_cpu), "--warmup", "1"],
+                             capture_output=True, text=True, timeout=900, env=env)
+        lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+        cpu = json.loads(lines[-1])["cpu_baseline"]
+        cpu["sample"] += "; measured by `bench.py --impl reference` in a fresh process"
+        return cpu
+    except Exception as e:   # noqa: BLE001 - the baseline is a report, never a reason to lose the bench line
+        stepc = cpu_reference_step_fn(BATCH, threads)
+        stepc()
+        t0 = time.perf_counter()
+        for _ in range(reps_cpu):
+            stepc()
+        dt = time.perf_counter() - t0
+        return {"value": BATCH * reps_cpu / dt, "unit": "rays/s", "cores": threads, "kind": "port",
+                "sample": f"{reps_cpu} full train steps on the 4096-ray batch; stock PyTorch CPU ops (oracle/torch_reference.py), {threads} threads on this "
+                          f"{os.cpu_count()}-core host; measured INSIDE the GPU arm's process (fresh-process run failed: {type(e).__name__})"}
+
+
 def gpu_reference_step_ms(dev, d_ro, d_rd, d_tg, z_vals, reps=10):
     """The reference's network and train step as stock PyTorch on the GPU ("the meaningful beat-this
     number"; the reference's own harness is main.py:1124-1133): fp32 (TF32 off) and TF32 matmuls, CUDA events."""
@@ -421,17 +448,7 @@ def run_ours(args):
 
     line = None
     if rank == 0:
-        cpu = None
-        if world == 1:
-            reps_cpu, threads = 20, cpu_threads()
-            stepc = cpu_reference_step_fn(BATCH, threads)
-            stepc()
-            t0 = time.perf_counter()
-            for _ in range(reps_cpu):
-                stepc()
-            dt = time.perf_counter() - t0
-            cpu = {"value": BATCH * reps_cpu / dt, "unit": "rays/s", "cores": threads, "kind": "port",
-                   "sample": f"{reps_cpu} full train steps on the 4096-ray batch; stock PyTorch CPU ops (oracle/torch_reference.py), {threads} threads on this {os.cpu_count()}-core host"}
+        cpu = cpu_baseline_leg() if world == 1 else None
         cfg = base_config(world)
         cfg["l2"] = "flushed: a 256 MiB buffer is written between timed iterations (untimed)"
         timing = {"step": "R2LTrainer.step_rays9 on a resident [N,9] batch: schedule scalars + forward_train + mse loss/grad + backward(chain, dW, tail) + allreduce(N>1) + Adam + pack_weights"

@@ -192,6 +192,18 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert other.returncode == 0 and other.stdout.strip() == ""
 
 
+def test_bench_cpu_baseline_is_the_reference_arm_in_a_fresh_process():
+    """Our arm's `cpu_baseline` object = the reference arm's own measurement (same code path, fresh process), not a second
+    implementation timed inside a process that holds a CUDA context."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_module_cpu", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    cpu = bench.cpu_baseline_leg(1)
+    assert cpu["kind"] == "port" and cpu["unit"] == "rays/s" and cpu["value"] > 0 and cpu["cores"] == bench.cpu_threads()
+    assert "fresh process" in cpu["sample"] and "4096-ray batch" in cpu["sample"]
+
+
 def test_bench_synthetic_rays_follow_the_reference_camera_model():
     """bench.py's synthetic batch = a seeded subset of the pixels of pose_spherical(theta, phi, 4) seen through get_rays at
     400x400, focal 555.56, checked against the oracle's restatement of those reference functions."""
