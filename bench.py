@@ -241,7 +241,7 @@ def cpu_baseline_leg(reps_cpu=20):
     try:
         env = dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0")
         res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(reps_cpu), "--warmup", "1"],
-                             capture_output=True, text=True, timeout=900, env=env)
+                             capture_output=True, text=True, timeout=300, env=env)
         lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
         cpu = json.loads(lines[-1])["cpu_baseline"]
         cpu["sample"] += "; measured by `bench.py --impl reference` in a fresh process"
