@@ -187,10 +187,48 @@ def cpu_reference_step_fn(n_rays, threads=None):
     return step
 
 
+def cgroup_cpu_limit():
+    """CPUs this process may actually use per scheduling period: the cgroup CFS quota (v2 cpu.max, v1 cpu.cfs_quota_us /
+    cpu.cfs_period_us), or None when there is no quota.  os.cpu_count() reports the host's cores even when the container is
+    limited to a few of them; running one OpenMP thread per host core under such a quota gets every thread throttled."""
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()[:2]
+        if quota != "max":
+            return float(quota) / float(period)
+        return None
+    except (OSError, ValueError):
+        pass
+    try:
+        with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f:
+            quota = float(f.read())
+        with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+            period = float(f.read())
+        return quota / period if quota > 0 else None
+    except (OSError, ValueError):
+        return None
+
+
 def cpu_threads():
-    """Thread policy of the CPU arms, fixed: every host core torch can use, capped at 64 (above that the 256-wide GEMMs
-    of this network only get slower on the hosts of this pool)."""
-    return max(1, min(os.cpu_count() or 1, 64))
+    """Thread policy of the CPU arms, fixed: every CPU this process may use - the smaller of the cores in its affinity mask
+    and its cgroup CPU quota - capped at 64 (above that the 256-wide GEMMs of this network only get slower on the hosts of
+    this pool).  R2L_CPU_THREADS overrides it for experiments."""
+    if os.environ.get("R2L_CPU_THREADS"):
+        return max(1, int(os.environ["R2L_CPU_THREADS"]))
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        cores = os.cpu_count() or 1
+    limit = cgroup_cpu_limit()
+    if limit is not None:
+        cores = min(cores, max(1, int(limit)))
+    return max(1, min(cores, 64))
+
+
+def cpu_host_note():
+    """'N-core host' text of the baseline's `sample`, with the cgroup quota when there is one."""
+    limit = cgroup_cpu_limit()
+    return f"{os.cpu_count()}-core host" + (f" (cgroup CPU quota {limit:g})" if limit is not None else "")
 
 
 def base_config(world):
@@ -226,7 +264,7 @@ def run_reference(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "reference_path": ref_path,
             "cpu_baseline": {"value": rays_s, "unit": "rays/s", "cores": threads, "kind": "port",
                              "sample": f"{args.steps} full train steps (fwd + img2mse + bwd + Adam) on the 4096-ray batch, torch {torch.__version__} CPU, "
-                                       f"{threads} threads on this {os.cpu_count()}-core host"},
+                                       f"{threads} threads on this {cpu_host_note()}"},
             "e2e": {"value": rays_s, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -255,7 +293,7 @@ def cpu_baseline_leg(reps_cpu=20):
         dt = time.perf_counter() - t0
         return {"value": BATCH * reps_cpu / dt, "unit": "rays/s", "cores": threads, "kind": "port",
                 "sample": f"{reps_cpu} full train steps on the 4096-ray batch; stock PyTorch CPU ops (oracle/torch_reference.py), {threads} threads on this "
-                          f"{os.cpu_count()}-core host; measured INSIDE the GPU arm's process (fresh-process run failed: {type(e).__name__})"}
+                          f"{cpu_host_note()}; measured INSIDE the GPU arm's process (fresh-process run failed: {type(e).__name__})"}
 
 
 def gpu_reference_step_ms(dev, d_ro, d_rd, d_tg, z_vals, reps=10):
