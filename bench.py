@@ -32,7 +32,17 @@ FWD_FLOP_PER_RAY = 11_789_824          # 5,894,912 MAC x
 BWD_FLOP_PER_RAY = 23_063_552
 METRIC = "rays/sec (W256D88 ResMLP fwd+bwd, batch 4096)"
 WORKLOAD = ("lego_noview W256D88 ResMLP train step (fwd+bwd+Adam) on 4096 synthetic lego-pose rays per GPU, "
-            "random-init weights (seed 0), perturb=0")
+            "random-init weights (seed 0), perturb=0, README schedule (lrate 5e-4, lrate_decay 500, warmup_lr 0.0001,200)")
+# The README's R2L schedule (reference README.md:97,102: --warmup_lr 0.0001,200; main.py:1181-1195), in EVERY arm.  With a constant 5e-4 from random
+# initialisation the network saturates in two steps (loss 0.096 -> 0.337, the reference's own behaviour without --warmup_lr);
+# its gradients then decay through the fp32 denormal range, and a CPU step - timed at 0.37 s - takes 2.5-12 s for a few
+# steps: the CPU arm's number depended on how many steps were timed (40 k rays/s over 12 steps, 8 k over 20).
+LRATE, LRATE_DECAY, WARMUP_LR = 5e-4, 500, "0.0001,200"
+
+
+def lr_schedule(step):
+    from r2l_b200.trainer import lr_at
+    return lr_at(step, LRATE, LRATE_DECAY, WARMUP_LR)
 
 
 FWD_ALGO_BYTES = 23_668_748 + BATCH * 36   # parameters read once + 24 B in, 12 B out per ray
@@ -176,9 +186,13 @@ def cpu_reference_step_fn(n_rays, threads=None):
     ro, rd, tg = synthetic_rays(n_rays, 0)
     ro, rd, tg = torch.from_numpy(ro), torch.from_numpy(rd), torch.from_numpy(tg)
     z = torch.from_numpy(orc.sampler_z_vals(2.0, 6.0))
-    opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+    opt = torch.optim.Adam(model.parameters(), lr=LRATE)
+    it = [0]
 
     def step():
+        it[0] += 1
+        for group in opt.param_groups:                      # main.py:1181-1195
+            group["lr"] = lr_schedule(it[0])
         opt.zero_grad()
         loss = ((model(embed(sample(ro, rd, z))) - tg) ** 2).mean()
         loss.backward()
@@ -272,8 +286,7 @@ def run_reference(args):
 def cpu_baseline_leg(reps_cpu=20):
     """The `cpu_baseline` object of our arm's line: the reference arm itself (`bench.py --impl reference`), run in a FRESH
     process and parsed - so both numbers come from one code path in one environment.  (Measured on the pool's boxes: the same
-    20 CPU steps inside this process, after the CUDA context exists, ran 4.6x slower than in a fresh process - 8.1 k against
-    37 k rays/s on the same 16-core host; an in-process number would understate the baseline.)  Falls back to the
+    CPU steps would run as fast inside this process; the point is one code path and one thread policy.)  Falls back to the
     in-process measurement, and says so, if the child cannot be run."""
     threads = cpu_threads()
     try:
@@ -309,9 +322,13 @@ def gpu_reference_step_ms(dev, d_ro, d_rd, d_tg, z_vals, reps=10):
         torch.backends.cuda.matmul.allow_tf32 = mode == "tf32"
         torch.backends.cudnn.allow_tf32 = mode == "tf32"
         model = RefR2L().load_flat(init_flat_params(0)).to(dev)
-        opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+        opt = torch.optim.Adam(model.parameters(), lr=LRATE)
+        it = [0]
 
         def step():
+            it[0] += 1
+            for group in opt.param_groups:                  # main.py:1181-1195
+                group["lr"] = lr_schedule(it[0])
             opt.zero_grad(set_to_none=True)
             loss = ((model(embed(sample(d_ro, d_rd, zt))) - d_tg) ** 2).mean()
             loss.backward()
@@ -366,7 +383,7 @@ def run_ours(args):
     with torch.no_grad():
         model.flat.copy_(init_flat_params(0).to(dev))
     ps = PointSampler(400, 400, 555.5555155968841, 16, 2.0, 6.0)
-    trainer = R2LTrainer(model, ps, lrate=5e-4, lrate_decay=500)     # CUDA graph on one GPU, eager + all-reduce on N > 1
+    trainer = R2LTrainer(model, ps, lrate=LRATE, lrate_decay=LRATE_DECAY, warmup_lr=WARMUP_LR)     # CUDA graph on one GPU, eager + all-reduce on N > 1
     packed = trainer.packed
     n_global = BATCH * world
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
