@@ -2,7 +2,7 @@
 """bench.py — R2L hot-path benchmark (contract: see the task statement / DESIGN.md "Measurement").
 
 Metric (BASELINE.json): rays/sec of the W256/D88 ResMLP light-field network, forward + backward, batch 4096
-synthetic rays per GPU, fp32-parity arithmetic (bf16x3 split on tcgen05).  One "step" = one full training pass of
+synthetic rays per GPU, fp32-parity arithmetic (fp16 hi/lo x3 split on tcgen05).  One "step" = one full training pass of
 the hot path over one batch: weight re-pack, fused forward (sampling + positional encoding + 88 layers), MSE
 gradient, fused backward (chain + weight gradients), gradient all-reduce when N > 1, Adam update.
 

@@ -34,7 +34,7 @@ size_t r2l_packed_bytes(void);
 size_t r2l_fwd_workspace_bytes(int64_t n_rays);
 
 /* params[R2L_NUM_PARAMS] fp32 in state_dict order (head.0.weight, head.0.bias, body.k.body.{0,2}.{weight,bias},
- * tail.0.weight, tail.0.bias; NeRF_v3_2.__init__, nerf_raybased.py:483-537)  ->  bf16 hi/lo tensor-core operand
+ * tail.0.weight, tail.0.bias; NeRF_v3_2.__init__, nerf_raybased.py:483-537)  ->  fp16 hi/lo tensor-core operand
  * images + fp32 bias tables in `packed`.  Call again after every parameter update. */
 int r2l_pack_weights(const float* params, void* packed, void* stream);
 
@@ -59,8 +59,8 @@ int r2l_render_poses(const float* c2w, int64_t n_poses, int height, int width, f
 /* ---- training: fused forward that keeps what the backward needs, and the fused backward ----
  * Replaces loss.backward() through NeRF_v3_2 (main.py:1404; autograd of nerf_raybased.py:539-544).
  *   zf        : [N,256] fp32 out, z_43 + h (input of the tail Linear)
- *   fwd_saved : r2l_train_fwd_saved_bytes(n) bytes; the bf16 hi/lo input operand of every Linear
- *   bwd_saved : r2l_train_bwd_saved_bytes(n) bytes; the bf16 hi/lo output-gradient operand of every Linear
+ *   fwd_saved : r2l_train_fwd_saved_bytes(n) bytes; the fp16 hi/lo input operand of every Linear
+ *   bwd_saved : r2l_train_bwd_saved_bytes(n) bytes; the fp16 hi/lo output-gradient operand of every Linear
  *   grads     : [R2L_NUM_PARAMS] fp32 in state_dict order, OVERWRITTEN with dL/dparams given grad_rgb = dL/drgb
  * `workspace`: r2l_bwd_workspace_bytes(n) bytes.  r2l_backward enqueues three kernels on `stream`; when the chain
  * grid leaves >= 90 SMs idle the weight-gradient kernel runs concurrently on an internal side stream (joined back

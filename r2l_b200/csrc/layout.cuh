@@ -43,13 +43,13 @@ constexpr float kInvWeightScale = 1.f / kWeightScale;
 // ---- tiles ----
 constexpr int kTileM = 128;    // rays per CTA tile = UMMA M = TMEM lanes
 constexpr int kChunkK = 64;    // K elements per 128-byte swizzled row
-constexpr int kPlaneBytes = kTileM * 128;        // one bf16 plane (hi or lo) of a [128 x 64] A chunk
+constexpr int kPlaneBytes = kTileM * 128;        // one fp16 plane (hi or lo) of a [128 x 64] A chunk
 constexpr int kAChunkBytes = 2 * kPlaneBytes;    // hi + lo
 constexpr int kAChunks = 4;                      // 256 / 64
 constexpr int kABytes = kAChunks * kAChunkBytes; // 131072: whole [128 x 256] A operand, hi+lo
-constexpr int kWImageBytes = kWidth * 128;       // 32768: [256 n x 64 k] bf16, one plane
+constexpr int kWImageBytes = kWidth * 128;       // 32768: [256 n x 64 k] fp16, one plane
 
-// ---- packed weight stream (bf16 planes, UMMA K-major SWIZZLE_128B images of 32 KiB) ----
+// ---- packed weight stream (fp16 planes, UMMA K-major SWIZZLE_128B images of 32 KiB) ----
 // image order = consumption order of the forward chain kernel:
 //   head (fused-PE feature order) : 16 chunks x {hi, lo}            images [0, 32)
 //   head (natural feature order)  : 16 chunks x {hi, lo}            images [32, 64)
@@ -87,7 +87,7 @@ __host__ __device__ inline int fused_slot_to_feature(int s, int slot) {
   return -1;
 }
 
-// byte offset of element (row, k) inside one [rows x 64] bf16 K-major SWIZZLE_128B plane
+// byte offset of element (row, k) inside one [rows x 64] 16-bit K-major SWIZZLE_128B plane
 __host__ __device__ inline uint32_t sw128_offset(uint32_t row, uint32_t k) {
   return row * 128u + ((((k >> 3) ^ (row & 7u)) << 4) | ((k & 7u) << 1));
 }

@@ -248,7 +248,7 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols
 //   bits [61,64)  layout type: 2 = SWIZZLE_128B
 // K-major operand  (rows = M/N index, 128 B of K per row, 8-row atoms of 1024 B):
 //     SBO = byte distance between 8-row atoms (1024 when rows are dense), LBO unused.
-// MN-major operand (rows = K index, 128 B (64 bf16) of M/N per row, 8-row atoms of 1024 B):
+// MN-major operand (rows = K index, 128 B (64 fp16) of M/N per row, 8-row atoms of 1024 B):
 //     SBO = byte distance between 8-k atoms, LBO = byte distance between 64-element M/N groups.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes,
                                                     uint32_t sbo_bytes) {
@@ -318,7 +318,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
-// 8 columns (one 16-byte operand unit of a row after the bf16 split)
+// 8 columns (one 16-byte operand unit of a row after the fp16 split)
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])

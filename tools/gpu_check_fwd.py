@@ -20,7 +20,7 @@ print("pack ok", packed.numel(), flush=True)
 
 # ---- pack check: decode image of body layer 3 chunk 1 and compare hi+lo with W ----
 P = packed.cpu().numpy()
-def decode_image(img_bytes):  # [256 n][64 k] from swizzled bf16 plane
+def decode_image(img_bytes):  # [256 n][64 k] from a swizzled 16-bit plane
     raw = np.frombuffer(img_bytes, dtype=np.uint16).reshape(256, 8, 8)  # row, 16B-unit position, elem
     out = np.zeros((256, 64), np.float32)
     for n in range(256):
