@@ -104,3 +104,26 @@ def test_two_rank_gradient_allreduce_matches_full_batch(tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), n, str(tmp_path)), nprocs=2, join=True)
     err = np.load(tmp_path / "err.npy")
     assert err[0] < 1e-12 and err[1] < 1e-12
+
+
+def _gather_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    for n in (7, 3, 2, 12):                     # ragged (3,2,2), one row each, an EMPTY shard on the last rank, even
+        full = torch.arange(n * 3, dtype=torch.float32).reshape(n, 3) * 0.5
+        lo, hi = parallel.shard_range(n, rank, world)
+        got = parallel.gather_rows(full[lo:hi].clone(), n)
+        assert torch.equal(got, full), (n, rank)
+    try:
+        parallel.gather_rows(torch.zeros(5, 3), 7)      # 5 rows is nobody's shard of 7 rows over 3 ranks
+        raise AssertionError("gather_rows accepted a wrong shard size")
+    except ValueError:
+        pass
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_rows_ragged_and_empty_shards_three_ranks():
+    """gather_rows (the only communication of sharded rendering): shard sizes that differ by one, a rank with no rows at all,
+    and a wrong local size is refused on every rank before any collective is entered."""
+    mp.spawn(_gather_worker, args=(3, _free_port()), nprocs=3, join=True)

@@ -290,3 +290,23 @@ def test_ndc_rays_and_pose_rays_match_the_reference(golden_holes):
     assert np.array_equal(ro.numpy(), h["ndc_in_o"]) and np.array_equal(rd.numpy(), h["ndc_in_d"])
     no, nd = rr.ndc_rays(H, W, focal, 1., ro, rd)
     assert np.array_equal(no.numpy(), h["ndc_rays_o"]) and np.array_equal(nd.numpy(), h["ndc_rays_d"])
+
+
+def test_bench_cpu_thread_policy(monkeypatch):
+    """bench.py's CPU arms use the CPUs the process may really use (affinity mask, cgroup quota), never more than 64, and an
+    explicit override for experiments."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_module_threads", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    monkeypatch.delenv("R2L_CPU_THREADS", raising=False)
+    n = bench.cpu_threads()
+    assert 1 <= n <= min(64, os.cpu_count())
+    monkeypatch.setattr(bench, "cgroup_cpu_limit", lambda: 2.5)
+    assert bench.cpu_threads() == min(2, n) and "cgroup CPU quota 2.5" in bench.cpu_host_note()
+    monkeypatch.setattr(bench, "cgroup_cpu_limit", lambda: None)
+    assert bench.cpu_threads() == n and "quota" not in bench.cpu_host_note()
+    monkeypatch.setenv("R2L_CPU_THREADS", "3")
+    assert bench.cpu_threads() == 3
+    # the schedule every arm steps with is the README one (warm-up from 1e-4 over 200 iterations, main.py:1181-1195)
+    assert bench.lr_schedule(1) == pytest.approx(1e-4 + (5e-4 - 1e-4) / 200) and bench.lr_schedule(200) == pytest.approx(5e-4)
