@@ -67,6 +67,12 @@ class HardRayPool:
         # appended in steps of n_hard_in until size >= batch_size * hard_mul (main.py:1423-1425)
         step = self.n_hard_in
         slots = -(-int(self.fill_level) // step) * step + step
+        full_size = max(1, -(-self.fill_level // step)) * step           # rays in the pool from the moment it counts as full
+        if self.n_hard_out > full_size:
+            # the reference would silently draw fewer rays than n_hard_out (permutation(len(pool))[:n_hard_out], main.py:1330);
+            # batches of a size that depends on the pool are not supported here
+            raise ValueError(f"HardRayPool: n_hard_out = {self.n_hard_out} exceeds the {int(full_size)} rays a full pool holds "
+                             f"(hard_ratio {hard_ratio}, hard_mul {hard_mul}, batch {batch_size})")
         self.seed = int(seed)
         self.rays = torch.zeros((slots, 9), dtype=torch.float32, device=device)
         self.state = torch.zeros(1, dtype=torch.int32, device=device)            # rays in the pool, advanced by the update kernel

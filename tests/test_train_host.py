@@ -125,6 +125,9 @@ def test_hard_ray_pool_host_mirror_follows_the_reference_fill():
         assert pool.full
     with pytest.raises(ValueError):
         HardRayPool(4, 0.2, 1, torch.device("cpu"))       # int(0.8) == 0 rays: refused (see the class docstring)
+    with pytest.raises(ValueError):
+        HardRayPool(100, [0.1, 0.3], 0.1, torch.device("cpu"))   # a full pool of 10 rays cannot supply 30 per batch
+    assert HardRayPool(100, 0.2, 0.1, torch.device("cpu")).n_hard_out == 20      # full after one append of 20 rays: fine
 
 
 def test_pool_slot_permutation_is_a_bijection_and_varies_with_the_step():
