@@ -285,9 +285,8 @@ def run_reference(args):
 
 def cpu_baseline_leg(reps_cpu=20):
     """The `cpu_baseline` object of our arm's line: the reference arm itself (`bench.py --impl reference`), run in a FRESH
-    process and parsed - so both numbers come from one code path in one environment.  (Measured on the pool's boxes: the same
-    CPU steps would run as fast inside this process; the point is one code path and one thread policy.)  Falls back to the
-    in-process measurement, and says so, if the child cannot be run."""
+    process and parsed - so both numbers come from one code path, one thread policy and one environment (no CUDA context, no
+    helper threads of this process).  Falls back to the in-process measurement, and says so, if the child cannot be run."""
     threads = cpu_threads()
     try:
         env = dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0")
