@@ -182,3 +182,22 @@ def test_split_arithmetic_meets_the_parity_bar_on_the_cpu(golden_r2l, flat_seed0
     sub = grads[g["grad_idx"]]
     err = np.linalg.norm(sub - g["grad_f64_sub"]) / np.linalg.norm(g["grad_f64_sub"])
     assert err < float(g["grad_f32_vs_f64_rel"]) and err < 1e-4, err
+
+
+def test_accumulator_rounding_model_explains_the_forward_error(golden_r2l, flat_seed0):
+    """DESIGN.md section 4 "Precision": with an fp32 accumulator that is rounded toward zero after every K = 16 instruction
+    (what the tensor core does), keeping the residual stream IN the accumulator costs ~6e-5 of relative RGB error - the level
+    both rounds measured on the GPU whatever the operand format - while a fresh accumulator per GEMM with an fp32 residual add
+    stays below 1e-5 (the half form; GPU: 2.4e-6).  64 rays of the golden batch keep this under ten seconds."""
+    from oracle import split_emulation as se
+    g = golden_r2l
+    x, ref = g["x_embed"][:64], g["rgb"][:64]
+    err = lambda rgb: float(np.max(np.abs(rgb.astype(np.float64) - ref) / np.abs(ref)))
+    in_place = err(se.r2l_forward_mma(flat_seed0, x, residual="in_place", order="big_first"))
+    fresh = err(se.r2l_forward_mma(flat_seed0, x, residual="fresh", order="small_first", eps_body=12 / 2 ** 24, eps_head=32 / 2 ** 24))
+    assert 2e-5 < in_place < 2e-4 and fresh < 1e-5 and in_place > 5 * fresh, (in_place, fresh)
+    # the rounding helper itself: toward zero never increases the magnitude and is within one ulp
+    v = np.array([1.0 + 2.0 ** -30, -(1.0 + 2.0 ** -30), 3.0000000001, -1e-30, 0.0])
+    rz = se.round_f32(v)
+    assert np.all(np.abs(rz.astype(np.float64)) <= np.abs(v)) and rz[0] == np.float32(1.0) and rz[1] == np.float32(-1.0)
+    assert np.all(np.abs(rz.astype(np.float64) - v) <= np.spacing(np.abs(rz)).astype(np.float64) + 1e-45)
