@@ -175,3 +175,42 @@ def test_camera_poses_and_rays_match_the_reference(tmp_path):
         assert abs(np.linalg.norm(p[:3, 3]) - 4.0) < 1e-5 and p[2, 3] >= -1e-6
         np.testing.assert_allclose(p[:3, :3] @ p[:3, :3].T, np.eye(3), atol=1e-6)
     assert np.array_equal(pd.get_rand_pose(np.random.RandomState(0)).numpy(), poses[0])
+
+
+def _radix_select_like_pool_cu(err: np.ndarray, k: int):
+    """numpy restatement of r2l_pool_update_kernel's selection (csrc/pool.cu): four 8-bit radix passes from the top digit find
+    the k-th largest key (keys = the float bits; -0.0 folded onto +0.0), then the rays above it in index order followed by
+    the lowest-index rays equal to it."""
+    keys = err.astype(np.float32).view(np.uint32).copy()
+    keys[keys == 0x80000000] = 0
+    prefix, mask, remaining = 0, 0, k
+    for p in (3, 2, 1, 0):
+        shift = 8 * p
+        hist = np.bincount(((keys[(keys & mask) == prefix] >> shift) & 255).astype(np.int64), minlength=256)
+        b = 255
+        while b > 0 and hist[b] < remaining:
+            remaining -= hist[b]
+            b -= 1
+        prefix |= b << shift
+        mask |= 255 << shift
+    above = np.nonzero(keys > prefix)[0]
+    equal = np.nonzero(keys == prefix)[0][:remaining]
+    assert len(above) == k - remaining
+    return np.concatenate([above, equal])
+
+
+def test_pool_selection_algorithm_equals_the_reference_sort():
+    """The selection rule of the pool update (radix select on the float bits) picks what main.py:1411-1414 picks -
+    torch.sort(err).indices[-n_hard_in:] - on distinct errors, and a valid top-k (lowest index first among equals) on ties;
+    the CUDA implementation of the same steps is checked on the GPU (tests/test_gpu_train.py)."""
+    rng = np.random.RandomState(0)
+    for n, k in ((40, 8), (640, 128), (4096, 819), (5000, 1), (1030, 1030)):
+        err = (rng.permutation(n).astype(np.float32) / 7.0) ** 2
+        got = _radix_select_like_pool_cu(err, k)
+        assert sorted(got.tolist()) == sorted(np.argsort(err, kind="stable")[-k:].tolist())
+    err = np.array([0.5, 0.25, 0.5, -0.0, 0.5, np.nan, 0.0, 0.5, 0.125], np.float32)
+    assert _radix_select_like_pool_cu(err, 3).tolist() == [5, 0, 2] and _radix_select_like_pool_cu(err, 8).tolist() == [0, 1, 2, 4, 5, 7, 8, 3]
+    err = rng.randint(0, 5, 1000).astype(np.float32)
+    for k in (1, 10, 500, 999, 1000):
+        got = _radix_select_like_pool_cu(err, k)
+        assert len(set(got.tolist())) == k and err[got].min() >= np.sort(err)[-k]
